@@ -1,0 +1,373 @@
+"""bench.py -- Gaussians/sec (fwd+bwd) of the rasterization hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n-gauss 2000000]
+                    [--width 1920 --height 1080] [--variant rgbed|mtgs]
+
+One "step" = one pass of the hot path over one synthetic camera view: rasterization forward (projection ->
+binning/sort -> blend) + backward to every Gaussian attribute, fixed random cotangents
+(loss = <render, w_c> + <alpha, w_a>).  Workload at N=1: the configuration the metric is quoted
+on ("@1920x1080, 2M splats"): BASELINE config 2's street slab scaled to 2 M Gaussians; `--n-gauss 500000`
+gives config 2 itself.  N>1 (torchrun, one rank per GPU): every rank renders its own traversal camera over
+the replicated Gaussians and the shared-node gradients are sum-all-reduced over NCCL (weak scaling).
+
+Prints ONE JSON line on rank 0 (contract in the task prompt): value = whole-job Gaussians/s with inputs
+resident in HBM; e2e = same through the public API from pinned HOST buffers (H2D + step + D2H inside the
+timed region); roofline = dominant kernel's achieved algorithmic HBM GB/s vs MEASURED_PEAKS.json;
+cpu_baseline = the CPU oracle port timed on this box's host cores on a bounded sample.
+`--impl reference` times the CPU port (the reference's own CPU-capable restatement; gsplat is not installable)
+as the reference arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "Gaussians/sec fwd+bwd @1920x1080, 2M splats"
+UNIT = "Gaussians/s"
+
+
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes(N, N_vis, M, P, d_in, cdim, absgrad):
+    """SURVEY.md 8d byte model (fp32, C = 1).  Returns per-stage and total algorithmic bytes."""
+    A = 1 if absgrad else 0
+    b = {}
+    b["project_fwd"] = N * (44 + 4 * d_in) + N * 32
+    b["bin"] = M * 16
+    b["blend_fwd"] = N_vis * (24 + 4 * cdim) + M * 4 + P * (4 * cdim + 8)
+    b["blend_bwd"] = P * (4 * cdim + 12) + M * 4 + N_vis * (24 + 4 * cdim) + N_vis * (24 + 4 * cdim + 8 * A)
+    b["project_bwd"] = N_vis * 24 + N * 76 + N * (44 + 4 * d_in)
+    b["total"] = sum(b.values())
+    return b
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        try:
+            rows = [l.strip().split(",") for l in open(self.path) if l.strip()]
+            sm = [float(r[0]) for r in rows if len(r) >= 7]
+            if sm:
+                out["sm_mhz"] = float(np.median(sm))
+                out["sm_max_mhz"] = float(rows[0][1])
+                out["samples"] = len(sm)
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for i, n in enumerate(names):
+                    if any("Active" in r[3 + i] and "Not" not in r[3 + i] for r in rows if len(r) >= 7):
+                        out["reasons"].append(n)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+def variant_cfg(name):
+    if name == "rgbed":  # BASELINE config 2, CDIM 4 variant (3DGS config of MTGS + absgrad/antialiased)
+        return dict(d_in=3, render_mode="RGB+ED", rasterize_mode="antialiased", absgrad=True)
+    if name == "mtgs":  # paper config: RGB + normals + ED -> CDIM 8 (mtgs/config/MTGS.py:101-111)
+        return dict(d_in=6, render_mode="RGB+ED", rasterize_mode="antialiased", absgrad=True)
+    raise SystemExit(f"unknown variant {name}")
+
+
+def run_cpu_port(args, scene, vcfg, sample_n, steps, warmup):
+    """Times the CPU oracle port (fwd+bwd) on `sample_n` Gaussians of the same scene; returns Gaussians/s."""
+    from oracle import cpu_ref
+    cpu_ref.build()
+    rng = np.random.default_rng(123)
+    idx = np.sort(rng.choice(scene["means"].shape[0], size=sample_n, replace=False)) if sample_n < scene["means"].shape[0] \
+        else np.arange(scene["means"].shape[0])
+    sub = {k: scene[k][idx] for k in ("means", "quats", "scales", "opacities", "colors")}
+    W, H = scene["width"], scene["height"]
+    d_out = vcfg["d_in"] + 1
+    v_r = rng.standard_normal((H, W, d_out)).astype(np.float32)
+    v_a = rng.standard_normal((H, W, 1)).astype(np.float32)
+
+    def step():
+        rc, ra, meta, ctx = cpu_ref.rasterization(sub["means"], sub["quats"], sub["scales"], sub["opacities"],
+                                                  sub["colors"], scene["viewmat"], scene["K"], W, H,
+                                                  render_mode=vcfg["render_mode"], rasterize_mode=vcfg["rasterize_mode"])
+        ctx["meta_offs"], ctx["meta_flat"] = meta["isect_offsets"], meta["flatten_ids"]
+        cpu_ref.rasterization_bwd(ctx, v_r, v_a, absgrad=vcfg["absgrad"])
+        return meta
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(1, steps)
+    return sample_n / dt, dt, cpu_ref.num_threads()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-gauss", type=int, default=2_000_000)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--variant", default="rgbed")
+    ap.add_argument("--cpu-sample", type=int, default=100_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    vcfg = variant_cfg(args.variant)
+    workload = (f"street-slab synthetic (BASELINE config 2 distribution) N={args.n_gauss} {args.width}x{args.height} "
+                f"{vcfg['render_mode']} {vcfg['rasterize_mode']} absgrad d_in={vcfg['d_in']}")
+    config = {"workload": workload, "n_gaussians": args.n_gauss, "width": args.width, "height": args.height,
+              "variant": args.variant, "cameras_per_rank": 1,
+              "parallelism": f"traversal-per-gpu x{world}" if world > 1 else "single-gpu",
+              "l2_policy": "per-step working set (>1 GB) exceeds the 126 MB L2; no explicit flush"}
+
+    from mtgs_b200 import scenes
+
+    # ---------------------------------------------------------------- reference arm (CPU port)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        scene = scenes.street(n=args.n_gauss, seed=1, width=args.width, height=args.height, d_in=vcfg["d_in"])
+        sample_n = min(args.n_gauss, args.cpu_sample)
+        steps = max(1, min(args.steps, 3))
+        val, dt, cores = run_cpu_port(args, scene, vcfg, sample_n, steps, 1)
+        line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": 1,
+                "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config, "impl": "reference",
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": f"{sample_n} of {args.n_gauss} Gaussians (uniform subsample), full "
+                                           f"{args.width}x{args.height} image, fwd+bwd, OpenMP oracle port; gsplat "
+                                           f"(the reference's implementation) is not installable offline"},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ---------------------------------------------------------------- our arm
+    import torch
+    from mtgs_b200 import _lib
+    from mtgs_b200 import rendering
+    from mtgs_b200.rendering import rasterization
+    from mtgs_b200.parallel import SharedGradArena
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback in the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    scene = scenes.street(n=args.n_gauss, seed=1, width=args.width, height=args.height, d_in=vcfg["d_in"], camera=rank)
+    N, W, H = args.n_gauss, args.width, args.height
+    d_out = vcfg["d_in"] + 1
+    names = ("means", "quats", "scales", "opacities", "colors")
+    host = {k: torch.from_numpy(scene[k]).pin_memory() for k in names}
+    params = {k: host[k].to(dev).requires_grad_(True) for k in names}
+    viewmat = torch.from_numpy(scene["viewmat"]).to(dev)[None]
+    Ks = torch.from_numpy(scene["K"]).to(dev)[None]
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    w_c = torch.randn(1, H, W, d_out, device=dev, generator=gen)
+    w_a = torch.randn(1, H, W, 1, device=dev, generator=gen)
+    arena = SharedGradArena([params[k] for k in names], average=True) if world > 1 else None
+
+    def step(p):
+        r, a, meta = rasterization(p["means"], p["quats"], p["scales"], p["opacities"], p["colors"], viewmat, Ks, W, H,
+                                   packed=False, render_mode=vcfg["render_mode"], rasterize_mode=vcfg["rasterize_mode"],
+                                   absgrad=vcfg["absgrad"])
+        loss = (r * w_c).sum() + (a * w_a).sum()
+        if arena is not None:
+            arena.zero_()
+        else:
+            for t in p.values():
+                t.grad = None
+        loss.backward()
+        if arena is not None:
+            arena.all_reduce()
+        return loss, meta
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        loss, meta = step(params)
+    barrier()
+    N_vis = int((meta["radii"] > 0).sum())
+    M = int(meta["flatten_ids"].numel())
+
+    # ---- timed region 1: inputs resident in HBM
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    rendering.PROFILE = {}
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss, meta = step(params)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    prof = rendering.PROFILE
+    rendering.PROFILE = None
+    stage_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in prof.items()}
+    t_ms = torch.tensor([ms], device=dev)
+    if dist is not None:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t_ms.item()) / args.steps
+    value = N * world / (ms_per_step * 1e-3)
+
+    # ---- timed region 2: end to end from pinned host buffers through the public API
+    e2e_steps = max(3, args.steps // 2)
+
+    def e2e_step():
+        p = {k: host[k].to(dev, non_blocking=True).requires_grad_(True) for k in names}
+        l, _ = step(p) if arena is None else step_e2e_multi(p)
+        gn = p["means"].grad.norm()
+        return torch.stack([l.detach(), gn]).cpu()  # D2H read of the step's result (8 bytes), synchronises
+
+    def step_e2e_multi(p):
+        # multi-GPU: fresh leaf tensors each step -> all-reduce their gradients after backward
+        r, a, m = rasterization(p["means"], p["quats"], p["scales"], p["opacities"], p["colors"], viewmat, Ks, W, H,
+                                packed=False, render_mode=vcfg["render_mode"], rasterize_mode=vcfg["rasterize_mode"],
+                                absgrad=vcfg["absgrad"])
+        l = (r * w_c).sum() + (a * w_a).sum()
+        l.backward()
+        flat = torch.cat([p[k].grad.reshape(-1) for k in names])
+        dist.all_reduce(flat)
+        return l, m
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    t2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if dist is not None:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t2.item()) / e2e_steps
+    h2d = sum(host[k].numel() * 4 for k in names)
+    e2e = {"value": N * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+           "ms_per_step": e2e_ms, "steps": e2e_steps}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (largest mean duration among the library's stages)
+    peak, peak_src = measured_peaks()
+    ab = algorithmic_bytes(N, N_vis, M, W * H, vcfg["d_in"], 4 if d_out <= 4 else 8, vcfg["absgrad"])
+    stage_bytes = {"project_fwd": ab["project_fwd"], "bin_sort_depth": N * 8 * 8, "bin_tiles": ab["bin"],
+                   "blend_fwd": ab["blend_fwd"], "blend_bwd": ab["blend_bwd"], "project_bwd": ab["project_bwd"]}
+    dom = max(stage_ms, key=stage_ms.get) if stage_ms else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if dom and os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(dom)
+        except Exception:
+            traffic = None
+    roofline = None
+    if dom:
+        ach = stage_bytes[dom] / (stage_ms[dom] * 1e-3) / 1e9
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": stage_bytes[dom],
+                    "kernel_ms": stage_ms[dom],
+                    "note": "blend kernels are FP32-ALU/MUFU/shuffle bound (SURVEY 8d): HBM fraction is small by "
+                            "construction; whole-step HBM fraction in roofline_step"}
+    step_frac = ab["total"] / (ms_per_step * 1e-3) / 1e9 / peak
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        try:
+            sample_n = min(N, args.cpu_sample)
+            v, dt, cores = run_cpu_port(args, scenes.street(n=N, seed=1, width=W, height=H, d_in=vcfg["d_in"]), vcfg,
+                                        sample_n, 1, 1)
+            cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": f"{sample_n} of {N} Gaussians (uniform subsample), full {W}x{H} image, fwd+bwd, "
+                                      f"{dt:.2f} s per step"}
+        except Exception as e:  # pragma: no cover
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "impl": "ours",
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "roofline_step": {"algorithmic_bytes": ab["total"], "frac_of_hbm_peak": step_frac,
+                              "bytes_per_gaussian": ab["total"] / N},
+            "cpu_baseline": cpu_baseline,
+            "stats": {"N_vis": N_vis, "M": M, "stage_ms": stage_ms,
+                      "loss": float(loss.item()) if math.isfinite(float(loss.item())) else None}}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

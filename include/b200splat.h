@@ -1,0 +1,119 @@
+/*
+ * b200splat.h -- flat C ABI of libb200splat.so (hand-written sm_100a CUDA kernels).
+ *
+ * Drop-in boundary for the one hot path MTGS delegates to gsplat v1.4.0
+ * (SURVEY.md section 8b).  Each entry point replaces an upstream operator that
+ * MTGS reaches through
+ *     gsplat.rendering.rasterization      mtgs/scene_model/mtgs_scene_graph.py:21, 641-662
+ *     gsplat.cuda._wrapper.spherical_harmonics
+ *                                         mtgs/scene_model/gaussian_model/vanilla_gaussian_splatting.py:16, 317
+ *                                         (same call: multi_color_gaussian_splatting.py:96,
+ *                                          rigid_node.py:248, deformable_node.py:125)
+ * The reference-side binding is Python (ctypes); see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - row-major contiguous fp32 / int32 / int64 buffers, one camera (C = 1);
+ *   - quaternions (w,x,y,z); viewmat = world->camera 4x4 (OpenCV axes); K = 3x3;
+ *   - the library never allocates, frees or synchronises: all buffers and the
+ *     scratch workspace are caller-owned; work is enqueued on `stream`;
+ *   - return value: 0 on success, B2S_ERR_* (< 0) on argument errors,
+ *     -(int)cudaError_t - 1000 on a CUDA launch error; b2s_error_string() names it;
+ *   - thread-compatible: no mutable globals; one in-flight call per stream.
+ */
+#ifndef B200SPLAT_H
+#define B200SPLAT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *b2s_stream_t; /* cudaStream_t */
+
+#define B2S_OK 0
+#define B2S_ERR_ARG (-1)         /* bad size / null pointer */
+#define B2S_ERR_UNSUPPORTED (-2) /* channel count / tile size / degree not built */
+#define B2S_ERR_WORKSPACE (-3)   /* workspace too small */
+
+int b2s_version(void);
+const char *b2s_error_string(int code);
+/* number of kernels launched by this library since load (bench.py "gpu_launches") */
+long long b2s_launch_count(void);
+
+/* ---- projection + EWA covariance (upstream fully_fused_projection fwd; SURVEY A.1, A.2 pass 1) ----
+ * Also emits, per Gaussian: the tile count of upstream isect_tiles pass 1, the depth sort key
+ * (float bits of depth, 0xFFFFFFFF when culled), the packed blend record
+ *   geo[g]     = (conic a, conic b, conic c, opacity * compensation)
+ *   colpack[g] = (colors_in[0..d_in), depth if with_depth, zero pad) , cdim floats
+ * comps may be NULL when calc_comp == 0.  colors_in is [N, d_in]. */
+int b2s_project_fwd(const float *means, const float *quats, const float *scales,
+                    const float *opacities, const float *colors_in, const float *viewmat,
+                    const float *K, int N, int W, int H, int tile_size, int tile_w, int tile_h,
+                    float eps2d, float near_plane, float far_plane, float radius_clip,
+                    int calc_comp, int d_in, int with_depth, int cdim, int32_t *radii,
+                    float *means2d, float *depths, float *geo, float *comps, float *colpack,
+                    int32_t *tiles_per_gauss, uint32_t *sort_keys, uint32_t *sort_vals,
+                    b2s_stream_t stream);
+
+/* upstream fully_fused_projection bwd fused with the opacity*compensation and
+ * colour/depth un-packing VJPs.  v_means2d[g * v_means2d_stride + {0,1}] (stride 2, or 4 when it aliases
+ * the blend's (xy, |xy|) arena), v_geo[g] = (v_conic a,b,c, v_opacity_eff), v_colpack[g][cdim].
+ * v_viewmat (16 floats, pre-zeroed) may be NULL. */
+int b2s_project_bwd(const float *means, const float *quats, const float *scales,
+                    const float *opacities, const float *viewmat, const float *K, int N, int W,
+                    int H, float eps2d, int calc_comp, int d_in, int with_depth, int cdim,
+                    const int32_t *radii, const float *geo, const float *comps,
+                    const float *v_means2d, int v_means2d_stride, const float *v_geo,
+                    const float *v_colpack,
+                    float *v_means, float *v_quats, float *v_scales, float *v_opacities,
+                    float *v_viewmat, b2s_stream_t stream);
+
+/* ---- tile binning + depth sort (upstream isect_tiles + radix sort + isect_offset_encode; A.2) ----
+ * Two-level formulation with identical results to the stable 64-bit sort:
+ *   (1) b2s_bin_sort_depth : stable sort of Gaussians by depth key -> order[N];
+ *       cum[i] = exclusive scan of tiles_per_gauss[order[i]];  *total (device int64) = M.
+ *   (2) b2s_bin_tiles      : emit (tile, gaussian) in depth order, stable sort by tile ->
+ *       flatten_ids[M], tile_keys[M] (sorted tile id per entry), isect_offsets[tile_h*tile_w].
+ *   (3) b2s_bin_isect_ids  : optional, rebuilds upstream's int64 isect_ids for inspection. */
+size_t b2s_bin_depth_workspace_bytes(int N);
+int b2s_bin_sort_depth(const uint32_t *sort_keys, const uint32_t *sort_vals,
+                       const int32_t *tiles_per_gauss, int N, int32_t *order, int32_t *cum,
+                       int64_t *total, void *workspace, size_t workspace_bytes,
+                       b2s_stream_t stream);
+size_t b2s_bin_tiles_workspace_bytes(int N, long long M);
+int b2s_bin_tiles(const float *means2d, const int32_t *radii, const int32_t *order,
+                  const int32_t *cum, int N, long long M, int tile_size, int tile_w, int tile_h,
+                  int32_t *flatten_ids, uint32_t *tile_keys, int32_t *isect_offsets,
+                  void *workspace, size_t workspace_bytes, b2s_stream_t stream);
+int b2s_bin_isect_ids(const uint32_t *tile_keys, const int32_t *flatten_ids, const float *depths,
+                      long long M, int64_t *isect_ids, b2s_stream_t stream);
+
+/* ---- alpha blending (upstream rasterize_to_pixels fwd / bwd; A.3, A.4) ----
+ * cdim in {4, 8}; d_out = channels written per pixel (<= cdim); expected_depth != 0 divides channel
+ * d_out-1 by max(alpha, 1e-10) in the epilogue (upstream does that in torch).  16x16 tiles only. */
+int b2s_blend_fwd(const float *means2d, const float *geo, const float *colpack,
+                  const int32_t *isect_offsets, const int32_t *flatten_ids, long long M, int W,
+                  int H, int tile_w, int tile_h, int cdim, int d_out, int expected_depth,
+                  float *render, float *alpha, int32_t *last_ids, b2s_stream_t stream);
+int b2s_blend_bwd(const float *means2d, const float *geo, const float *colpack,
+                  const int32_t *isect_offsets, const int32_t *flatten_ids, long long M, int W,
+                  int H, int tile_w, int tile_h, int cdim, int d_out, int expected_depth,
+                  const float *render, const float *alpha, const int32_t *last_ids,
+                  const float *v_render, const float *v_alpha, float *v_xyabs, float *v_geo,
+                  float *v_colpack, b2s_stream_t stream);
+
+/* ---- spherical harmonics (upstream compute_sh fwd / bwd; A.6) ----
+ * dirs [N,3], coeffs [N,K,3], masks (uint8, may be NULL), degree in 0..4 with (degree+1)^2 <= K. */
+int b2s_sh_fwd(int degree, const float *dirs, const float *coeffs, const uint8_t *masks, int N,
+               int K, float *colors, b2s_stream_t stream);
+int b2s_sh_bwd(int degree, const float *dirs, const float *coeffs, const uint8_t *masks, int N,
+               int K, const float *v_colors, float *v_coeffs, float *v_dirs /* may be NULL */,
+               b2s_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SPLAT_H */

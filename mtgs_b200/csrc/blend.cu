@@ -1,0 +1,529 @@
+// Front-to-back alpha blending of depth-sorted tile lists, forward and backward (sm_100a).
+//
+// Replaces upstream gsplat v1.4.0 rasterize_to_pixels_{fwd,bwd}_kernel (kernels K8/K9)
+// as reached from mtgs/scene_model/mtgs_scene_graph.py:641-662, plus the torch glue upstream runs around
+// them: the expected-depth division render[..., -1] / alpha.clamp(1e-10) and its VJP.
+//
+// These kernels are FP32-ALU / MUFU.EX2 / shuffle bound, not HBM bound: no tensor cores.
+// Blackwell-first choices:
+//   * one CTA of 128 threads per 16x16 tile, TWO pixels per thread (same column, adjacent rows): the staged
+//     Gaussian record is read from shared memory once per two pixel-pairs and the per-(warp,Gaussian) gradient
+//     reduction in the backward covers 64 pixels instead of 32;
+//   * exact per-tile culling while staging: a (Gaussian, tile) pair whose minimum exponent over the tile's
+//     pixel centres already gives alpha < 1/255 contributes to no pixel, so it is dropped from the staged batch
+//     (ballot compaction).  The isect lists stay bit-identical to upstream; only dead work disappears;
+//   * exponent evaluated in log2 units (log2e folded into the conic while staging) -> one ex2.approx per pair;
+//   * backward: the 16 per-Gaussian partial sums (xy, |xy|, conic, opacity, <=8 colour channels) are reduced
+//     with a transposing butterfly (16 shuffles instead of 16 x 5), parked per warp in shared memory, summed
+//     over the CTA's four warps and flushed with 16-byte vector reductions (red.global.add.v4.f32): at most
+//     2 + CDIM/4 L2 atomic operations per (tile, Gaussian) instead of upstream's (9 + CDIM) per (warp, Gaussian).
+#include "common.cuh"
+
+constexpr int BL_THREADS = 128;
+constexpr int BL_WARPS = BL_THREADS / 32;
+constexpr int BL_BATCH = BL_THREADS;
+
+// exponent in log2 units: s = A dx^2 + B dx dy + C dy^2 with A = a/2*log2e, B = b*log2e, C = c/2*log2e.
+// Written with explicit roundings so that forward and backward evaluate identical bits.
+__device__ __forceinline__ float splat_power(float A, float B, float C, float dx, float dy) {
+    float u = fmaf(B, dy, __fmul_rn(A, dx));
+    return fmaf(__fmul_rn(C, dy), dy, __fmul_rn(u, dx));
+}
+
+// Can this Gaussian reach alpha >= 1/255 at any pixel centre of the rectangle [rx0,rx1]x[ry0,ry1]?
+// Conservative (never drops a contributing pair): exact box-constrained minimum of the convex quadratic,
+// compared with log2(255 * opacity) plus a slack that dominates fp32 evaluation error.
+__device__ __forceinline__ bool tile_keep(float mx, float my, float A, float B, float C, float opac, float rx0,
+                                          float ry0, float rx1, float ry1) {
+    if (!(opac >= 0.0039f)) return false;  // opac * e^-sigma <= opac < 1/255 (also drops NaN)
+    float ex = fminf(fmaxf(mx, rx0), rx1) - mx;  // nearest pixel-centre coordinate minus mean (0 if inside)
+    float ey = fminf(fmaxf(my, ry0), ry1) - my;
+    if (ex == 0.f && ey == 0.f) return true;
+    float tau = __log2f(opac * 255.0f);
+    float smin = 3.0e38f, mag = 0.f;
+    if (ex != 0.f) {  // facing vertical edge: dx fixed, minimise over dy
+        float dy = fminf(fmaxf(-B * ex / (2.f * C), ry0 - my), ry1 - my);
+        float t0 = A * ex * ex, t1 = B * ex * dy, t2 = C * dy * dy;
+        float s = t0 + t1 + t2;
+        if (s < smin) { smin = s; mag = fabsf(t0) + fabsf(t1) + fabsf(t2); }
+    }
+    if (ey != 0.f) {  // facing horizontal edge
+        float dx = fminf(fmaxf(-B * ey / (2.f * A), rx0 - mx), rx1 - mx);
+        float t0 = A * dx * dx, t1 = B * dx * ey, t2 = C * ey * ey;
+        float s = t0 + t1 + t2;
+        if (s < smin) { smin = s; mag = fabsf(t0) + fabsf(t1) + fabsf(t2); }
+    }
+    return !(smin > tau + 0.02f + 2e-5f * mag);  // NaN-safe: keep on NaN
+}
+
+struct TileGeom {
+    int x, y0;               // this thread's pixel column and first row (second row is y0 + 1)
+    bool in0, in1;
+    float px, py0, py1;
+    float rx0, ry0, rx1, ry1;  // pixel-centre rectangle of the tile clipped to the image
+    int start, end;
+};
+
+__device__ __forceinline__ TileGeom tile_geom(int tile_w, int tile_h, int W, int H, long long M,
+                                              const int32_t *__restrict__ offsets) {
+    TileGeom g;
+    const int tile = blockIdx.x;
+    const int ti = tile / tile_w, tj = tile - ti * tile_w;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    g.x = tj * 16 + (lane & 15);
+    g.y0 = ti * 16 + 4 * warp + 2 * (lane >> 4);
+    g.in0 = g.x < W && g.y0 < H;
+    g.in1 = g.x < W && (g.y0 + 1) < H;
+    g.px = (float)g.x + 0.5f;
+    g.py0 = (float)g.y0 + 0.5f;
+    g.py1 = g.py0 + 1.0f;
+    g.rx0 = (float)(tj * 16) + 0.5f;
+    g.ry0 = (float)(ti * 16) + 0.5f;
+    g.rx1 = (float)min(tj * 16 + 16, W) - 0.5f;
+    g.ry1 = (float)min(ti * 16 + 16, H) - 0.5f;
+    g.start = offsets[tile];
+    g.end = (tile == tile_w * tile_h - 1) ? (int)M : offsets[tile + 1];
+    return g;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+template <int CDIM, int DOUT, bool ED>
+__global__ void __launch_bounds__(BL_THREADS)
+k_blend_fwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, const float4 *__restrict__ colpack,
+            const int32_t *__restrict__ offsets, const int32_t *__restrict__ flatten_ids, long long M, int W, int H,
+            int tile_w, int tile_h, float *__restrict__ render, float *__restrict__ alpha_out,
+            int32_t *__restrict__ last_ids) {
+    constexpr int CQ = CDIM / 4;
+    __shared__ float4 s_q[BL_BATCH];        // mx, my, A, B
+    __shared__ float2 s_c[BL_BATCH];        // C, opacity
+    __shared__ int s_idx[BL_BATCH];         // index into the sorted list
+    __shared__ float4 s_col[BL_BATCH][CQ];
+    __shared__ int s_wcnt[BL_WARPS];
+
+    const TileGeom tg = tile_geom(tile_w, tile_h, W, H, M, offsets);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lt = lanemask_lt();
+
+    float T0 = 1.f, T1 = 1.f;
+    float acc0[CDIM], acc1[CDIM];
+#pragma unroll
+    for (int k = 0; k < CDIM; ++k) acc0[k] = acc1[k] = 0.f;
+    int cur0 = 0, cur1 = 0;
+    bool done0 = !tg.in0, done1 = !tg.in1;
+
+    for (int base = tg.start; base < tg.end; base += BL_BATCH) {
+        if (__syncthreads_and(done0 && done1)) break;
+        const int idx = base + threadIdx.x;
+        bool keep = false;
+        int g = 0;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        float2 c = make_float2(0.f, 0.f);
+        if (idx < tg.end) {
+            g = flatten_ids[idx];
+            const float2 m = means2d[g];
+            const float4 ge = geo[g];
+            q = make_float4(m.x, m.y, 0.5f * B2S_LOG2E * ge.x, B2S_LOG2E * ge.y);
+            c = make_float2(0.5f * B2S_LOG2E * ge.z, ge.w);
+            keep = tile_keep(m.x, m.y, q.z, q.w, c.x, c.y, tg.rx0, tg.ry0, tg.rx1, tg.ry1);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_wcnt[warp] = __popc(bal);
+        __syncthreads();
+        int off = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < BL_WARPS; ++w) {
+            int n = s_wcnt[w];
+            off += (w < warp) ? n : 0;
+            total += n;
+        }
+        if (keep) {
+            const int slot = off + __popc(bal & lt);
+            s_q[slot] = q;
+            s_c[slot] = c;
+            s_idx[slot] = idx;
+#pragma unroll
+            for (int k = 0; k < CQ; ++k) s_col[slot][k] = colpack[(size_t)g * CQ + k];
+        }
+        __syncthreads();
+
+#pragma unroll 2
+        for (int t = 0; t < total; ++t) {
+            const float4 sq = s_q[t];
+            const float2 sc = s_c[t];
+            const float dx = sq.x - tg.px;
+            const float dy0 = sq.y - tg.py0, dy1 = sq.y - tg.py1;
+            const float p0 = splat_power(sq.z, sq.w, sc.x, dx, dy0);
+            const float p1 = splat_power(sq.z, sq.w, sc.x, dx, dy1);
+            const float a0 = fminf(B2S_ALPHA_MAX, __fmul_rn(sc.y, ex2_approx(-p0)));
+            const float a1 = fminf(B2S_ALPHA_MAX, __fmul_rn(sc.y, ex2_approx(-p1)));
+            const bool ok0 = !done0 && p0 >= 0.f && a0 >= B2S_ALPHA_MIN;
+            const bool ok1 = !done1 && p1 >= 0.f && a1 >= B2S_ALPHA_MIN;
+            if (ok0 || ok1) {
+                float col[CDIM];
+#pragma unroll
+                for (int k = 0; k < CQ; ++k) {
+                    const float4 v = s_col[t][k];
+                    col[4 * k] = v.x; col[4 * k + 1] = v.y; col[4 * k + 2] = v.z; col[4 * k + 3] = v.w;
+                }
+                const int id = s_idx[t];
+                if (ok0) {
+                    const float nT = __fmul_rn(T0, __fsub_rn(1.0f, a0));
+                    if (nT <= B2S_T_EPS) {
+                        done0 = true;
+                    } else {
+                        const float vis = __fmul_rn(a0, T0);
+#pragma unroll
+                        for (int k = 0; k < CDIM; ++k) acc0[k] = fmaf(col[k], vis, acc0[k]);
+                        cur0 = id;
+                        T0 = nT;
+                    }
+                }
+                if (ok1) {
+                    const float nT = __fmul_rn(T1, __fsub_rn(1.0f, a1));
+                    if (nT <= B2S_T_EPS) {
+                        done1 = true;
+                    } else {
+                        const float vis = __fmul_rn(a1, T1);
+#pragma unroll
+                        for (int k = 0; k < CDIM; ++k) acc1[k] = fmaf(col[k], vis, acc1[k]);
+                        cur1 = id;
+                        T1 = nT;
+                    }
+                }
+            }
+        }
+    }
+
+    // epilogue: optional expected-depth normalisation of the last written channel
+    if (tg.in0) {
+        const size_t pid = (size_t)tg.y0 * W + tg.x;
+        const float al = 1.0f - T0;
+        if (ED) acc0[DOUT - 1] = acc0[DOUT - 1] / fmaxf(al, 1e-10f);
+        alpha_out[pid] = al;
+        last_ids[pid] = cur0;
+        if (DOUT == 4) {
+            reinterpret_cast<float4 *>(render)[pid] = make_float4(acc0[0], acc0[1], acc0[2], acc0[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < DOUT; ++k) render[pid * DOUT + k] = acc0[k];
+        }
+    }
+    if (tg.in1) {
+        const size_t pid = (size_t)(tg.y0 + 1) * W + tg.x;
+        const float al = 1.0f - T1;
+        if (ED) acc1[DOUT - 1] = acc1[DOUT - 1] / fmaxf(al, 1e-10f);
+        alpha_out[pid] = al;
+        last_ids[pid] = cur1;
+        if (DOUT == 4) {
+            reinterpret_cast<float4 *>(render)[pid] = make_float4(acc1[0], acc1[1], acc1[2], acc1[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < DOUT; ++k) render[pid * DOUT + k] = acc1[k];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+// Per-pixel gradient contribution of one Gaussian (upstream rasterize_to_pixels_bwd inner body).
+// v[0..1] = v_mean2d, v[2..3] = |v_mean2d|, v[4..6] = v_conic (a,b,c), v[7] = v_opacity, v[8..] = v_colour.
+template <int CDIM>
+__device__ __forceinline__ void pixel_grad(float (&v)[16], float &T, float (&buf)[CDIM], const float (&vrc)[CDIM],
+                                           const float vra, const float Tf, const float (&col)[CDIM], const float A,
+                                           const float B, const float C, const float opac, const float dx,
+                                           const float dy, const float alpha, const float vis) {
+    const float ra = 1.0f / (1.0f - alpha);
+    T *= ra;
+    const float fac = alpha * T;
+    float v_alpha = 0.f;
+#pragma unroll
+    for (int k = 0; k < CDIM; ++k) {
+        v[8 + k] = fmaf(fac, vrc[k], v[8 + k]);
+        v_alpha = fmaf(fmaf(col[k], T, -buf[k] * ra), vrc[k], v_alpha);
+    }
+    v_alpha = fmaf(Tf * ra, vra, v_alpha);
+    if (opac * vis <= B2S_ALPHA_MAX) {
+        const float v_sigma = -opac * vis * v_alpha;
+        v[4] = fmaf(0.5f * v_sigma * dx, dx, v[4]);
+        v[5] = fmaf(v_sigma * dx, dy, v[5]);
+        v[6] = fmaf(0.5f * v_sigma * dy, dy, v[6]);
+        const float vs = v_sigma * B2S_LN2;  // conic_raw = (2A, B, 2C) * ln2
+        const float vx = vs * fmaf(2.f * A, dx, B * dy);
+        const float vy = vs * fmaf(B, dx, 2.f * C * dy);
+        v[0] += vx;
+        v[1] += vy;
+        v[2] += fabsf(vx);
+        v[3] += fabsf(vy);
+        v[7] = fmaf(vis, v_alpha, v[7]);
+    }
+#pragma unroll
+    for (int k = 0; k < CDIM; ++k) buf[k] = fmaf(col[k], fac, buf[k]);
+}
+
+// Transposing butterfly: 16 values per lane -> value k summed over the warp lands in lane 2k (and 2k+1).
+__device__ __forceinline__ float warp_reduce16_transposed(float (&v)[16], const int lane) {
+    bool hi = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float send = hi ? v[i] : v[i + 8];
+        const float keep = hi ? v[i + 8] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    hi = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = hi ? v[i] : v[i + 4];
+        const float keep = hi ? v[i + 4] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    hi = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = hi ? v[i] : v[i + 2];
+        const float keep = hi ? v[i + 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    hi = lane & 2;
+    {
+        const float send = hi ? v[0] : v[1];
+        const float keep = hi ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+    return v[0];
+}
+
+template <int CDIM, int DOUT, bool ED>
+__device__ __forceinline__ void load_pixel_cotangent(size_t pid, const float *__restrict__ render,
+                                                     const float *__restrict__ alpha_in,
+                                                     const float *__restrict__ v_render,
+                                                     const float *__restrict__ v_alpha, float (&vrc)[CDIM],
+                                                     float &vra, float &Tf) {
+    const float al = alpha_in[pid];
+    Tf = 1.0f - al;
+#pragma unroll
+    for (int k = 0; k < CDIM; ++k) vrc[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < DOUT; ++k) vrc[k] = v_render[pid * DOUT + k];
+    vra = v_alpha[pid];
+    if (ED) {
+        // out_d = acc_d / max(alpha, 1e-10): v_acc_d = v_out_d / a ; v_alpha -= v_out_d * out_d / a (alpha >= 1e-10)
+        const float a = fmaxf(al, 1e-10f);
+        const float vd = vrc[DOUT - 1];
+        const float outd = render[pid * DOUT + DOUT - 1];
+        vrc[DOUT - 1] = vd / a;
+        if (al >= 1e-10f) vra -= vd * outd / a;
+    }
+}
+
+template <int CDIM, int DOUT, bool ED>
+__global__ void __launch_bounds__(BL_THREADS)
+k_blend_bwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, const float4 *__restrict__ colpack,
+            const int32_t *__restrict__ offsets, const int32_t *__restrict__ flatten_ids, long long M, int W, int H,
+            int tile_w, int tile_h, const float *__restrict__ render, const float *__restrict__ alpha_in,
+            const int32_t *__restrict__ last_ids, const float *__restrict__ v_render,
+            const float *__restrict__ v_alpha, float *__restrict__ v_xyabs, float *__restrict__ v_geo,
+            float *__restrict__ v_colpack) {
+    constexpr int CQ = CDIM / 4;
+    constexpr int NQUAD = 2 + CQ;  // float4 groups flushed per Gaussian
+    __shared__ float4 s_q[BL_BATCH];
+    __shared__ float2 s_c[BL_BATCH];
+    __shared__ int s_idx[BL_BATCH];
+    __shared__ int s_gid[BL_BATCH];
+    __shared__ float4 s_col[BL_BATCH][CQ];
+    __shared__ int s_wcnt[BL_WARPS];
+    __shared__ __align__(16) float s_acc[BL_WARPS][BL_BATCH][16];
+
+    const TileGeom tg = tile_geom(tile_w, tile_h, W, H, M, offsets);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lt = lanemask_lt();
+
+    float T0 = 1.f, T1 = 1.f, Tf0 = 1.f, Tf1 = 1.f, vra0 = 0.f, vra1 = 0.f;
+    float vrc0[CDIM], vrc1[CDIM], buf0[CDIM], buf1[CDIM];
+#pragma unroll
+    for (int k = 0; k < CDIM; ++k) vrc0[k] = vrc1[k] = buf0[k] = buf1[k] = 0.f;
+    int bin0 = -1, bin1 = -1;
+    if (tg.in0) {
+        const size_t pid = (size_t)tg.y0 * W + tg.x;
+        load_pixel_cotangent<CDIM, DOUT, ED>(pid, render, alpha_in, v_render, v_alpha, vrc0, vra0, Tf0);
+        T0 = Tf0;
+        bin0 = last_ids[pid];
+    }
+    if (tg.in1) {
+        const size_t pid = (size_t)(tg.y0 + 1) * W + tg.x;
+        load_pixel_cotangent<CDIM, DOUT, ED>(pid, render, alpha_in, v_render, v_alpha, vrc1, vra1, Tf1);
+        T1 = Tf1;
+        bin1 = last_ids[pid];
+    }
+    // last sorted index any pixel of this tile blended
+    int maxbin = __reduce_max_sync(0xffffffffu, max(bin0, bin1));
+    if (lane == 0) s_wcnt[warp] = maxbin;
+    __syncthreads();
+    maxbin = max(max(s_wcnt[0], s_wcnt[1]), max(s_wcnt[2], s_wcnt[3]));
+    const int hi0 = min(tg.end - 1, maxbin);
+
+    for (int hi = hi0; hi >= tg.start; hi -= BL_BATCH) {
+        __syncthreads();  // previous batch fully flushed before its buffers are reused
+        const int idx = hi - (int)threadIdx.x;  // back to front: slot order == descending sorted index
+        bool keep = false;
+        int g = 0;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        float2 c = make_float2(0.f, 0.f);
+        if (idx >= tg.start) {
+            g = flatten_ids[idx];
+            const float2 m = means2d[g];
+            const float4 ge = geo[g];
+            q = make_float4(m.x, m.y, 0.5f * B2S_LOG2E * ge.x, B2S_LOG2E * ge.y);
+            c = make_float2(0.5f * B2S_LOG2E * ge.z, ge.w);
+            keep = tile_keep(m.x, m.y, q.z, q.w, c.x, c.y, tg.rx0, tg.ry0, tg.rx1, tg.ry1);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_wcnt[warp] = __popc(bal);
+        __syncthreads();
+        int off = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < BL_WARPS; ++w) {
+            int n = s_wcnt[w];
+            off += (w < warp) ? n : 0;
+            total += n;
+        }
+        if (keep) {
+            const int slot = off + __popc(bal & lt);
+            s_q[slot] = q;
+            s_c[slot] = c;
+            s_idx[slot] = idx;
+            s_gid[slot] = g;
+#pragma unroll
+            for (int k = 0; k < CQ; ++k) s_col[slot][k] = colpack[(size_t)g * CQ + k];
+        }
+        __syncthreads();
+
+        for (int t = 0; t < total; ++t) {
+            const float4 sq = s_q[t];
+            const float2 sc = s_c[t];
+            const int id = s_idx[t];
+            const float dx = sq.x - tg.px;
+            const float dy0 = sq.y - tg.py0, dy1 = sq.y - tg.py1;
+            const float p0 = splat_power(sq.z, sq.w, sc.x, dx, dy0);
+            const float p1 = splat_power(sq.z, sq.w, sc.x, dx, dy1);
+            const float e0 = ex2_approx(-p0), e1 = ex2_approx(-p1);
+            const float a0 = fminf(B2S_ALPHA_MAX, __fmul_rn(sc.y, e0));
+            const float a1 = fminf(B2S_ALPHA_MAX, __fmul_rn(sc.y, e1));
+            const bool ok0 = id <= bin0 && p0 >= 0.f && a0 >= B2S_ALPHA_MIN;
+            const bool ok1 = id <= bin1 && p1 >= 0.f && a1 >= B2S_ALPHA_MIN;
+            if (!__any_sync(0xffffffffu, ok0 || ok1)) {
+                if (lane < 16) s_acc[warp][t][lane] = 0.f;
+                continue;
+            }
+            float v[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = 0.f;
+            float col[CDIM];
+#pragma unroll
+            for (int k = 0; k < CQ; ++k) {
+                const float4 cv = s_col[t][k];
+                col[4 * k] = cv.x; col[4 * k + 1] = cv.y; col[4 * k + 2] = cv.z; col[4 * k + 3] = cv.w;
+            }
+            if (ok0) pixel_grad<CDIM>(v, T0, buf0, vrc0, vra0, Tf0, col, sq.z, sq.w, sc.x, sc.y, dx, dy0, a0, e0);
+            if (ok1) pixel_grad<CDIM>(v, T1, buf1, vrc1, vra1, Tf1, col, sq.z, sq.w, sc.x, sc.y, dx, dy1, a1, e1);
+            const float r = warp_reduce16_transposed(v, lane);
+            if (!(lane & 1)) s_acc[warp][t][lane >> 1] = r;
+        }
+        __syncthreads();
+
+        // flush: item = (slot, quad); consecutive threads read consecutive float4s of s_acc (conflict free)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int item = (int)threadIdx.x + BL_THREADS * j;
+            const int slot = item >> 2, quad = item & 3;
+            if (slot < total && quad < NQUAD) {
+                float4 s = reinterpret_cast<const float4 *>(&s_acc[0][slot][0])[quad];
+#pragma unroll
+                for (int w = 1; w < BL_WARPS; ++w) {
+                    const float4 o = reinterpret_cast<const float4 *>(&s_acc[w][slot][0])[quad];
+                    s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+                }
+                if (s.x != 0.f || s.y != 0.f || s.z != 0.f || s.w != 0.f) {
+                    const int gid = s_gid[slot];
+                    float *dst = quad == 0 ? v_xyabs + (size_t)gid * 4
+                               : quad == 1 ? v_geo + (size_t)gid * 4
+                                           : v_colpack + (size_t)gid * CDIM + (quad - 2) * 4;
+                    red_add_v4(dst, s.x, s.y, s.z, s.w);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+template <int CDIM, int DOUT, bool ED>
+static int launch_fwd(const float *means2d, const float *geo, const float *colpack, const int32_t *offsets,
+                      const int32_t *flatten_ids, long long M, int W, int H, int tile_w, int tile_h, float *render,
+                      float *alpha, int32_t *last_ids, cudaStream_t st) {
+    k_blend_fwd<CDIM, DOUT, ED><<<tile_w * tile_h, BL_THREADS, 0, st>>>(
+        (const float2 *)means2d, (const float4 *)geo, (const float4 *)colpack, offsets, flatten_ids, M, W, H, tile_w,
+        tile_h, render, alpha, last_ids);
+    B2S_LAUNCH_CHECK();
+    return B2S_OK;
+}
+template <int CDIM, int DOUT, bool ED>
+static int launch_bwd(const float *means2d, const float *geo, const float *colpack, const int32_t *offsets,
+                      const int32_t *flatten_ids, long long M, int W, int H, int tile_w, int tile_h,
+                      const float *render, const float *alpha, const int32_t *last_ids, const float *v_render,
+                      const float *v_alpha, float *v_xyabs, float *v_geo, float *v_colpack, cudaStream_t st) {
+    k_blend_bwd<CDIM, DOUT, ED><<<tile_w * tile_h, BL_THREADS, 0, st>>>(
+        (const float2 *)means2d, (const float4 *)geo, (const float4 *)colpack, offsets, flatten_ids, M, W, H, tile_w,
+        tile_h, render, alpha, last_ids, v_render, v_alpha, v_xyabs, v_geo, v_colpack);
+    B2S_LAUNCH_CHECK();
+    return B2S_OK;
+}
+
+// (cdim, d_out) combinations MTGS reaches: RGB -> (4,3); RGB+ED -> (4,4);
+// RGB+normals -> (8,6); RGB+normals+ED -> (8,7).  Others in 1..cdim are instantiated for completeness.
+#define B2S_DISPATCH(FN, ...)                                                                      \
+    do {                                                                                           \
+        const bool ed = expected_depth != 0;                                                       \
+        if (cdim == 4) {                                                                           \
+            switch (d_out) {                                                                       \
+                case 1: return ed ? FN<4, 1, true>(__VA_ARGS__) : FN<4, 1, false>(__VA_ARGS__);    \
+                case 2: return ed ? FN<4, 2, true>(__VA_ARGS__) : FN<4, 2, false>(__VA_ARGS__);    \
+                case 3: return ed ? FN<4, 3, true>(__VA_ARGS__) : FN<4, 3, false>(__VA_ARGS__);    \
+                case 4: return ed ? FN<4, 4, true>(__VA_ARGS__) : FN<4, 4, false>(__VA_ARGS__);    \
+            }                                                                                      \
+        } else if (cdim == 8) {                                                                    \
+            switch (d_out) {                                                                       \
+                case 5: return ed ? FN<8, 5, true>(__VA_ARGS__) : FN<8, 5, false>(__VA_ARGS__);    \
+                case 6: return ed ? FN<8, 6, true>(__VA_ARGS__) : FN<8, 6, false>(__VA_ARGS__);    \
+                case 7: return ed ? FN<8, 7, true>(__VA_ARGS__) : FN<8, 7, false>(__VA_ARGS__);    \
+                case 8: return ed ? FN<8, 8, true>(__VA_ARGS__) : FN<8, 8, false>(__VA_ARGS__);    \
+            }                                                                                      \
+        }                                                                                          \
+        return B2S_ERR_UNSUPPORTED;                                                                \
+    } while (0)
+
+extern "C" int b2s_blend_fwd(const float *means2d, const float *geo, const float *colpack,
+                             const int32_t *isect_offsets, const int32_t *flatten_ids, long long M, int W, int H,
+                             int tile_w, int tile_h, int cdim, int d_out, int expected_depth, float *render,
+                             float *alpha, int32_t *last_ids, b2s_stream_t stream) {
+    if (W <= 0 || H <= 0 || M < 0 || tile_w * 16 < W || tile_h * 16 < H) return B2S_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    B2S_DISPATCH(launch_fwd, means2d, geo, colpack, isect_offsets, flatten_ids, M, W, H, tile_w, tile_h, render,
+                 alpha, last_ids, st);
+}
+
+extern "C" int b2s_blend_bwd(const float *means2d, const float *geo, const float *colpack,
+                             const int32_t *isect_offsets, const int32_t *flatten_ids, long long M, int W, int H,
+                             int tile_w, int tile_h, int cdim, int d_out, int expected_depth, const float *render,
+                             const float *alpha, const int32_t *last_ids, const float *v_render,
+                             const float *v_alpha, float *v_xyabs, float *v_geo, float *v_colpack,
+                             b2s_stream_t stream) {
+    if (W <= 0 || H <= 0 || M < 0 || tile_w * 16 < W || tile_h * 16 < H) return B2S_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    B2S_DISPATCH(launch_bwd, means2d, geo, colpack, isect_offsets, flatten_ids, M, W, H, tile_w, tile_h, render,
+                 alpha, last_ids, v_render, v_alpha, v_xyabs, v_geo, v_colpack, st);
+}

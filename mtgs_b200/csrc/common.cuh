@@ -1,0 +1,58 @@
+// Shared device/host helpers for libb200splat (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200splat.h"
+
+#define B2S_ALPHA_MAX 0.999f
+#define B2S_ALPHA_MIN (1.0f / 255.0f)
+#define B2S_T_EPS 1e-4f
+#define B2S_LOG2E 1.4426950408889634f
+#define B2S_LN2 0.6931471805599453f
+
+extern long long g_b2s_launches;  // defined in api.cu
+
+static inline int b2s_check_launch() {
+    cudaError_t e = cudaGetLastError();
+    ++g_b2s_launches;
+    return e == cudaSuccess ? B2S_OK : -(int)e - 1000;
+}
+
+#define B2S_LAUNCH_CHECK()                 \
+    do {                                   \
+        int _rc = b2s_check_launch();      \
+        if (_rc != B2S_OK) return _rc;     \
+    } while (0)
+
+static inline int b2s_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+// 16-byte vector reduction to global memory (sm_90+): one L2 atomic op for four floats.
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
+                 "f"(d)
+                 : "memory");
+}
+// streaming (read-once) loads that do not pollute L1
+__device__ __forceinline__ float4 ldg_stream4(const float4 *p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}

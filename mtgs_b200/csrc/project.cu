@@ -1,0 +1,476 @@
+// Projection + EWA covariance, forward and backward (sm_100a).
+//
+// Replaces upstream gsplat v1.4.0 fully_fused_projection_{fwd,bwd}_kernel as reached from
+// mtgs/scene_model/mtgs_scene_graph.py:641-662, and fuses into the same pass
+//   - upstream isect_tiles pass 1 (tile count per Gaussian, A.2),
+//   - the depth sort key,
+//   - torch glue that upstream does outside the kernel: opacities*compensations, cat(colors, depths),
+//     zero padding of the colour channels.
+//
+// The forward is HBM-bound streaming work: one thread per Gaussian, SoA reads that a warp covers with
+// fully used 32 B sectors (means 12 B, quats 16 B, scales 12 B per lane -> contiguous per warp).
+//
+// CANONICAL OP ORDER: every fp32 operation of the forward that feeds a discrete decision
+// (radius, cull, tile rectangle, depth key) is a single IEEE round-to-nearest op written with
+// __fmul_rn/__fadd_rn/__fsub_rn/__fdiv_rn/__fsqrt_rn in a fixed order, never contracted to FMA, so
+// radii / tile counts / keys are reproducible bit for bit by an independent fp32 implementation.
+#include "common.cuh"
+
+#define MUL(a, b) __fmul_rn((a), (b))
+#define ADD(a, b) __fadd_rn((a), (b))
+#define SUB(a, b) __fsub_rn((a), (b))
+#define DIV(a, b) __fdiv_rn((a), (b))
+#define SQRT(a) __fsqrt_rn((a))
+#define DOT3(a0, b0, a1, b1, a2, b2) ADD(ADD(MUL(a0, b0), MUL(a1, b1)), MUL(a2, b2))
+
+struct CamParams {
+    float R[9];
+    float t[3];
+    float fx, fy, cx, cy;
+    float lim_x_pos, lim_x_neg, lim_y_pos, lim_y_neg;
+    float Wf, Hf;
+};
+
+__device__ __forceinline__ void load_camera(const float *__restrict__ viewmat, const float *__restrict__ K,
+                                            int W, int H, CamParams &c) {
+    c.R[0] = viewmat[0]; c.R[1] = viewmat[1]; c.R[2] = viewmat[2];
+    c.R[3] = viewmat[4]; c.R[4] = viewmat[5]; c.R[5] = viewmat[6];
+    c.R[6] = viewmat[8]; c.R[7] = viewmat[9]; c.R[8] = viewmat[10];
+    c.t[0] = viewmat[3]; c.t[1] = viewmat[7]; c.t[2] = viewmat[11];
+    c.fx = K[0]; c.fy = K[4]; c.cx = K[2]; c.cy = K[5];
+    c.Wf = (float)W; c.Hf = (float)H;
+    float tan_fovx = DIV(MUL(0.5f, c.Wf), c.fx);
+    float tan_fovy = DIV(MUL(0.5f, c.Hf), c.fy);
+    c.lim_x_pos = ADD(DIV(SUB(c.Wf, c.cx), c.fx), MUL(0.3f, tan_fovx));
+    c.lim_x_neg = ADD(DIV(c.cx, c.fx), MUL(0.3f, tan_fovx));
+    c.lim_y_pos = ADD(DIV(SUB(c.Hf, c.cy), c.fy), MUL(0.3f, tan_fovy));
+    c.lim_y_neg = ADD(DIV(c.cy, c.fy), MUL(0.3f, tan_fovy));
+}
+
+// normalised-quaternion rotation matrix, row-major (upstream quat_to_rotmat)
+__device__ __forceinline__ void quat_to_rotmat_rn(float w, float x, float y, float z, float *R) {
+    float inv_norm = DIV(1.0f, SQRT(ADD(ADD(ADD(MUL(x, x), MUL(y, y)), MUL(z, z)), MUL(w, w))));
+    x = MUL(x, inv_norm); y = MUL(y, inv_norm); z = MUL(z, inv_norm); w = MUL(w, inv_norm);
+    float x2 = MUL(x, x), y2 = MUL(y, y), z2 = MUL(z, z);
+    float xy = MUL(x, y), xz = MUL(x, z), yz = MUL(y, z);
+    float wx = MUL(w, x), wy = MUL(w, y), wz = MUL(w, z);
+    R[0] = SUB(1.f, MUL(2.f, ADD(y2, z2))); R[1] = MUL(2.f, SUB(xy, wz)); R[2] = MUL(2.f, ADD(xz, wy));
+    R[3] = MUL(2.f, ADD(xy, wz)); R[4] = SUB(1.f, MUL(2.f, ADD(x2, z2))); R[5] = MUL(2.f, SUB(yz, wx));
+    R[6] = MUL(2.f, SUB(xz, wy)); R[7] = MUL(2.f, ADD(yz, wx)); R[8] = SUB(1.f, MUL(2.f, ADD(x2, y2)));
+}
+
+// camera-space covariance Sc = R (Rq S)(Rq S)^T R^T, all nine entries in canonical order
+__device__ __forceinline__ void covar_cam_rn(const float *R, const float *Rq, float s0, float s1, float s2,
+                                             float *Sigma, float *Sc) {
+    float M[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        M[i * 3 + 0] = MUL(Rq[i * 3 + 0], s0);
+        M[i * 3 + 1] = MUL(Rq[i * 3 + 1], s1);
+        M[i * 3 + 2] = MUL(Rq[i * 3 + 2], s2);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            Sigma[i * 3 + j] = DOT3(M[i * 3 + 0], M[j * 3 + 0], M[i * 3 + 1], M[j * 3 + 1], M[i * 3 + 2], M[j * 3 + 2]);
+    float A[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            A[i * 3 + j] = DOT3(R[i * 3 + 0], Sigma[0 * 3 + j], R[i * 3 + 1], Sigma[1 * 3 + j], R[i * 3 + 2], Sigma[2 * 3 + j]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            Sc[i * 3 + j] = DOT3(A[i * 3 + 0], R[j * 3 + 0], A[i * 3 + 1], R[j * 3 + 1], A[i * 3 + 2], R[j * 3 + 2]);
+}
+
+template <int CDIM>
+__global__ void __launch_bounds__(256)
+k_project_fwd(const float *__restrict__ means, const float *__restrict__ quats, const float *__restrict__ scales,
+              const float *__restrict__ opacities, const float *__restrict__ colors_in,
+              const float *__restrict__ viewmat, const float *__restrict__ K, int N, int W, int H, int tile_w,
+              int tile_h, float eps2d, float near_plane, float far_plane, float radius_clip, int calc_comp,
+              int d_in, int with_depth, int32_t *__restrict__ radii, float2 *__restrict__ means2d,
+              float *__restrict__ depths, float4 *__restrict__ geo, float *__restrict__ comps,
+              float *__restrict__ colpack, int32_t *__restrict__ tiles_per_gauss,
+              uint32_t *__restrict__ sort_keys, uint32_t *__restrict__ sort_vals) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N) return;
+    CamParams cam;
+    load_camera(viewmat, K, W, H, cam);
+
+    float p0 = means[3 * g], p1 = means[3 * g + 1], p2 = means[3 * g + 2];
+    float pc[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        pc[i] = ADD(DOT3(cam.R[i * 3 + 0], p0, cam.R[i * 3 + 1], p1, cam.R[i * 3 + 2], p2), cam.t[i]);
+
+    int32_t radius_i = 0;
+    int32_t ntiles = 0;
+    float mx = 0.f, my = 0.f, ca = 0.f, cb = 0.f, cc = 0.f, comp = 1.f;
+    float z = pc[2];
+    bool ok = !(z < near_plane || z > far_plane);
+    if (ok) {
+        const float4 q = reinterpret_cast<const float4 *>(quats)[g];
+        float s0 = scales[3 * g], s1 = scales[3 * g + 1], s2 = scales[3 * g + 2];
+        float Rq[9], Sigma[9], Sc[9];
+        quat_to_rotmat_rn(q.x, q.y, q.z, q.w, Rq);
+        covar_cam_rn(cam.R, Rq, s0, s1, s2, Sigma, Sc);
+
+        float x = pc[0], y = pc[1];
+        float rz = DIV(1.0f, z);
+        float rz2 = MUL(rz, rz);
+        float tx = MUL(z, fminf(cam.lim_x_pos, fmaxf(-cam.lim_x_neg, MUL(x, rz))));
+        float ty = MUL(z, fminf(cam.lim_y_pos, fmaxf(-cam.lim_y_neg, MUL(y, rz))));
+        float j00 = MUL(cam.fx, rz), j02 = -MUL(MUL(cam.fx, tx), rz2);
+        float j11 = MUL(cam.fy, rz), j12 = -MUL(MUL(cam.fy, ty), rz2);
+        float B00 = ADD(MUL(j00, Sc[0]), MUL(j02, Sc[6]));
+        float B01 = ADD(MUL(j00, Sc[1]), MUL(j02, Sc[7]));
+        float B02 = ADD(MUL(j00, Sc[2]), MUL(j02, Sc[8]));
+        float B11 = ADD(MUL(j11, Sc[4]), MUL(j12, Sc[7]));
+        float B12 = ADD(MUL(j11, Sc[5]), MUL(j12, Sc[8]));
+        float c00 = ADD(MUL(B00, j00), MUL(B02, j02));
+        float c01 = ADD(MUL(B01, j11), MUL(B02, j12));
+        float c11 = ADD(MUL(B11, j11), MUL(B12, j12));
+        mx = ADD(MUL(MUL(cam.fx, x), rz), cam.cx);
+        my = ADD(MUL(MUL(cam.fy, y), rz), cam.cy);
+
+        float det_orig = SUB(MUL(c00, c11), MUL(c01, c01));
+        c00 = ADD(c00, eps2d);
+        c11 = ADD(c11, eps2d);
+        float det = SUB(MUL(c00, c11), MUL(c01, c01));
+        comp = SQRT(fmaxf(0.0f, DIV(det_orig, det)));
+        ok = det > 0.0f;
+        if (ok) {
+            float inv_det = DIV(1.0f, det);
+            ca = MUL(c11, inv_det);
+            cb = MUL(-c01, inv_det);
+            cc = MUL(c00, inv_det);
+            float b = MUL(0.5f, ADD(c00, c11));
+            float v1 = ADD(b, SQRT(fmaxf(0.01f, SUB(MUL(b, b), det))));
+            float radius = ceilf(MUL(3.0f, SQRT(v1)));
+            ok = !(radius <= radius_clip);
+            ok = ok && !(ADD(mx, radius) <= 0.0f || SUB(mx, radius) >= cam.Wf || ADD(my, radius) <= 0.0f ||
+                         SUB(my, radius) >= cam.Hf);
+            if (ok) {
+                radius_i = (int32_t)radius;
+                // upstream isect_tiles pass 1 on the integer radius (tile size 16: divisions are exact)
+                float tr = DIV((float)radius_i, 16.0f);
+                float txc = DIV(mx, 16.0f), tyc = DIV(my, 16.0f);
+                float fx0 = floorf(SUB(txc, tr)), fy0 = floorf(SUB(tyc, tr));
+                float fx1 = ceilf(ADD(txc, tr)), fy1 = ceilf(ADD(tyc, tr));
+                int x0 = fx0 <= 0.f ? 0 : (fx0 >= (float)tile_w ? tile_w : (int)fx0);
+                int y0 = fy0 <= 0.f ? 0 : (fy0 >= (float)tile_h ? tile_h : (int)fy0);
+                int x1 = fx1 <= 0.f ? 0 : (fx1 >= (float)tile_w ? tile_w : (int)fx1);
+                int y1 = fy1 <= 0.f ? 0 : (fy1 >= (float)tile_h ? tile_h : (int)fy1);
+                ntiles = (y1 - y0) * (x1 - x0);
+            }
+        }
+    }
+    radii[g] = radius_i;
+    tiles_per_gauss[g] = ntiles;
+    sort_keys[g] = radius_i > 0 ? __float_as_uint(z) : 0xFFFFFFFFu;
+    sort_vals[g] = (uint32_t)g;
+    if (radius_i > 0) {
+        float op = opacities[g];
+        if (calc_comp) {
+            comps[g] = comp;
+            op = MUL(op, comp);
+        }
+        means2d[g] = make_float2(mx, my);
+        depths[g] = z;
+        geo[g] = make_float4(ca, cb, cc, op);
+        float cp[CDIM];
+#pragma unroll
+        for (int k = 0; k < CDIM; ++k) cp[k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < CDIM; ++k)
+            if (k < d_in) cp[k] = colors_in[(size_t)g * d_in + k];
+        if (with_depth) {
+#pragma unroll
+            for (int k = 0; k < CDIM; ++k)
+                if (k == d_in) cp[k] = z;
+        }
+        float4 *dst = reinterpret_cast<float4 *>(colpack + (size_t)g * CDIM);
+#pragma unroll
+        for (int k = 0; k < CDIM / 4; ++k) dst[k] = make_float4(cp[4 * k], cp[4 * k + 1], cp[4 * k + 2], cp[4 * k + 3]);
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// backward.  Tolerance-checked, so FMA contraction is allowed here.
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mat3_mul(const float *A, const float *B, float *C) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            C[i * 3 + j] = A[i * 3 + 0] * B[0 * 3 + j] + A[i * 3 + 1] * B[1 * 3 + j] + A[i * 3 + 2] * B[2 * 3 + j];
+}
+__device__ __forceinline__ void mat3_mul_bt(const float *A, const float *B, float *C) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            C[i * 3 + j] = A[i * 3 + 0] * B[j * 3 + 0] + A[i * 3 + 1] * B[j * 3 + 1] + A[i * 3 + 2] * B[j * 3 + 2];
+}
+__device__ __forceinline__ void mat3_mul_at(const float *A, const float *B, float *C) {  // A^T B
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            C[i * 3 + j] = A[0 * 3 + i] * B[0 * 3 + j] + A[1 * 3 + i] * B[1 * 3 + j] + A[2 * 3 + i] * B[2 * 3 + j];
+}
+
+template <int CDIM>
+__global__ void __launch_bounds__(256)
+k_project_bwd(const float *__restrict__ means, const float *__restrict__ quats, const float *__restrict__ scales,
+              const float *__restrict__ opacities, const float *__restrict__ viewmat, const float *__restrict__ K,
+              int N, int W, int H, float eps2d, int calc_comp, int d_in, int with_depth,
+              const int32_t *__restrict__ radii, const float4 *__restrict__ geo, const float *__restrict__ comps,
+              const float *__restrict__ v_means2d, int v_m2d_stride, const float4 *__restrict__ v_geo,
+              const float *__restrict__ v_colpack, float *__restrict__ v_means, float4 *__restrict__ v_quats,
+              float *__restrict__ v_scales, float *__restrict__ v_opacities, float *__restrict__ v_viewmat) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    float vR[9], vt[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) vR[k] = 0.f;
+    vt[0] = vt[1] = vt[2] = 0.f;
+    const bool live = g < N && radii[g] > 0;
+    if (g < N && !live) {
+        v_means[3 * g] = v_means[3 * g + 1] = v_means[3 * g + 2] = 0.f;
+        v_scales[3 * g] = v_scales[3 * g + 1] = v_scales[3 * g + 2] = 0.f;
+        v_quats[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+        v_opacities[g] = 0.f;
+    }
+    if (live) {
+        CamParams cam;
+        load_camera(viewmat, K, W, H, cam);
+        const float *R = cam.R;
+        const float4 cg = geo[g];
+        const float2 gxy = *reinterpret_cast<const float2 *>(v_means2d + (size_t)g * v_m2d_stride);
+        const float4 gge = v_geo[g];
+        float ia = cg.x, ib = cg.y, ic = cg.z;
+        // inverse VJP: v_cov2d = -Minv * G * Minv with G = [[ga, gb/2],[gb/2, gc]]
+        float ga = gge.x, gb = 0.5f * gge.y, gc = gge.z;
+        float p00 = ia * ga + ib * gb, p01 = ia * gb + ib * gc;
+        float p10 = ib * ga + ic * gb, p11 = ib * gb + ic * gc;
+        float G[4];
+        G[0] = -(p00 * ia + p01 * ib); G[1] = -(p00 * ib + p01 * ic);
+        G[2] = -(p10 * ia + p11 * ib); G[3] = -(p10 * ib + p11 * ic);
+        // opacity_eff = opacity * comp
+        float v_op_eff = gge.w;
+        float op = opacities[g];
+        if (calc_comp) {
+            float comp = comps[g];
+            float v_comp = v_op_eff * op;
+            v_opacities[g] = v_op_eff * comp;
+            float det_conic = ia * ic - ib * ib;
+            float v_sqr_comp = v_comp * 0.5f / (comp + 1e-6f);
+            float one_minus = 1.0f - comp * comp;
+            G[0] += v_sqr_comp * (one_minus * ia - eps2d * det_conic);
+            G[1] += v_sqr_comp * (one_minus * ib);
+            G[2] += v_sqr_comp * (one_minus * ib);
+            G[3] += v_sqr_comp * (one_minus * ic - eps2d * det_conic);
+        } else {
+            v_opacities[g] = v_op_eff;
+        }
+        float v_depth = with_depth ? v_colpack[(size_t)g * CDIM + d_in] : 0.f;
+
+        float p[3] = {means[3 * g], means[3 * g + 1], means[3 * g + 2]};
+        float pc[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) pc[i] = R[i * 3 + 0] * p[0] + R[i * 3 + 1] * p[1] + R[i * 3 + 2] * p[2] + cam.t[i];
+        const float4 q = reinterpret_cast<const float4 *>(quats)[g];
+        float s[3] = {scales[3 * g], scales[3 * g + 1], scales[3 * g + 2]};
+        float inv_norm = rsqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+        float qw = q.x * inv_norm, qx = q.y * inv_norm, qy = q.z * inv_norm, qz = q.w * inv_norm;
+        float Rq[9];
+        {
+            float x2 = qx * qx, y2 = qy * qy, z2 = qz * qz, xy = qx * qy, xz = qx * qz, yz = qy * qz;
+            float wx = qw * qx, wy = qw * qy, wz = qw * qz;
+            Rq[0] = 1.f - 2.f * (y2 + z2); Rq[1] = 2.f * (xy - wz); Rq[2] = 2.f * (xz + wy);
+            Rq[3] = 2.f * (xy + wz); Rq[4] = 1.f - 2.f * (x2 + z2); Rq[5] = 2.f * (yz - wx);
+            Rq[6] = 2.f * (xz - wy); Rq[7] = 2.f * (yz + wx); Rq[8] = 1.f - 2.f * (x2 + y2);
+        }
+        float Mm[9], Sigma[9], RS[9], Sc[9];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) Mm[i * 3 + j] = Rq[i * 3 + j] * s[j];
+        mat3_mul_bt(Mm, Mm, Sigma);
+        mat3_mul(R, Sigma, RS);     // R Sigma  (Sigma symmetric => also R Sigma^T)
+        mat3_mul_bt(RS, R, Sc);
+
+        // perspective projection VJP
+        float x = pc[0], y = pc[1], z = pc[2];
+        float rz = 1.0f / z, rz2 = rz * rz, rz3 = rz2 * rz;
+        float xr = x * rz, yr = y * rz;
+        float tx = z * fminf(cam.lim_x_pos, fmaxf(-cam.lim_x_neg, xr));
+        float ty = z * fminf(cam.lim_y_pos, fmaxf(-cam.lim_y_neg, yr));
+        float J[6] = {cam.fx * rz, 0.f, -cam.fx * tx * rz2, 0.f, cam.fy * rz, -cam.fy * ty * rz2};
+        float GJ[6], GtJ[6];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                GJ[i * 3 + j] = G[i * 2 + 0] * J[0 * 3 + j] + G[i * 2 + 1] * J[1 * 3 + j];
+                GtJ[i * 3 + j] = G[0 * 2 + i] * J[0 * 3 + j] + G[1 * 2 + i] * J[1 * 3 + j];
+            }
+        float vSc[9];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) vSc[i * 3 + j] = J[0 * 3 + i] * GJ[0 * 3 + j] + J[1 * 3 + i] * GJ[1 * 3 + j];
+        float vpc[3];
+        vpc[0] = cam.fx * rz * gxy.x;
+        vpc[1] = cam.fy * rz * gxy.y;
+        vpc[2] = -(cam.fx * x * gxy.x + cam.fy * y * gxy.y) * rz2;
+        float vJ[6];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                float a = 0.f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) a += GJ[i * 3 + k] * Sc[j * 3 + k] + GtJ[i * 3 + k] * Sc[k * 3 + j];
+                vJ[i * 3 + j] = a;
+            }
+        if (xr <= cam.lim_x_pos && xr >= -cam.lim_x_neg) vpc[0] += -cam.fx * rz2 * vJ[2];
+        else vpc[2] += -cam.fx * rz3 * vJ[2] * tx;
+        if (yr <= cam.lim_y_pos && yr >= -cam.lim_y_neg) vpc[1] += -cam.fy * rz2 * vJ[5];
+        else vpc[2] += -cam.fy * rz3 * vJ[5] * ty;
+        vpc[2] += -cam.fx * rz2 * vJ[0] - cam.fy * rz2 * vJ[4] + 2.f * cam.fx * tx * rz3 * vJ[2] +
+                  2.f * cam.fy * ty * rz3 * vJ[5];
+        vpc[2] += v_depth;
+
+        // world->camera VJPs
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            vt[i] = vpc[i];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) vR[i * 3 + j] = vpc[i] * p[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) v_means[3 * g + j] = R[0 * 3 + j] * vpc[0] + R[1 * 3 + j] * vpc[1] + R[2 * 3 + j] * vpc[2];
+        // v_R += vSc (R Sigma^T) + vSc^T (R Sigma)
+        float tmp[9];
+        mat3_mul(vSc, RS, tmp);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) vR[k] += tmp[k];
+        mat3_mul_at(vSc, RS, tmp);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) vR[k] += tmp[k];
+        // v_Sigma = R^T vSc R
+        float vSigma[9];
+        mat3_mul_at(R, vSc, tmp);
+        mat3_mul(tmp, R, vSigma);
+
+        // quat/scale VJP: Sigma = M M^T, M = Rq S
+        float Sym[9], vM[9];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) Sym[i * 3 + j] = vSigma[i * 3 + j] + vSigma[j * 3 + i];
+        mat3_mul(Sym, Mm, vM);
+        float Gq[9];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) Gq[i * 3 + j] = vM[i * 3 + j] * s[j];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            v_scales[3 * g + j] = Rq[0 * 3 + j] * vM[0 * 3 + j] + Rq[1 * 3 + j] * vM[1 * 3 + j] + Rq[2 * 3 + j] * vM[2 * 3 + j];
+        float vqn[4];
+        vqn[0] = 2.f * (qx * (Gq[7] - Gq[5]) + qy * (Gq[2] - Gq[6]) + qz * (Gq[3] - Gq[1]));
+        vqn[1] = 2.f * (-2.f * qx * (Gq[4] + Gq[8]) + qy * (Gq[1] + Gq[3]) + qz * (Gq[2] + Gq[6]) + qw * (Gq[7] - Gq[5]));
+        vqn[2] = 2.f * (qx * (Gq[1] + Gq[3]) - 2.f * qy * (Gq[0] + Gq[8]) + qz * (Gq[5] + Gq[7]) + qw * (Gq[2] - Gq[6]));
+        vqn[3] = 2.f * (qx * (Gq[2] + Gq[6]) + qy * (Gq[5] + Gq[7]) - 2.f * qz * (Gq[0] + Gq[4]) + qw * (Gq[3] - Gq[1]));
+        float dotp = vqn[0] * qw + vqn[1] * qx + vqn[2] * qy + vqn[3] * qz;
+        v_quats[g] = make_float4((vqn[0] - dotp * qw) * inv_norm, (vqn[1] - dotp * qx) * inv_norm,
+                                 (vqn[2] - dotp * qy) * inv_norm, (vqn[3] - dotp * qz) * inv_norm);
+    }
+    // viewmat gradient: 12 sums over all Gaussians -> warp butterfly, smem across warps, 12 atomics / CTA
+    if (v_viewmat != nullptr) {
+        __shared__ float s_part[8][12];
+        float vals[12];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) vals[k] = vR[k];
+        vals[9] = vt[0]; vals[10] = vt[1]; vals[11] = vt[2];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) vals[k] += __shfl_xor_sync(0xffffffffu, vals[k], o);
+        }
+        int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) s_part[warp][k] = vals[k];
+        }
+        __syncthreads();
+        if (threadIdx.x < 12) {
+            float a = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) a += s_part[w][threadIdx.x];
+            int k = threadIdx.x;
+            int dst = k < 9 ? (k / 3) * 4 + (k % 3) : (k - 9) * 4 + 3;
+            if (a != 0.f) atomicAdd(v_viewmat + dst, a);
+        }
+    }
+}
+
+extern "C" int b2s_project_fwd(const float *means, const float *quats, const float *scales,
+                               const float *opacities, const float *colors_in, const float *viewmat,
+                               const float *K, int N, int W, int H, int tile_size, int tile_w, int tile_h,
+                               float eps2d, float near_plane, float far_plane, float radius_clip, int calc_comp,
+                               int d_in, int with_depth, int cdim, int32_t *radii, float *means2d, float *depths,
+                               float *geo, float *comps, float *colpack, int32_t *tiles_per_gauss,
+                               uint32_t *sort_keys, uint32_t *sort_vals, b2s_stream_t stream) {
+    if (N < 0 || W <= 0 || H <= 0) return B2S_ERR_ARG;
+    if (tile_size != 16) return B2S_ERR_UNSUPPORTED;
+    if (cdim != 4 && cdim != 8) return B2S_ERR_UNSUPPORTED;
+    if (d_in < 0 || d_in + (with_depth ? 1 : 0) > cdim) return B2S_ERR_ARG;
+    if (calc_comp && comps == nullptr) return B2S_ERR_ARG;
+    if (N == 0) return B2S_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(b2s_div_up(N, 256)), block(256);
+#define LAUNCH(CD)                                                                                           \
+    k_project_fwd<CD><<<grid, block, 0, st>>>(means, quats, scales, opacities, colors_in, viewmat, K, N, W, H, \
+                                              tile_w, tile_h, eps2d, near_plane, far_plane, radius_clip,     \
+                                              calc_comp, d_in, with_depth, radii, (float2 *)means2d, depths, \
+                                              (float4 *)geo, comps, colpack, tiles_per_gauss, sort_keys, sort_vals)
+    if (cdim == 4) LAUNCH(4);
+    else LAUNCH(8);
+#undef LAUNCH
+    B2S_LAUNCH_CHECK();
+    return B2S_OK;
+}
+
+extern "C" int b2s_project_bwd(const float *means, const float *quats, const float *scales,
+                               const float *opacities, const float *viewmat, const float *K, int N, int W, int H,
+                               float eps2d, int calc_comp, int d_in, int with_depth, int cdim,
+                               const int32_t *radii, const float *geo, const float *comps, const float *v_means2d,
+                               int v_means2d_stride, const float *v_geo, const float *v_colpack, float *v_means,
+                               float *v_quats,
+                               float *v_scales, float *v_opacities, float *v_viewmat, b2s_stream_t stream) {
+    if (N < 0) return B2S_ERR_ARG;
+    if (cdim != 4 && cdim != 8) return B2S_ERR_UNSUPPORTED;
+    if (calc_comp && comps == nullptr) return B2S_ERR_ARG;
+    if (v_means2d_stride < 2 || (v_means2d_stride & 1)) return B2S_ERR_ARG;
+    if (N == 0) return B2S_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(b2s_div_up(N, 256)), block(256);
+#define LAUNCH(CD)                                                                                            \
+    k_project_bwd<CD><<<grid, block, 0, st>>>(means, quats, scales, opacities, viewmat, K, N, W, H, eps2d,     \
+                                              calc_comp, d_in, with_depth, radii, (const float4 *)geo, comps, \
+                                              v_means2d, v_means2d_stride, (const float4 *)v_geo, v_colpack, \
+                                              v_means, (float4 *)v_quats, v_scales, v_opacities, v_viewmat)
+    if (cdim == 4) LAUNCH(4);
+    else LAUNCH(8);
+#undef LAUNCH
+    B2S_LAUNCH_CHECK();
+    return B2S_OK;
+}

@@ -1,0 +1,366 @@
+"""``rasterization`` -- drop-in for ``gsplat.rendering.rasterization`` as MTGS calls it.
+
+Reference call site: mtgs/scene_model/mtgs_scene_graph.py:641-662 (kwargs), consumers of the returns at
+:663-690 (``render``/``alpha``), :666-670 and :1157-1183 (``info["means2d"]`` with ``.retain_grad()`` /
+``.grad`` / ``.absgrad``, ``info["radii"]``).  Signature, argument meaning, return layout and error
+behaviour follow upstream gsplat v1.4.0 (requirements.txt:12); the arithmetic runs in hand-written
+sm_100a kernels behind the C ABI of ``include/b200splat.h``.  PyTorch is used for device memory, the
+autograd graph and the current stream only.  There is no CPU / PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# Optional per-stage CUDA-event timing (bench.py sets PROFILE = {} to collect (start, end) event pairs per
+# stage on the launching stream; None = zero overhead).
+PROFILE = None
+
+
+class _timed:
+    def __init__(self, stage: str):
+        self.stage = stage
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.b.record()
+            PROFILE.setdefault(self.stage, []).append((self.a, self.b))
+        return False
+
+
+def _need_cuda(*ts: Tensor) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("mtgs_b200 kernels need CUDA tensors (no CPU fallback path exists)")
+
+
+def _f32c(t: Tensor) -> Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"expected float32 tensor, got {t.dtype}")
+    return t.contiguous()
+
+
+def padded_channels(ch: int) -> int:
+    """Blend width for ``ch`` payload channels (4 or 8; upstream pads to its own compile-time set)."""
+    if ch < 1 or ch > 8:
+        raise NotImplementedError(f"{ch} blended channels: this build instantiates 1..8 (MTGS uses 3, 4, 6, 7)")
+    return 4 if ch <= 4 else 8
+
+
+class Meta(dict):
+    """``info`` dict.  ``isect_ids`` (upstream's int64 keys) is rebuilt on first access: the two-level
+    sort never materialises them, and MTGS never reads them."""
+
+    _lazy = None
+
+    def __missing__(self, key):
+        if key == "isect_ids" and self._lazy is not None:
+            val = self._lazy()
+            self[key] = val
+            return val
+        raise KeyError(key)
+
+    def get(self, key, default=None):
+        try:
+            return self[key]
+        except KeyError:
+            return default
+
+
+# ------------------------------------------------------------------------------------------------
+class _Project(torch.autograd.Function):
+    """Projection + EWA (+ tile count, sort key, blend record packing).  One kernel each way."""
+
+    @staticmethod
+    def forward(ctx, means, quats, scales, opacities, colors, viewmat, K, W, H, tile_w, tile_h, eps2d, near, far,
+                radius_clip, calc_comp, with_depth, cdim):
+        lib = _lib.load()
+        N = means.shape[0]
+        d_in = 0 if colors is None else colors.shape[1]
+        dev = means.device
+        radii = torch.empty(N, dtype=torch.int32, device=dev)
+        # culled rows are never written by the kernel: zero-fill so every returned value is defined
+        means2d = torch.zeros(1, N, 2, dtype=torch.float32, device=dev)
+        depths = torch.zeros(N, dtype=torch.float32, device=dev)
+        geo = torch.zeros(N, 4, dtype=torch.float32, device=dev)
+        comps = torch.zeros(N, dtype=torch.float32, device=dev) if calc_comp else None
+        colpack = torch.zeros(N, cdim, dtype=torch.float32, device=dev)
+        tiles = torch.empty(N, dtype=torch.int32, device=dev)
+        keys = torch.empty(N, dtype=torch.int32, device=dev)
+        vals = torch.empty(N, dtype=torch.int32, device=dev)
+        with _timed("project_fwd"):
+            _lib.check(lib.b2s_project_fwd(_ptr(means), _ptr(quats), _ptr(scales), _ptr(opacities), _ptr(colors),
+                                           _ptr(viewmat), _ptr(K), N, W, H, 16, tile_w, tile_h, eps2d, near, far,
+                                           radius_clip, int(calc_comp), d_in, int(with_depth), cdim, _ptr(radii),
+                                           _ptr(means2d), _ptr(depths), _ptr(geo), _ptr(comps), _ptr(colpack),
+                                           _ptr(tiles), _ptr(keys), _ptr(vals), _stream()), "b2s_project_fwd")
+        ctx.save_for_backward(means, quats, scales, opacities, viewmat, K, radii, geo, comps)
+        ctx.cfg = (W, H, eps2d, calc_comp, d_in, with_depth, cdim)
+        ctx.has_colors = colors is not None
+        ctx.mark_non_differentiable(radii, depths, tiles, keys, vals)
+        return means2d, geo, colpack, radii, depths, tiles, keys, vals
+
+    @staticmethod
+    def backward(ctx, v_means2d, v_geo, v_colpack, *_unused):
+        lib = _lib.load()
+        means, quats, scales, opacities, viewmat, K, radii, geo, comps = ctx.saved_tensors
+        W, H, eps2d, calc_comp, d_in, with_depth, cdim = ctx.cfg
+        N = means.shape[0]
+        dev = means.device
+        if v_means2d is None:
+            v_means2d = torch.zeros(N, 2, dtype=torch.float32, device=dev)
+        v_means2d = v_means2d.reshape(N, 2)
+        if not (v_means2d.stride(1) == 1 and v_means2d.stride(0) in (2, 4) and v_means2d.data_ptr() % 8 == 0):
+            v_means2d = v_means2d.contiguous()
+        v_geo = torch.zeros(N, 4, dtype=torch.float32, device=dev) if v_geo is None else v_geo.contiguous()
+        v_colpack = (torch.zeros(N, cdim, dtype=torch.float32, device=dev) if v_colpack is None
+                     else v_colpack.contiguous())
+        v_means = torch.empty_like(means)
+        v_quats = torch.empty_like(quats)
+        v_scales = torch.empty_like(scales)
+        v_opac = torch.empty_like(opacities)
+        need_view = ctx.needs_input_grad[5]
+        v_view = torch.zeros(4, 4, dtype=torch.float32, device=dev) if need_view else None
+        with _timed("project_bwd"):
+            _lib.check(lib.b2s_project_bwd(_ptr(means), _ptr(quats), _ptr(scales), _ptr(opacities), _ptr(viewmat),
+                                           _ptr(K), N, W, H, eps2d, int(calc_comp), d_in, int(with_depth), cdim,
+                                           _ptr(radii), _ptr(geo), _ptr(comps), _ptr(v_means2d),
+                                           int(v_means2d.stride(0)), _ptr(v_geo), _ptr(v_colpack), _ptr(v_means),
+                                           _ptr(v_quats), _ptr(v_scales), _ptr(v_opac), _ptr(v_view), _stream()),
+                       "b2s_project_bwd")
+        v_colors = v_colpack[:, :d_in] if (ctx.has_colors and ctx.needs_input_grad[4]) else None
+        return (v_means, v_quats, v_scales, v_opac, v_colors, v_view) + (None,) * 12
+
+
+class _Blend(torch.autograd.Function):
+    """Per-tile front-to-back blend.  ``means2d`` is a formal input so ``retain_grad()`` / ``.absgrad`` work
+    exactly as with upstream (mtgs_scene_graph.py:666-667, 1171-1174)."""
+
+    @staticmethod
+    def forward(ctx, means2d, geo, colpack, offsets, flatten_ids, W, H, tile_w, tile_h, cdim, d_out, ed, absgrad):
+        lib = _lib.load()
+        dev = means2d.device
+        M = flatten_ids.shape[0]
+        render = torch.empty(1, H, W, d_out, dtype=torch.float32, device=dev)
+        alpha = torch.empty(1, H, W, 1, dtype=torch.float32, device=dev)
+        last_ids = torch.empty(H, W, dtype=torch.int32, device=dev)
+        with _timed("blend_fwd"):
+            _lib.check(lib.b2s_blend_fwd(_ptr(means2d), _ptr(geo), _ptr(colpack), _ptr(offsets), _ptr(flatten_ids),
+                                         M, W, H, tile_w, tile_h, cdim, d_out, int(ed), _ptr(render), _ptr(alpha),
+                                         _ptr(last_ids), _stream()), "b2s_blend_fwd")
+        ctx.save_for_backward(means2d, geo, colpack, offsets, flatten_ids, render, alpha, last_ids)
+        ctx.cfg = (W, H, tile_w, tile_h, cdim, d_out, ed, absgrad)
+        return render, alpha
+
+    @staticmethod
+    def backward(ctx, v_render, v_alpha):
+        lib = _lib.load()
+        means2d, geo, colpack, offsets, flatten_ids, render, alpha, last_ids = ctx.saved_tensors
+        W, H, tile_w, tile_h, cdim, d_out, ed, absgrad = ctx.cfg
+        dev = means2d.device
+        N = geo.shape[0]
+        M = flatten_ids.shape[0]
+        v_render = torch.zeros_like(render) if v_render is None else v_render.contiguous()
+        v_alpha = torch.zeros_like(alpha) if v_alpha is None else v_alpha.contiguous()
+        v_xyabs = torch.zeros(N, 4, dtype=torch.float32, device=dev)
+        v_geo = torch.zeros(N, 4, dtype=torch.float32, device=dev)
+        v_colpack = torch.zeros(N, cdim, dtype=torch.float32, device=dev)
+        with _timed("blend_bwd"):
+            _lib.check(lib.b2s_blend_bwd(_ptr(means2d), _ptr(geo), _ptr(colpack), _ptr(offsets), _ptr(flatten_ids),
+                                         M, W, H, tile_w, tile_h, cdim, d_out, int(ed), _ptr(render), _ptr(alpha),
+                                         _ptr(last_ids), _ptr(v_render), _ptr(v_alpha), _ptr(v_xyabs), _ptr(v_geo),
+                                         _ptr(v_colpack), _stream()), "b2s_blend_bwd")
+        if absgrad:
+            # upstream: `means2d.absgrad = v_means2d_abs` on the tensor object handed in by the caller
+            means2d.absgrad = v_xyabs[:, 2:4].unsqueeze(0)
+        return (v_xyabs[:, 0:2].unsqueeze(0), v_geo, v_colpack) + (None,) * 10
+
+
+# ------------------------------------------------------------------------------------------------
+def _bin(means2d: Tensor, radii: Tensor, depths: Tensor, tiles: Tensor, keys: Tensor, vals: Tensor, tile_w: int,
+         tile_h: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """Depth order + tile lists.  Returns (flatten_ids [M] int32, tile_keys [M] int32, offsets [th,tw] int32)."""
+    lib = _lib.load()
+    dev = means2d.device
+    N = radii.shape[0]
+    order = torch.empty(N, dtype=torch.int32, device=dev)
+    cum = torch.empty(N, dtype=torch.int32, device=dev)
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    wsb = int(lib.b2s_bin_depth_workspace_bytes(N))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    with _timed("bin_sort_depth"):
+        _lib.check(lib.b2s_bin_sort_depth(_ptr(keys), _ptr(vals), _ptr(tiles), N, _ptr(order), _ptr(cum),
+                                          _ptr(total), _ptr(ws), wsb, _stream()), "b2s_bin_sort_depth")
+    M = int(total.item())  # the one unavoidable device->host read: sizes the intersection buffers
+    if M >= 2 ** 31:
+        raise RuntimeError(f"{M} tile intersections exceed the int32 offset range (same limit as upstream)")
+    flatten_ids = torch.empty(M, dtype=torch.int32, device=dev)
+    tile_keys = torch.empty(M, dtype=torch.int32, device=dev)
+    offsets = torch.empty(tile_h, tile_w, dtype=torch.int32, device=dev)
+    wsb2 = int(lib.b2s_bin_tiles_workspace_bytes(N, M))
+    ws2 = torch.empty(wsb2, dtype=torch.uint8, device=dev)
+    with _timed("bin_tiles"):
+        _lib.check(lib.b2s_bin_tiles(_ptr(means2d), _ptr(radii), _ptr(order), _ptr(cum), N, M, 16, tile_w, tile_h,
+                                     _ptr(flatten_ids), _ptr(tile_keys), _ptr(offsets), _ptr(ws2), wsb2, _stream()),
+                   "b2s_bin_tiles")
+    return flatten_ids, tile_keys, offsets
+
+
+def _isect_ids(tile_keys: Tensor, flatten_ids: Tensor, depths: Tensor) -> Tensor:
+    lib = _lib.load()
+    M = flatten_ids.shape[0]
+    out = torch.empty(M, dtype=torch.int64, device=flatten_ids.device)
+    with torch.cuda.device(flatten_ids.device):
+        _lib.check(lib.b2s_bin_isect_ids(_ptr(tile_keys), _ptr(flatten_ids), _ptr(depths), M, _ptr(out), _stream()),
+                   "b2s_bin_isect_ids")
+    return out
+
+
+def _rasterize_one(means, quats, scales, opacities, colors, viewmat, K, width, height, near_plane, far_plane,
+                   radius_clip, eps2d, render_mode, absgrad, rasterize_mode):
+    N = means.shape[0]
+    with_depth = render_mode in ("RGB+D", "RGB+ED", "D", "ED")
+    ed = render_mode in ("RGB+ED", "ED")
+    cols = None if render_mode in ("D", "ED") else colors
+    d_in = 0 if cols is None else cols.shape[1]
+    d_out = d_in + (1 if with_depth else 0)
+    cdim = padded_channels(d_out)
+    tile_w = math.ceil(width / 16.0)
+    tile_h = math.ceil(height / 16.0)
+    calc_comp = rasterize_mode == "antialiased"
+    means2d, geo, colpack, radii, depths, tiles, keys, vals = _Project.apply(
+        means, quats, scales, opacities, cols, viewmat, K, width, height, tile_w, tile_h, float(eps2d),
+        float(near_plane), float(far_plane), float(radius_clip), calc_comp, with_depth, cdim)
+    flatten_ids, tile_keys, offsets = _bin(means2d, radii, depths, tiles, keys, vals, tile_w, tile_h)
+    render, alpha = _Blend.apply(means2d, geo, colpack, offsets, flatten_ids, width, height, tile_w, tile_h, cdim,
+                                 d_out, ed, bool(absgrad))
+    meta = dict(radii=radii.unsqueeze(0), means2d=means2d, depths=depths.unsqueeze(0),
+                conics=geo.detach()[:, :3].unsqueeze(0), opacities=geo.detach()[:, 3].unsqueeze(0),
+                tiles_per_gauss=tiles.unsqueeze(0), flatten_ids=flatten_ids, isect_offsets=offsets.unsqueeze(0),
+                tile_keys=tile_keys)
+    return render, alpha, meta
+
+
+def rasterization(
+    means: Tensor,  # [N, 3]
+    quats: Tensor,  # [N, 4]  (w, x, y, z)
+    scales: Tensor,  # [N, 3]
+    opacities: Tensor,  # [N]
+    colors: Tensor,  # [N, D] (or [N, K, 3] SH coefficients when sh_degree is given)
+    viewmats: Tensor,  # [C, 4, 4] world -> camera
+    Ks: Tensor,  # [C, 3, 3]
+    width: int,
+    height: int,
+    near_plane: float = 0.01,
+    far_plane: float = 1e10,
+    radius_clip: float = 0.0,
+    eps2d: float = 0.3,
+    sh_degree: Optional[int] = None,
+    packed: bool = True,
+    tile_size: int = 16,
+    backgrounds: Optional[Tensor] = None,
+    render_mode: str = "RGB",
+    sparse_grad: bool = False,
+    absgrad: bool = False,
+    rasterize_mode: str = "classic",
+    channel_chunk: int = 32,
+    distributed: bool = False,
+    camera_model: str = "pinhole",
+    covars: Optional[Tensor] = None,
+) -> Tuple[Tensor, Tensor, Dict]:
+    """Rasterize 3D Gaussians to ``(render_colors [C,H,W,D(+1)], render_alphas [C,H,W,1], meta)``.
+
+    Same contract as upstream for the argument combinations MTGS uses:
+    ``packed=False, tile_size=16, sparse_grad=False``, ``render_mode`` in RGB / RGB+D / RGB+ED / D / ED,
+    ``rasterize_mode`` classic / antialiased, optional ``absgrad`` and ``backgrounds``.  Other combinations
+    raise ``NotImplementedError`` (never a silent fallback).
+    """
+    N = means.shape[0]
+    C_ = viewmats.shape[0]
+    assert means.shape == (N, 3), means.shape
+    assert quats.shape == (N, 4), quats.shape
+    assert scales.shape == (N, 3), scales.shape
+    assert opacities.shape == (N,), opacities.shape
+    assert viewmats.shape == (C_, 4, 4), viewmats.shape
+    assert Ks.shape == (C_, 3, 3), Ks.shape
+    assert render_mode in ("RGB", "D", "ED", "RGB+D", "RGB+ED"), render_mode
+    assert rasterize_mode in ("classic", "antialiased"), rasterize_mode
+    if packed:
+        raise NotImplementedError("packed=True is not built (MTGS passes packed=False, mtgs_scene_graph.py:652)")
+    if tile_size != 16:
+        raise NotImplementedError("only tile_size=16 is built (MTGS: BLOCK_WIDTH = 16, mtgs_scene_graph.py:640)")
+    if sparse_grad or distributed or covars is not None or camera_model != "pinhole":
+        raise NotImplementedError("sparse_grad / distributed / covars / non-pinhole cameras are not built")
+    _need_cuda(means, quats, scales, opacities, colors, viewmats, Ks)
+    if sh_degree is None:
+        assert (colors.dim() == 2 and colors.shape[0] == N) or (colors.dim() == 3 and colors.shape[:2] == (C_, N)), \
+            colors.shape
+    else:
+        assert colors.dim() == 3 and colors.shape[0] == N and colors.shape[2] == 3, colors.shape
+        assert (sh_degree + 1) ** 2 <= colors.shape[1], colors.shape
+
+    means, quats, scales, opacities = _f32c(means), _f32c(quats), _f32c(scales), _f32c(opacities)
+    viewmats, Ks = _f32c(viewmats), _f32c(Ks)
+    renders, alphas, metas = [], [], []
+    with torch.cuda.device(means.device):
+        for c in range(C_):
+            if sh_degree is not None:
+                from .cuda._wrapper import spherical_harmonics
+                campos = torch.inverse(viewmats[c])[:3, 3]
+                dirs = means - campos
+                cols = torch.clamp_min(spherical_harmonics(sh_degree, dirs, colors) + 0.5, 0.0)
+            else:
+                cols = colors if colors.dim() == 2 else colors[c]
+            cols = _f32c(cols)
+            r, a, m = _rasterize_one(means, quats, scales, opacities, cols, viewmats[c], Ks[c], int(width),
+                                     int(height), near_plane, far_plane, radius_clip, eps2d, render_mode, absgrad,
+                                     rasterize_mode)
+            if backgrounds is not None and render_mode not in ("D", "ED"):
+                nb = backgrounds.shape[-1]
+                r = torch.cat([r[..., :nb] + (1.0 - a) * backgrounds[c].reshape(1, 1, 1, nb), r[..., nb:]], dim=-1)
+            renders.append(r)
+            alphas.append(a)
+            metas.append(m)
+
+    tile_w = math.ceil(width / 16.0)
+    tile_h = math.ceil(height / 16.0)
+    meta = Meta(tile_width=tile_w, tile_height=tile_h, width=width, height=height, tile_size=tile_size,
+                n_cameras=C_, camera_ids=None, gaussian_ids=None)
+    if C_ == 1:
+        m = metas[0]
+        meta.update({k: v for k, v in m.items() if k != "tile_keys"})
+        depths0 = m["depths"][0]
+        meta._lazy = lambda: _isect_ids(m["tile_keys"], m["flatten_ids"], depths0)
+        return renders[0], alphas[0], meta
+    # C > 1: per-camera results stacked; flatten_ids / offsets follow upstream's camera-major numbering
+    for k in ("radii", "means2d", "depths", "conics", "opacities", "tiles_per_gauss"):
+        meta[k] = torch.cat([m[k] for m in metas], dim=0)
+    m_before, offs = 0, []
+    for m in metas:
+        offs.append(m["isect_offsets"] + m_before)
+        m_before += m["flatten_ids"].shape[0]
+    meta["isect_offsets"] = torch.cat(offs, dim=0)
+    meta["flatten_ids"] = torch.cat([m["flatten_ids"] + c * N for c, m in enumerate(metas)], dim=0)
+    return torch.cat(renders, dim=0), torch.cat(alphas, dim=0), meta

@@ -301,3 +301,10 @@ def rasterization_fwd_bwd(*args, v_render=None, v_alpha=None, absgrad=False, **k
     ctx["meta_offs"], ctx["meta_flat"] = meta["isect_offsets"], meta["flatten_ids"]
     grads = rasterization_bwd(ctx, v_render, v_alpha, absgrad=absgrad) if v_render is not None else None
     return rc, ra, meta, grads
+
+
+def quat_to_rotmat(quats) -> np.ndarray:
+    q = _f32(quats)
+    out = np.zeros((q.shape[0], 3, 3), np.float32)
+    lib().orc_quat_to_rotmat(_p(q, _f), C.c_int(q.shape[0]), _p(out, _f))
+    return out

@@ -727,3 +727,9 @@ void orc_sh_bwd(int degree, const float *dirs, const float *coeffs, const uint8_
         v_dirs[3 * g + 2] = (float)((gn[2] - dotp * nz) * inorm);
     }
 }
+
+/* exposed for the golden-vector pin against the reference's own quat_to_rotmat
+ * (mtgs/scene_model/gaussian_model/utils.py:14-41, same (w,x,y,z) convention) */
+void orc_quat_to_rotmat(const float *quats, int N, float *R) {
+    for (int g = 0; g < N; ++g) quat_to_rotmat(quats + 4 * g, R + 9 * g);
+}
