@@ -56,7 +56,7 @@ int b2s_project_fwd(const float *means, const float *quats, const float *scales,
                     int calc_comp, int d_in, int with_depth, int cdim, int32_t *radii,
                     float *means2d, float *depths, float *geo, float *comps, float *colpack,
                     int32_t *tiles_per_gauss, uint32_t *sort_keys, uint32_t *sort_vals,
-                    b2s_stream_t stream);
+                    int32_t *tile_rects /* [N,2]: x0 | x1 << 16, y0 | y1 << 16 */, b2s_stream_t stream);
 
 /* upstream fully_fused_projection bwd fused with the opacity*compensation and
  * colour/depth un-packing VJPs.  v_means2d[g * v_means2d_stride + {0,1}] (stride 2, or 4 when it aliases
@@ -75,21 +75,20 @@ int b2s_project_bwd(const float *means, const float *quats, const float *scales,
  * Two-level formulation with identical results to the stable 64-bit sort:
  *   (1) b2s_bin_sort_depth : stable sort of Gaussians by depth key -> order[N];
  *       cum[i] = exclusive scan of tiles_per_gauss[order[i]];  *total (device int64) = M.
- *   (2) b2s_bin_tiles      : emit (tile, gaussian) in depth order, stable sort by tile ->
- *       flatten_ids[M], tile_keys[M] (sorted tile id per entry), isect_offsets[tile_h*tile_w].
+ *   (2) b2s_bin_tiles      : ordered bucket fill of the (tile, gaussian) intersections walking the
+ *       Gaussians in depth order -> flatten_ids[M], isect_offsets[tile_h*tile_w] (no sort of M items).
  *   (3) b2s_bin_isect_ids  : optional, rebuilds upstream's int64 isect_ids for inspection. */
 size_t b2s_bin_depth_workspace_bytes(int N);
 int b2s_bin_sort_depth(const uint32_t *sort_keys, const uint32_t *sort_vals,
                        const int32_t *tiles_per_gauss, int N, int32_t *order, int32_t *cum,
                        int64_t *total, void *workspace, size_t workspace_bytes,
                        b2s_stream_t stream);
-size_t b2s_bin_tiles_workspace_bytes(int N, long long M);
-int b2s_bin_tiles(const float *means2d, const int32_t *radii, const int32_t *order,
-                  const int32_t *cum, int N, long long M, int tile_size, int tile_w, int tile_h,
-                  int32_t *flatten_ids, uint32_t *tile_keys, int32_t *isect_offsets,
-                  void *workspace, size_t workspace_bytes, b2s_stream_t stream);
-int b2s_bin_isect_ids(const uint32_t *tile_keys, const int32_t *flatten_ids, const float *depths,
-                      long long M, int64_t *isect_ids, b2s_stream_t stream);
+size_t b2s_bin_tiles_workspace_bytes(int N, long long M, int tile_w, int tile_h);
+int b2s_bin_tiles(const int32_t *tile_rects, const int32_t *order, const int32_t *cum, int N, long long M, int tile_size, int tile_w, int tile_h,
+                  int32_t *flatten_ids, int32_t *isect_offsets, void *workspace,
+                  size_t workspace_bytes, b2s_stream_t stream);
+int b2s_bin_isect_ids(const int32_t *isect_offsets, int n_tiles, const int32_t *flatten_ids,
+                      const float *depths, long long M, int64_t *isect_ids, b2s_stream_t stream);
 
 /* ---- alpha blending (upstream rasterize_to_pixels fwd / bwd; A.3, A.4) ----
  * cdim in {4, 8}; d_out = channels written per pixel (<= cdim); expected_depth != 0 divides channel

@@ -8,10 +8,9 @@
 // bits)", ties in emission order (= ascending Gaussian id).  A stable sort by a composite key equals a
 // stable sort by the minor key followed by a stable sort by the major key, and all intersections of one
 // Gaussian share its depth, so:
-//   1. stable LSD radix sort of the N Gaussians by their 32 depth bits        (N items, 8 B each)
-//   2. emit (tile, gaussian) pairs walking Gaussians in that order            (M items, written once)
-//   3. stable LSD radix sort of the M pairs by tile id only (<= 16 bits -> 2 passes instead of 6)
-// gives bit-identical flatten_ids / isect_offsets while moving ~1/3 of the bytes of the 64-bit sort.
+//   1. stable LSD radix sort of the N Gaussians by their 32 depth bits        (this file; N items, 8 B each)
+//   2. ordered bucket fill of the M (tile, gaussian) intersections by tile    (tilelists.cu; M items written once)
+// gives bit-identical flatten_ids / isect_offsets without ever sorting M 64-bit keys.
 // isect_ids (int64) are not needed by the blend; b2s_bin_isect_ids rebuilds them on request.
 //
 // All kernels are HBM/L2-bound integer work: coalesced 4-byte streams, warp-match ranking, no tensor cores.
@@ -107,10 +106,10 @@ k_scan_down(const int32_t *in, const int32_t *__restrict__ gather, int n,
     }
 }
 
-static inline size_t scan_ws_ints(int n) { return (size_t)b2s_div_up(n > 0 ? n : 1, SCAN_TILE) + 1; }
+size_t b2s_scan_ws_ints(int n) { return (size_t)b2s_div_up(n > 0 ? n : 1, SCAN_TILE) + 1; }
 
-// exclusive scan of in[gather[i]] (or in[i]) into out; ws needs scan_ws_ints(n) ints
-static int device_excl_scan(const int32_t *in, const int32_t *gather, int n, int32_t *out, int64_t *total_out,
+// exclusive scan of in[gather[i]] (or in[i]) into out; ws needs b2s_scan_ws_ints(n) ints
+int b2s_device_excl_scan(const int32_t *in, const int32_t *gather, int n, int32_t *out, int64_t *total_out,
                             int32_t *ws, cudaStream_t st) {
     int nb = b2s_div_up(n, SCAN_TILE);
     k_scan_reduce<<<nb, SCAN_THREADS, 0, st>>>(in, gather, n, ws);
@@ -210,7 +209,7 @@ static inline int radix_nblocks(long long n) { return b2s_div_up(n > 0 ? n : 1, 
 // ints needed: table (256 * nblocks) + scan workspace for that table
 static inline size_t radix_ws_ints(long long n) {
     size_t nb = (size_t)radix_nblocks(n);
-    return nb * RDX_BINS + scan_ws_ints((int)(nb * RDX_BINS));
+    return nb * RDX_BINS + b2s_scan_ws_ints((int)(nb * RDX_BINS));
 }
 
 static int radix_pass(const uint32_t *kin, const uint32_t *vin, uint32_t *kout, uint32_t *vout, long long n,
@@ -220,7 +219,7 @@ static int radix_pass(const uint32_t *kin, const uint32_t *vin, uint32_t *kout, 
     int32_t *scan_ws = ws + (size_t)nb * RDX_BINS;
     k_radix_hist<<<nb, RDX_THREADS, 0, st>>>(kin, n, shift, table, nb);
     B2S_LAUNCH_CHECK();
-    int rc = device_excl_scan(table, nullptr, nb * RDX_BINS, table, nullptr, scan_ws, st);
+    int rc = b2s_device_excl_scan(table, nullptr, nb * RDX_BINS, table, nullptr, scan_ws, st);
     if (rc != B2S_OK) return rc;
     k_radix_scatter<<<nb, RDX_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift, table, nb);
     B2S_LAUNCH_CHECK();
@@ -235,7 +234,7 @@ static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 extern "C" size_t b2s_bin_depth_workspace_bytes(int N) {
     size_t n = (size_t)(N > 0 ? N : 1);
     // key ping, key pong, val pong  + radix table/scan ints + scan ints
-    return 3 * align256(n * 4) + align256(radix_ws_ints(N) * 4) + align256(scan_ws_ints(N) * 4) + 1024;
+    return 3 * align256(n * 4) + align256(radix_ws_ints(N) * 4) + align256(b2s_scan_ws_ints(N) * 4) + 1024;
 }
 
 extern "C" int b2s_bin_sort_depth(const uint32_t *sort_keys, const uint32_t *sort_vals,
@@ -262,151 +261,6 @@ extern "C" int b2s_bin_sort_depth(const uint32_t *sort_keys, const uint32_t *sor
     rc = radix_pass(kB, vB, kA, vA, N, 8, rws, st);                if (rc) return rc;
     rc = radix_pass(kA, vA, kB, vB, N, 16, rws, st);               if (rc) return rc;
     rc = radix_pass(kB, vB, kA, vA, N, 24, rws, st);               if (rc) return rc;
-    return device_excl_scan(tiles_per_gauss, order, N, cum, total, sws, st);
+    return b2s_device_excl_scan(tiles_per_gauss, order, N, cum, total, sws, st);
 }
 
-// ------------------------------------------------------------------------------------------------
-// step 2: emit (tile, gaussian) in depth order, stable sort by tile, offsets
-// ------------------------------------------------------------------------------------------------
-// one warp per 32 consecutive depth-ordered Gaussians; lanes stride over the tiles of each rectangle so that
-// the writes of one Gaussian are contiguous (upstream isect_tiles pass 2 emission order: row-major).
-__global__ void __launch_bounds__(256)
-k_emit(const float2 *__restrict__ means2d, const int32_t *__restrict__ radii, const int32_t *__restrict__ order,
-       const int32_t *__restrict__ cum, int N, int tile_w, int tile_h, uint32_t *__restrict__ tile_out,
-       uint32_t *__restrict__ gid_out) {
-    const int lane = threadIdx.x & 31;
-    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int i = gwarp * 32 + lane;
-    int g = -1, x0 = 0, y0 = 0, wdt = 0, cnt = 0, start = 0;
-    if (i < N) {
-        g = order[i];
-        int r = radii[g];
-        if (r > 0) {
-            float2 m = means2d[g];
-            float tr = __fdiv_rn((float)r, 16.0f);
-            float txc = __fdiv_rn(m.x, 16.0f), tyc = __fdiv_rn(m.y, 16.0f);
-            float fx0 = floorf(__fsub_rn(txc, tr)), fy0 = floorf(__fsub_rn(tyc, tr));
-            float fx1 = ceilf(__fadd_rn(txc, tr)), fy1 = ceilf(__fadd_rn(tyc, tr));
-            x0 = fx0 <= 0.f ? 0 : (fx0 >= (float)tile_w ? tile_w : (int)fx0);
-            y0 = fy0 <= 0.f ? 0 : (fy0 >= (float)tile_h ? tile_h : (int)fy0);
-            int x1 = fx1 <= 0.f ? 0 : (fx1 >= (float)tile_w ? tile_w : (int)fx1);
-            int y1 = fy1 <= 0.f ? 0 : (fy1 >= (float)tile_h ? tile_h : (int)fy1);
-            wdt = x1 - x0;
-            cnt = (y1 - y0) * wdt;
-            start = cum[i];
-        }
-    }
-    unsigned any = __ballot_sync(0xffffffffu, cnt > 0);
-    while (any) {
-        int src = __ffs(any) - 1;
-        any &= any - 1;
-        int c = __shfl_sync(0xffffffffu, cnt, src);
-        int sx0 = __shfl_sync(0xffffffffu, x0, src);
-        int sy0 = __shfl_sync(0xffffffffu, y0, src);
-        int sw = __shfl_sync(0xffffffffu, wdt, src);
-        int sst = __shfl_sync(0xffffffffu, start, src);
-        int sg = __shfl_sync(0xffffffffu, g, src);
-        for (int k = lane; k < c; k += 32) {
-            int ty = sy0 + k / sw, tx = sx0 + k % sw;
-            tile_out[sst + k] = (uint32_t)(ty * tile_w + tx);
-            gid_out[sst + k] = (uint32_t)sg;
-        }
-    }
-}
-
-// upstream isect_offset_encode on the sorted tile keys
-__global__ void __launch_bounds__(256)
-k_offsets(const uint32_t *__restrict__ tile_keys, long long M, int n_tiles, int32_t *__restrict__ offsets) {
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= M) return;
-    int cur = (int)tile_keys[idx];
-    if (idx == 0) {
-        for (int t = 0; t <= cur; ++t) offsets[t] = 0;
-    } else {
-        int prev = (int)tile_keys[idx - 1];
-        for (int t = prev + 1; t <= cur; ++t) offsets[t] = (int32_t)idx;
-    }
-    if (idx == M - 1) {
-        for (int t = cur + 1; t < n_tiles; ++t) offsets[t] = (int32_t)M;
-    }
-}
-
-static inline int tile_passes(int n_tiles) {
-    int bits = 0;
-    while ((1LL << bits) < (long long)n_tiles) ++bits;  // ids in [0, n_tiles)
-    return bits <= 8 ? 1 : (bits <= 16 ? 2 : (bits <= 24 ? 3 : 4));
-}
-
-extern "C" size_t b2s_bin_tiles_workspace_bytes(int N, long long M) {
-    (void)N;
-    size_t m = (size_t)(M > 0 ? M : 1);
-    // tile ping, gid ping, gid pong (+ tile pong is the caller's tile_keys) + radix ints
-    return 3 * align256(m * 4) + align256(radix_ws_ints(M) * 4) + 1024;
-}
-
-extern "C" int b2s_bin_tiles(const float *means2d, const int32_t *radii, const int32_t *order,
-                             const int32_t *cum, int N, long long M, int tile_size, int tile_w, int tile_h,
-                             int32_t *flatten_ids, uint32_t *tile_keys, int32_t *isect_offsets, void *workspace,
-                             size_t workspace_bytes, b2s_stream_t stream) {
-    if (N < 0 || M < 0 || M >= (1LL << 31)) return B2S_ERR_ARG;
-    if (tile_size != 16) return B2S_ERR_UNSUPPORTED;
-    if (workspace_bytes < b2s_bin_tiles_workspace_bytes(N, M)) return B2S_ERR_WORKSPACE;
-    cudaStream_t st = (cudaStream_t)stream;
-    int n_tiles = tile_w * tile_h;
-    if (M == 0 || N == 0) {
-        cudaMemsetAsync(isect_offsets, 0, sizeof(int32_t) * (size_t)n_tiles, st);
-        return B2S_OK;
-    }
-    char *w = (char *)workspace;
-    size_t m4 = align256((size_t)M * 4);
-    uint32_t *tA = (uint32_t *)w; w += m4;
-    uint32_t *gA = (uint32_t *)w; w += m4;
-    uint32_t *gB = (uint32_t *)w; w += m4;
-    int32_t *rws = (int32_t *)w;
-    uint32_t *tOut = tile_keys;
-    uint32_t *gOut = (uint32_t *)flatten_ids;
-    int passes = tile_passes(n_tiles);
-    // choose the emit target so that the last pass writes (tile_keys, flatten_ids)
-    //   1 pass : emit -> (tA,gA) ; pass0 -> out
-    //   2 pass : emit -> (tA,gA) ; pass0 -> (tOut?,..)   we need ping-pong: A -> B -> A ...
-    // buffers: A = (tA, gA), B = (tOut, gB) for intermediate; final must be (tOut, gOut).
-    // odd #passes : emit->A, A->OUT                      (1) ; emit->A, A->B', B'->A, A->OUT (3, B'=(tOut,gB))
-    // even #passes: emit->B', B'->A, A->OUT              (2) ; ...
-    uint32_t *tk[2] = {tA, tOut};
-    uint32_t *gk[2] = {gA, gB};
-    int cur = (passes % 2 == 1) ? 0 : 1;
-    k_emit<<<b2s_div_up(N, 256), 256, 0, st>>>((const float2 *)means2d, radii, order, cum, N, tile_w, tile_h,
-                                                   tk[cur], gk[cur]);
-    B2S_LAUNCH_CHECK();
-    for (int p = 0; p < passes; ++p) {
-        int nxt = cur ^ 1;
-        bool last = (p == passes - 1);
-        uint32_t *to = last ? tOut : tk[nxt];
-        uint32_t *go = last ? gOut : gk[nxt];
-        int rc = radix_pass(tk[cur], gk[cur], to, go, M, 8 * p, rws, st);
-        if (rc) return rc;
-        cur = nxt;
-    }
-    k_offsets<<<b2s_div_up(M, 256), 256, 0, st>>>(tile_keys, M, n_tiles, isect_offsets);
-    B2S_LAUNCH_CHECK();
-    return B2S_OK;
-}
-
-__global__ void __launch_bounds__(256)
-k_isect_ids(const uint32_t *__restrict__ tile_keys, const int32_t *__restrict__ flatten_ids,
-            const float *__restrict__ depths, long long M, int64_t *__restrict__ isect_ids) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= M) return;
-    // upstream: (cam << (32 + tile_bits)) | (tile << 32) | (int64)(int32 view of depth); cam = 0
-    int32_t dbits = __float_as_int(depths[flatten_ids[i]]);
-    isect_ids[i] = ((int64_t)tile_keys[i] << 32) | (int64_t)dbits;
-}
-
-extern "C" int b2s_bin_isect_ids(const uint32_t *tile_keys, const int32_t *flatten_ids, const float *depths,
-                                 long long M, int64_t *isect_ids, b2s_stream_t stream) {
-    if (M < 0) return B2S_ERR_ARG;
-    if (M == 0) return B2S_OK;
-    k_isect_ids<<<b2s_div_up(M, 256), 256, 0, (cudaStream_t)stream>>>(tile_keys, flatten_ids, depths, M, isect_ids);
-    B2S_LAUNCH_CHECK();
-    return B2S_OK;
-}

@@ -235,7 +235,7 @@ __device__ __forceinline__ void pixel_grad(float (&v)[16], float &T, float (&buf
                                            const float vra, const float Tf, const float (&col)[CDIM], const float A,
                                            const float B, const float C, const float opac, const float dx,
                                            const float dy, const float alpha, const float vis) {
-    const float ra = 1.0f / (1.0f - alpha);
+    const float ra = rcp_approx(1.0f - alpha);  // alpha <= 0.999: well conditioned, 1 ulp is ample
     T *= ra;
     const float fac = alpha * T;
     float v_alpha = 0.f;

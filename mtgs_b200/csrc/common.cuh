@@ -56,3 +56,9 @@ __device__ __forceinline__ float4 ldg_stream4(const float4 *p) {
                  : "l"(p));
     return v;
 }
+
+// device-wide exclusive scan of int32 (binning.cu); `in` may alias `out`; gather may be null.
+// ws must hold b2s_scan_ws_ints(n) ints.  Grand total (int64) is written to *total_out when non-null.
+size_t b2s_scan_ws_ints(int n);
+int b2s_device_excl_scan(const int32_t *in, const int32_t *gather, int n, int32_t *out, int64_t *total_out,
+                         int32_t *ws, cudaStream_t st);

@@ -96,7 +96,7 @@ k_project_fwd(const float *__restrict__ means, const float *__restrict__ quats, 
               int d_in, int with_depth, int32_t *__restrict__ radii, float2 *__restrict__ means2d,
               float *__restrict__ depths, float4 *__restrict__ geo, float *__restrict__ comps,
               float *__restrict__ colpack, int32_t *__restrict__ tiles_per_gauss,
-              uint32_t *__restrict__ sort_keys, uint32_t *__restrict__ sort_vals) {
+              uint32_t *__restrict__ sort_keys, uint32_t *__restrict__ sort_vals, int2 *__restrict__ tile_rects) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= N) return;
     CamParams cam;
@@ -110,6 +110,7 @@ k_project_fwd(const float *__restrict__ means, const float *__restrict__ quats, 
 
     int32_t radius_i = 0;
     int32_t ntiles = 0;
+    int2 rect = make_int2(0, 0);  // (x0 | x1 << 16, y0 | y1 << 16) in tiles, max exclusive
     float mx = 0.f, my = 0.f, ca = 0.f, cb = 0.f, cc = 0.f, comp = 1.f;
     float z = pc[2];
     bool ok = !(z < near_plane || z > far_plane);
@@ -167,11 +168,13 @@ k_project_fwd(const float *__restrict__ means, const float *__restrict__ quats, 
                 int x1 = fx1 <= 0.f ? 0 : (fx1 >= (float)tile_w ? tile_w : (int)fx1);
                 int y1 = fy1 <= 0.f ? 0 : (fy1 >= (float)tile_h ? tile_h : (int)fy1);
                 ntiles = (y1 - y0) * (x1 - x0);
+                rect = make_int2(x0 | (x1 << 16), y0 | (y1 << 16));
             }
         }
     }
     radii[g] = radius_i;
     tiles_per_gauss[g] = ntiles;
+    tile_rects[g] = rect;
     sort_keys[g] = radius_i > 0 ? __float_as_uint(z) : 0xFFFFFFFFu;
     sort_vals[g] = (uint32_t)g;
     if (radius_i > 0) {
@@ -197,6 +200,15 @@ k_project_fwd(const float *__restrict__ means, const float *__restrict__ quats, 
         float4 *dst = reinterpret_cast<float4 *>(colpack + (size_t)g * CDIM);
 #pragma unroll
         for (int k = 0; k < CDIM / 4; ++k) dst[k] = make_float4(cp[4 * k], cp[4 * k + 1], cp[4 * k + 2], cp[4 * k + 3]);
+    } else {
+        // culled rows are never read by the blend; define them (zeros) so callers need no memset pass
+        if (calc_comp) comps[g] = 0.f;
+        means2d[g] = make_float2(0.f, 0.f);
+        depths[g] = 0.f;
+        geo[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 *dst = reinterpret_cast<float4 *>(colpack + (size_t)g * CDIM);
+#pragma unroll
+        for (int k = 0; k < CDIM / 4; ++k) dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 
@@ -428,9 +440,10 @@ extern "C" int b2s_project_fwd(const float *means, const float *quats, const flo
                                float eps2d, float near_plane, float far_plane, float radius_clip, int calc_comp,
                                int d_in, int with_depth, int cdim, int32_t *radii, float *means2d, float *depths,
                                float *geo, float *comps, float *colpack, int32_t *tiles_per_gauss,
-                               uint32_t *sort_keys, uint32_t *sort_vals, b2s_stream_t stream) {
+                               uint32_t *sort_keys, uint32_t *sort_vals, int32_t *tile_rects,
+                               b2s_stream_t stream) {
     if (N < 0 || W <= 0 || H <= 0) return B2S_ERR_ARG;
-    if (tile_size != 16) return B2S_ERR_UNSUPPORTED;
+    if (tile_size != 16 || tile_w > 32767 || tile_h > 32767) return B2S_ERR_UNSUPPORTED;
     if (cdim != 4 && cdim != 8) return B2S_ERR_UNSUPPORTED;
     if (d_in < 0 || d_in + (with_depth ? 1 : 0) > cdim) return B2S_ERR_ARG;
     if (calc_comp && comps == nullptr) return B2S_ERR_ARG;
@@ -441,7 +454,8 @@ extern "C" int b2s_project_fwd(const float *means, const float *quats, const flo
     k_project_fwd<CD><<<grid, block, 0, st>>>(means, quats, scales, opacities, colors_in, viewmat, K, N, W, H, \
                                               tile_w, tile_h, eps2d, near_plane, far_plane, radius_clip,     \
                                               calc_comp, d_in, with_depth, radii, (float2 *)means2d, depths, \
-                                              (float4 *)geo, comps, colpack, tiles_per_gauss, sort_keys, sort_vals)
+                                              (float4 *)geo, comps, colpack, tiles_per_gauss, sort_keys, sort_vals, \
+                                              (int2 *)tile_rects)
     if (cdim == 4) LAUNCH(4);
     else LAUNCH(8);
 #undef LAUNCH

@@ -101,26 +101,28 @@ class _Project(torch.autograd.Function):
         d_in = 0 if colors is None else colors.shape[1]
         dev = means.device
         radii = torch.empty(N, dtype=torch.int32, device=dev)
-        # culled rows are never written by the kernel: zero-fill so every returned value is defined
-        means2d = torch.zeros(1, N, 2, dtype=torch.float32, device=dev)
-        depths = torch.zeros(N, dtype=torch.float32, device=dev)
-        geo = torch.zeros(N, 4, dtype=torch.float32, device=dev)
-        comps = torch.zeros(N, dtype=torch.float32, device=dev) if calc_comp else None
-        colpack = torch.zeros(N, cdim, dtype=torch.float32, device=dev)
+        # every row is written by the kernel (zeros for culled Gaussians): no memset passes
+        means2d = torch.empty(1, N, 2, dtype=torch.float32, device=dev)
+        depths = torch.empty(N, dtype=torch.float32, device=dev)
+        geo = torch.empty(N, 4, dtype=torch.float32, device=dev)
+        comps = torch.empty(N, dtype=torch.float32, device=dev) if calc_comp else None
+        colpack = torch.empty(N, cdim, dtype=torch.float32, device=dev)
         tiles = torch.empty(N, dtype=torch.int32, device=dev)
         keys = torch.empty(N, dtype=torch.int32, device=dev)
         vals = torch.empty(N, dtype=torch.int32, device=dev)
+        rects = torch.empty(N, 2, dtype=torch.int32, device=dev)
         with _timed("project_fwd"):
             _lib.check(lib.b2s_project_fwd(_ptr(means), _ptr(quats), _ptr(scales), _ptr(opacities), _ptr(colors),
                                            _ptr(viewmat), _ptr(K), N, W, H, 16, tile_w, tile_h, eps2d, near, far,
                                            radius_clip, int(calc_comp), d_in, int(with_depth), cdim, _ptr(radii),
                                            _ptr(means2d), _ptr(depths), _ptr(geo), _ptr(comps), _ptr(colpack),
-                                           _ptr(tiles), _ptr(keys), _ptr(vals), _stream()), "b2s_project_fwd")
+                                           _ptr(tiles), _ptr(keys), _ptr(vals), _ptr(rects), _stream()),
+                       "b2s_project_fwd")
         ctx.save_for_backward(means, quats, scales, opacities, viewmat, K, radii, geo, comps)
         ctx.cfg = (W, H, eps2d, calc_comp, d_in, with_depth, cdim)
         ctx.has_colors = colors is not None
-        ctx.mark_non_differentiable(radii, depths, tiles, keys, vals)
-        return means2d, geo, colpack, radii, depths, tiles, keys, vals
+        ctx.mark_non_differentiable(radii, depths, tiles, keys, vals, rects)
+        return means2d, geo, colpack, radii, depths, tiles, keys, vals, rects
 
     @staticmethod
     def backward(ctx, v_means2d, v_geo, v_colpack, *_unused):
@@ -199,12 +201,11 @@ class _Blend(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------
-def _bin(means2d: Tensor, radii: Tensor, depths: Tensor, tiles: Tensor, keys: Tensor, vals: Tensor, tile_w: int,
-         tile_h: int) -> Tuple[Tensor, Tensor, Tensor]:
-    """Depth order + tile lists.  Returns (flatten_ids [M] int32, tile_keys [M] int32, offsets [th,tw] int32)."""
+def _bin(rects: Tensor, tiles: Tensor, keys: Tensor, vals: Tensor, tile_w: int, tile_h: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """Depth order + tile lists.  Returns (flatten_ids [M] int32, offsets [th,tw] int32)."""
     lib = _lib.load()
-    dev = means2d.device
-    N = radii.shape[0]
+    dev = rects.device
+    N = tiles.shape[0]
     order = torch.empty(N, dtype=torch.int32, device=dev)
     cum = torch.empty(N, dtype=torch.int32, device=dev)
     total = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -217,24 +218,25 @@ def _bin(means2d: Tensor, radii: Tensor, depths: Tensor, tiles: Tensor, keys: Te
     if M >= 2 ** 31:
         raise RuntimeError(f"{M} tile intersections exceed the int32 offset range (same limit as upstream)")
     flatten_ids = torch.empty(M, dtype=torch.int32, device=dev)
-    tile_keys = torch.empty(M, dtype=torch.int32, device=dev)
     offsets = torch.empty(tile_h, tile_w, dtype=torch.int32, device=dev)
-    wsb2 = int(lib.b2s_bin_tiles_workspace_bytes(N, M))
+    wsb2 = int(lib.b2s_bin_tiles_workspace_bytes(N, M, tile_w, tile_h))
+    if wsb2 == 0:
+        raise NotImplementedError(f"tile grid {tile_w}x{tile_h} not supported")
     ws2 = torch.empty(wsb2, dtype=torch.uint8, device=dev)
     with _timed("bin_tiles"):
-        _lib.check(lib.b2s_bin_tiles(_ptr(means2d), _ptr(radii), _ptr(order), _ptr(cum), N, M, 16, tile_w, tile_h,
-                                     _ptr(flatten_ids), _ptr(tile_keys), _ptr(offsets), _ptr(ws2), wsb2, _stream()),
+        _lib.check(lib.b2s_bin_tiles(_ptr(rects), _ptr(order), _ptr(cum), N, M, 16, tile_w, tile_h,
+                                     _ptr(flatten_ids), _ptr(offsets), _ptr(ws2), wsb2, _stream()),
                    "b2s_bin_tiles")
-    return flatten_ids, tile_keys, offsets
+    return flatten_ids, offsets
 
 
-def _isect_ids(tile_keys: Tensor, flatten_ids: Tensor, depths: Tensor) -> Tensor:
+def _isect_ids(offsets: Tensor, flatten_ids: Tensor, depths: Tensor) -> Tensor:
     lib = _lib.load()
     M = flatten_ids.shape[0]
     out = torch.empty(M, dtype=torch.int64, device=flatten_ids.device)
     with torch.cuda.device(flatten_ids.device):
-        _lib.check(lib.b2s_bin_isect_ids(_ptr(tile_keys), _ptr(flatten_ids), _ptr(depths), M, _ptr(out), _stream()),
-                   "b2s_bin_isect_ids")
+        _lib.check(lib.b2s_bin_isect_ids(_ptr(offsets), offsets.numel(), _ptr(flatten_ids), _ptr(depths), M, _ptr(out),
+                                         _stream()), "b2s_bin_isect_ids")
     return out
 
 
@@ -250,16 +252,15 @@ def _rasterize_one(means, quats, scales, opacities, colors, viewmat, K, width, h
     tile_w = math.ceil(width / 16.0)
     tile_h = math.ceil(height / 16.0)
     calc_comp = rasterize_mode == "antialiased"
-    means2d, geo, colpack, radii, depths, tiles, keys, vals = _Project.apply(
+    means2d, geo, colpack, radii, depths, tiles, keys, vals, rects = _Project.apply(
         means, quats, scales, opacities, cols, viewmat, K, width, height, tile_w, tile_h, float(eps2d),
         float(near_plane), float(far_plane), float(radius_clip), calc_comp, with_depth, cdim)
-    flatten_ids, tile_keys, offsets = _bin(means2d, radii, depths, tiles, keys, vals, tile_w, tile_h)
+    flatten_ids, offsets = _bin(rects, tiles, keys, vals, tile_w, tile_h)
     render, alpha = _Blend.apply(means2d, geo, colpack, offsets, flatten_ids, width, height, tile_w, tile_h, cdim,
                                  d_out, ed, bool(absgrad))
     meta = dict(radii=radii.unsqueeze(0), means2d=means2d, depths=depths.unsqueeze(0),
                 conics=geo.detach()[:, :3].unsqueeze(0), opacities=geo.detach()[:, 3].unsqueeze(0),
-                tiles_per_gauss=tiles.unsqueeze(0), flatten_ids=flatten_ids, isect_offsets=offsets.unsqueeze(0),
-                tile_keys=tile_keys)
+                tiles_per_gauss=tiles.unsqueeze(0), flatten_ids=flatten_ids, isect_offsets=offsets.unsqueeze(0))
     return render, alpha, meta
 
 
@@ -350,9 +351,9 @@ def rasterization(
                 n_cameras=C_, camera_ids=None, gaussian_ids=None)
     if C_ == 1:
         m = metas[0]
-        meta.update({k: v for k, v in m.items() if k != "tile_keys"})
+        meta.update(m)
         depths0 = m["depths"][0]
-        meta._lazy = lambda: _isect_ids(m["tile_keys"], m["flatten_ids"], depths0)
+        meta._lazy = lambda: _isect_ids(m["isect_offsets"][0].contiguous(), m["flatten_ids"], depths0)
         return renders[0], alphas[0], meta
     # C > 1: per-camera results stacked; flatten_ids / offsets follow upstream's camera-major numbering
     for k in ("radii", "means2d", "depths", "conics", "opacities", "tiles_per_gauss"):
