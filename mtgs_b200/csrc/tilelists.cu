@@ -22,12 +22,14 @@
 //     exclusive scan IS isect_offsets; pass 2 (k_tile_fill) writes flatten_ids.
 // Work ~ (rows covered by the rectangles) ~ M / mean width instead of M; M x 4 B written once.
 // Integer work, issue-bound at full occupancy; no tensor cores.
+#include <cstdlib>
+
 #include "common.cuh"
 
 constexpr int TR_MAX_ROWS = 24;  // tile rows per band = warps per CTA
 constexpr int TR_NG = 4;         // 32-tile column groups per lane -> 128 tile columns per band
 constexpr int TR_COST_C = 16;    // chunk cost = tiles + TR_COST_C per Gaussian
-constexpr int TR_TARGET_CTAS = 148 * 3;
+constexpr int TR_TARGET_CTAS = 148 * 12;  // chunks per band: rows near the horizon carry most hits, so many short chunks
 
 // f(i) = cum[i] + c * i is the cost of the stream before Gaussian i; first i in [0, nv) with f(i) >= target, else nv
 __device__ __forceinline__ int lower_bound_cost(const int32_t *__restrict__ cum, int nv, long long c, long long target) {
@@ -264,7 +266,12 @@ static TlPlan tl_plan(int N, int tile_w, int tile_h) {
     p.rows_per_band = (tile_h + p.row_bands - 1) / p.row_bands;  // ... evenly split (1080p: 4 x 17)
     p.col_bands = (tile_w + 32 * TR_NG - 1) / (32 * TR_NG);
     int bands = p.row_bands * p.col_bands;
-    int r = TR_TARGET_CTAS / bands;
+    static const int target_ctas = [] {  // tuning knob (read once): B2S_TL_CTAS overrides the CTA budget
+        const char *e = getenv("B2S_TL_CTAS");
+        int v = e ? atoi(e) : 0;
+        return v > 0 ? v : TR_TARGET_CTAS;
+    }();
+    int r = target_ctas / bands;
     int by_work = N / 512;  // no point in chunks shorter than a batch
     if (r > by_work) r = by_work;
     if (r > 1023) r = 1023;
