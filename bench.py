@@ -124,6 +124,7 @@ def run_cpu_port(args, scene, vcfg, sample_n, steps, warmup):
     """Times the CPU oracle port (fwd+bwd) on `sample_n` Gaussians of the same scene; returns Gaussians/s."""
     from oracle import cpu_ref
     cpu_ref.build()
+    cpu_ref.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: use every host core
     rng = np.random.default_rng(123)
     idx = np.sort(rng.choice(scene["means"].shape[0], size=sample_n, replace=False)) if sample_n < scene["means"].shape[0] \
         else np.arange(scene["means"].shape[0])
@@ -355,6 +356,43 @@ def main():
         except Exception as e:  # pragma: no cover
             cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
 
+    # ---- HBM-bound stages: achieved algorithmic GB/s of the streaming kernels + the SH operator (row a9)
+    hbm_stages = {}
+    for k in ("project_fwd", "project_bwd"):
+        if k in stage_ms:
+            gbs = stage_bytes[k] / (stage_ms[k] * 1e-3) / 1e9
+            hbm_stages[k] = {"ms": stage_ms[k], "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peak}
+    try:
+        from mtgs_b200.cuda._wrapper import spherical_harmonics
+        K_sh = 16
+        dirs = torch.randn(N, 3, device=dev)
+        coeffs = torch.randn(N, K_sh, 3, device=dev, requires_grad=True)
+        w3 = torch.randn(N, 3, device=dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        t_f = t_b = 0.0
+        reps = 6
+        for it in range(reps + 2):
+            coeffs.grad = None
+            ev[0].record()
+            out = spherical_harmonics(3, dirs, coeffs)
+            ev[1].record()
+            out.backward(w3)
+            ev[2].record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                t_f += ev[0].elapsed_time(ev[1])
+                t_b += ev[1].elapsed_time(ev[2])
+        t_f, t_b = t_f / reps, t_b / reps
+        b_f = N * (12 + 12 * K_sh + 12)
+        b_b = N * (12 + 12 + 12 * K_sh)  # dirs + v_colors in, v_coeffs out (dirs need no grad: coeffs are not re-read)
+        hbm_stages["sh_fwd_deg3"] = {"ms": t_f, "algorithmic_GBps": b_f / (t_f * 1e-3) / 1e9,
+                                     "frac_of_hbm_peak": b_f / (t_f * 1e-3) / 1e9 / peak}
+        hbm_stages["sh_bwd_deg3"] = {"ms": t_b, "algorithmic_GBps": b_b / (t_b * 1e-3) / 1e9,
+                                     "frac_of_hbm_peak": b_b / (t_b * 1e-3) / 1e9 / peak}
+        del dirs, coeffs, w3, out
+    except Exception as e:  # pragma: no cover
+        hbm_stages["sh_error"] = str(e)
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "impl": "ours",
@@ -362,7 +400,7 @@ def main():
             "roofline_step": {"algorithmic_bytes": ab["total"], "frac_of_hbm_peak": step_frac,
                               "bytes_per_gaussian": ab["total"] / N},
             "cpu_baseline": cpu_baseline,
-            "stats": {"N_vis": N_vis, "M": M, "stage_ms": stage_ms,
+            "stats": {"N_vis": N_vis, "M": M, "stage_ms": stage_ms, "hbm_bound_stages": hbm_stages,
                       "loss": float(loss.item()) if math.isfinite(float(loss.item())) else None}}
     print(json.dumps(line))
     if dist is not None:

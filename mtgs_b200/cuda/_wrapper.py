@@ -30,8 +30,9 @@ class _SphericalHarmonics(torch.autograd.Function):
     def forward(ctx, degree: int, dirs: Tensor, coeffs: Tensor, masks: Optional[Tensor]):
         lib = _lib.load()
         N, K = coeffs.shape[0], coeffs.shape[1]
-        colors = torch.zeros(N, 3, dtype=torch.float32, device=coeffs.device)
         m8 = masks.to(torch.uint8).contiguous() if masks is not None else None
+        alloc = torch.zeros if m8 is not None else torch.empty  # masked rows are not written by the kernel
+        colors = alloc(N, 3, dtype=torch.float32, device=coeffs.device)
         with torch.cuda.device(coeffs.device):
             _lib.check(lib.b2s_sh_fwd(degree, _ptr(dirs), _ptr(coeffs), _ptr(m8), N, K, _ptr(colors), _stream()),
                        "b2s_sh_fwd")

@@ -75,12 +75,15 @@ class SharedGradArena:
         backward work and optimizer steps that follow)."""
         if not dist.is_available() or not dist.is_initialized():
             return
+        # NCCL averages inside the collective (no extra pass over the arena); gloo has no AVG
+        self._avg_in_op = self.average and self._stream is not None and dist.get_backend(self.group) == "nccl"
+        op = dist.ReduceOp.AVG if self._avg_in_op else dist.ReduceOp.SUM
         if self._stream is not None:
             self._stream.wait_stream(torch.cuda.current_stream(self.arena.device))
             with torch.cuda.stream(self._stream):
-                self._work = dist.all_reduce(self.arena, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                self._work = dist.all_reduce(self.arena, op=op, group=self.group, async_op=True)
         else:
-            self._work = dist.all_reduce(self.arena, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._work = dist.all_reduce(self.arena, op=op, group=self.group, async_op=True)
 
     def wait(self) -> None:
         if self._work is not None:
@@ -88,7 +91,7 @@ class SharedGradArena:
             self._work = None
             if self._stream is not None:
                 torch.cuda.current_stream(self.arena.device).wait_stream(self._stream)
-        if self.average and dist.is_available() and dist.is_initialized():
+        if self.average and not getattr(self, "_avg_in_op", False) and dist.is_available() and dist.is_initialized():
             self.arena.div_(dist.get_world_size(self.group))
 
     def all_reduce(self) -> None:

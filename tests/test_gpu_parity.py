@@ -60,6 +60,9 @@ SCENES = {
     "tiny_ragged": lambda: scenes.tiny(n=257, seed=9, width=77, height=53),  # W,H not multiples of 16
     "config1": lambda: scenes.config1(),
     "street20k": lambda: scenes.street(n=20_000, seed=1, width=1920, height=1080),
+    # BASELINE config 5 resolutions: 4K exercises two column bands / seven row bands of the tile-list kernels
+    "street20k_4k": lambda: scenes.street(n=20_000, seed=2, width=3840, height=2160),
+    "street20k_540p": lambda: scenes.street(n=20_000, seed=3, width=960, height=540),
 }
 
 
@@ -106,7 +109,7 @@ def test_forward_image_parity(oracle, cuda_device, scene, mode, rmode, d_in):
         assert psnr(r[0, ..., :3].cpu().numpy(), rc[..., :3]) > 60.0  # >> the 0.05 dB PSNR-delta bar
 
 
-@pytest.mark.parametrize("scene", ["tiny", "tiny_ragged", "config1", "street20k"])
+@pytest.mark.parametrize("scene", ["tiny", "tiny_ragged", "config1", "street20k", "street20k_4k"])
 @pytest.mark.parametrize("mode,rmode,d_in", [("classic", "RGB", 3), ("antialiased", "RGB+ED", 3),
                                               ("antialiased", "RGB+ED", 6)])
 def test_backward_parity(oracle, cuda_device, scene, mode, rmode, d_in):
