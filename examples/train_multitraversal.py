@@ -1,0 +1,158 @@
+"""Procedural stand-in for BASELINE configs 3-4 (multi-traversal road block; the nuPlan data is not available).
+
+A "true" scene (shared geometry + per-traversal colour residuals, the structure of the reference's
+MultiColorGaussianSplattingModel: features_dc + features_adapters[:, t], features_rest; reference
+mtgs/scene_model/gaussian_model/multi_color_gaussian_splatting.py:53-101) renders target images for T traversals;
+a perturbed copy is then optimised against them through the SAME public API MTGS uses:
+
+    spherical_harmonics(n, viewdirs, coeffs) -> clamp(+0.5) -> rasterization(..., render_mode="RGB+ED",
+    rasterize_mode="antialiased", absgrad=True) -> L1 (+ depth) -> backward -> Adam,
+    densification statistic from info["means2d"].absgrad (mtgs_scene_graph.py:1171-1178).
+
+Single GPU:   python examples/train_multitraversal.py --iters 300
+Multi GPU :   torchrun --nproc-per-node 4 --master-addr 127.0.0.1 examples/train_multitraversal.py --traversals 4
+              (rank r owns traversal r; shared-node gradients are all-reduced through SharedGradArena, the
+               per-traversal adapters stay rank-local -- SURVEY.md 8e)
+"""
+from __future__ import annotations
+
+import argparse
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from mtgs_b200 import scenes  # noqa: E402
+from mtgs_b200.cuda._wrapper import spherical_harmonics  # noqa: E402
+from mtgs_b200.parallel import SharedGradArena, traversal_of_rank  # noqa: E402
+from mtgs_b200.rendering import rasterization  # noqa: E402
+
+C0 = 0.28209479177387814
+
+
+def make_model(n, n_trav, width, height, seed, dev):
+    s = scenes.street(n=n, seed=seed, width=width, height=height)
+    g = torch.Generator().manual_seed(seed)
+    p = {
+        "means": torch.tensor(s["means"]),
+        "scales": torch.log(torch.tensor(s["scales"])),                       # raw (exp activation)
+        "quats": torch.tensor(s["quats"]),                                     # raw (normalised on use)
+        "opacities": torch.logit(torch.tensor(s["opacities"]).clamp(1e-4, 1 - 1e-4)),
+        "features_dc": (torch.tensor(s["colors"]) - 0.5) / C0,
+        "features_rest": 0.05 * torch.randn(n, 15, 3, generator=g),
+        "features_adapters": 0.3 * torch.randn(n, n_trav, 3, generator=g),     # per-traversal colour residual
+    }
+    return {k: v.to(dev).float() for k, v in p.items()}, s
+
+
+def render(p, trav, viewmat, K, W, H, sh_degree, absgrad=True):
+    means = p["means"]
+    scales = torch.exp(p["scales"])
+    quats = p["quats"] / p["quats"].norm(dim=-1, keepdim=True)
+    opac = torch.sigmoid(p["opacities"])
+    dc = p["features_dc"] + p["features_adapters"][:, trav, :]
+    coeffs = torch.cat([dc[:, None, :], p["features_rest"]], dim=1)
+    campos = torch.inverse(viewmat)[:3, 3]
+    dirs = means.detach() - campos
+    dirs = dirs / dirs.norm(dim=-1, keepdim=True)
+    rgbs = torch.clamp(spherical_harmonics(sh_degree, dirs, coeffs) + 0.5, 0.0, 1.0)
+    out, alpha, info = rasterization(means=means, quats=quats, scales=scales, opacities=opac, colors=rgbs,
+                                     viewmats=viewmat[None], Ks=K[None], width=W, height=H, tile_size=16,
+                                     packed=False, near_plane=0.01, far_plane=1e10, render_mode="RGB+ED",
+                                     sparse_grad=False, absgrad=absgrad, rasterize_mode="antialiased")
+    rgb = torch.clamp(out[..., :3] + (1 - alpha) * 1.0, 0.0, 1.0)
+    return rgb[0], out[0, ..., 3:4], alpha[0], info
+
+
+def psnr(a, b):
+    return float(-10.0 * torch.log10(torch.mean((a - b) ** 2).clamp_min(1e-12)))
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=100_000)
+    ap.add_argument("--traversals", type=int, default=3)
+    ap.add_argument("--width", type=int, default=960)
+    ap.add_argument("--height", type=int, default=540)
+    ap.add_argument("--iters", type=int, default=300)
+    ap.add_argument("--log-every", type=int, default=50)
+    ap.add_argument("--seed", type=int, default=7)
+    args = ap.parse_args(argv)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    W, H, T = args.width, args.height, args.traversals
+    truth, s = make_model(args.n, T, W, H, args.seed, dev)
+    K = torch.tensor(s["K"], device=dev)
+    cams = [torch.tensor(scenes.street(n=8, seed=args.seed, width=W, height=H, camera=c)["viewmat"], device=dev)
+            for c in range(T)]
+    my_travs = traversal_of_rank(rank, world, T)
+    with torch.no_grad():
+        targets = {t: render(truth, t, cams[t], K, W, H, 3, absgrad=False)[:2] for t in my_travs}
+
+    # perturbed model (identical on every rank: same seed)
+    g = torch.Generator().manual_seed(args.seed + 1)
+    model = {}
+    for k, v in truth.items():
+        noise = {"means": 0.02, "scales": 0.15, "quats": 0.05, "opacities": 0.5, "features_dc": 0.5,
+                 "features_rest": 0.05, "features_adapters": 0.3}[k]
+        model[k] = (v + noise * torch.randn(v.shape, generator=g).to(dev)).requires_grad_(True)
+    shared = [model[k] for k in ("means", "scales", "quats", "opacities", "features_dc", "features_rest")]
+    arena = SharedGradArena(shared, average=True) if world > 1 else None
+    lrs = {"means": 1.6e-4, "scales": 5e-3, "quats": 1e-3, "opacities": 5e-2, "features_dc": 2.5e-3,
+           "features_rest": 1.25e-4, "features_adapters": 2.5e-3}
+    opt = torch.optim.Adam([{"params": [model[k]], "lr": lrs[k], "eps": 1e-15} for k in model])
+    grad_norm_acc = torch.zeros(args.n, device=dev)
+    first = {}
+    vis_count = torch.zeros(args.n, device=dev)
+
+    for it in range(args.iters + 1):
+        t = my_travs[it % len(my_travs)]
+        sh_degree = min(it // max(1, args.iters // 4), 3)  # progressive SH degree (reference: sh_degree_interval)
+        rgb, depth, alpha, info = render(model, t, cams[t], K, W, H, sh_degree)
+        info["means2d"].retain_grad()
+        tgt_rgb, tgt_depth = targets[t]
+        loss = (rgb - tgt_rgb).abs().mean() + 0.01 * (depth - tgt_depth).abs().mean() / 50.0
+        first.setdefault(t, psnr(rgb.detach(), tgt_rgb))
+        if arena is not None:
+            arena.zero_()
+            model["features_adapters"].grad = None
+        else:
+            opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if arena is not None:
+            arena.all_reduce()
+        with torch.no_grad():  # densification statistics exactly as mtgs_scene_graph.py:1171-1178
+            grads = info["means2d"].absgrad[0]
+            vis = info["radii"][0] > 0
+            grad_norm_acc[vis] += (grads[vis] * grads.new_tensor([W, H]) * 0.5).norm(dim=-1)
+            vis_count[vis] += 1
+        opt.step()
+        if it % args.log_every == 0 and rank == 0:
+            print(f"iter {it:5d}  traversal {t}  sh {sh_degree}  loss {float(loss):.5f}  "
+                  f"psnr {psnr(rgb.detach(), tgt_rgb):.2f} dB  visible {int(vis.sum())}  "
+                  f"mean absgrad stat {float(grad_norm_acc.sum() / vis_count.sum().clamp_min(1)):.4e}", flush=True)
+    final = {t: psnr(render(model, t, cams[t], K, W, H, 3, absgrad=False)[0].detach(), targets[t][0]) for t in my_travs}
+    if rank == 0:
+        print("final PSNR per traversal:", {k: round(v, 2) for k, v in final.items()})
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return first, final
+
+
+if __name__ == "__main__":
+    main()

@@ -17,6 +17,8 @@
 //     with a transposing butterfly (16 shuffles instead of 16 x 5), parked per warp in shared memory, summed
 //     over the CTA's four warps and flushed with 16-byte vector reductions (red.global.add.v4.f32): at most
 //     2 + CDIM/4 L2 atomic operations per (tile, Gaussian) instead of upstream's (9 + CDIM) per (warp, Gaussian).
+#include <cstdlib>
+
 #include "common.cuh"
 
 constexpr int BL_THREADS = 128;
@@ -319,85 +321,116 @@ __device__ __forceinline__ void load_pixel_cotangent(size_t pid, const float *__
     }
 }
 
-template <int CDIM, int DOUT, bool ED>
-__global__ void __launch_bounds__(BL_THREADS)
+// PX pixels per thread (same column, PX adjacent rows); 256 / PX threads per tile.  PX = 4 halves the number of
+// (warp, Gaussian) reductions and staged-record reads per pixel compared with PX = 2.
+template <int CDIM, int DOUT, bool ED, int PX>
+__global__ void __launch_bounds__(256 / PX)
 k_blend_bwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, const float4 *__restrict__ colpack,
             const int32_t *__restrict__ offsets, const int32_t *__restrict__ flatten_ids, long long M, int W, int H,
             int tile_w, int tile_h, const float *__restrict__ render, const float *__restrict__ alpha_in,
             const int32_t *__restrict__ last_ids, const float *__restrict__ v_render,
             const float *__restrict__ v_alpha, float *__restrict__ v_xyabs, float *__restrict__ v_geo,
             float *__restrict__ v_colpack) {
+    constexpr int THREADS = 256 / PX;
+    constexpr int WARPS = THREADS / 32;
+    constexpr int BATCH = 128;            // staged Gaussians per round
+    constexpr int SPT = BATCH / THREADS;  // staged per thread
     constexpr int CQ = CDIM / 4;
     constexpr int NQUAD = 2 + CQ;  // float4 groups flushed per Gaussian
-    __shared__ float4 s_q[BL_BATCH];
-    __shared__ float2 s_c[BL_BATCH];
-    __shared__ int s_idx[BL_BATCH];
-    __shared__ int s_gid[BL_BATCH];
-    __shared__ float4 s_col[BL_BATCH][CQ];
-    __shared__ int s_wcnt[BL_WARPS];
-    __shared__ __align__(16) float s_acc[BL_WARPS][BL_BATCH][16];
+    __shared__ float4 s_q[BATCH];
+    __shared__ float2 s_c[BATCH];
+    __shared__ int s_idx[BATCH];
+    __shared__ int s_gid[BATCH];
+    __shared__ float4 s_col[BATCH][CQ];
+    __shared__ int s_wcnt[SPT][WARPS];
+    __shared__ __align__(16) float s_acc[WARPS][BATCH][16];
 
-    const TileGeom tg = tile_geom(tile_w, tile_h, W, H, M, offsets);
+    const int tile = blockIdx.x;
+    const int ti = tile / tile_w, tj = tile - ti * tile_w;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned lt = lanemask_lt();
+    const int x = tj * 16 + (lane & 15);
+    const int ybase = ti * 16 + 2 * PX * warp + PX * (lane >> 4);
+    const float px = (float)x + 0.5f;
+    const float rx0 = (float)(tj * 16) + 0.5f, ry0 = (float)(ti * 16) + 0.5f;
+    const float rx1 = (float)min(tj * 16 + 16, W) - 0.5f, ry1 = (float)min(ti * 16 + 16, H) - 0.5f;
+    const int start = offsets[tile];
+    const int end = (tile == tile_w * tile_h - 1) ? (int)M : offsets[tile + 1];
 
-    float T0 = 1.f, T1 = 1.f, Tf0 = 1.f, Tf1 = 1.f, vra0 = 0.f, vra1 = 0.f;
-    float vrc0[CDIM], vrc1[CDIM], buf0[CDIM], buf1[CDIM];
+    float T[PX], Tf[PX], vra[PX], py[PX];
+    float vrc[PX][CDIM], buf[PX][CDIM];
+    int bin[PX];
+    int maxbin = -1;
 #pragma unroll
-    for (int k = 0; k < CDIM; ++k) vrc0[k] = vrc1[k] = buf0[k] = buf1[k] = 0.f;
-    int bin0 = -1, bin1 = -1;
-    if (tg.in0) {
-        const size_t pid = (size_t)tg.y0 * W + tg.x;
-        load_pixel_cotangent<CDIM, DOUT, ED>(pid, render, alpha_in, v_render, v_alpha, vrc0, vra0, Tf0);
-        T0 = Tf0;
-        bin0 = last_ids[pid];
-    }
-    if (tg.in1) {
-        const size_t pid = (size_t)(tg.y0 + 1) * W + tg.x;
-        load_pixel_cotangent<CDIM, DOUT, ED>(pid, render, alpha_in, v_render, v_alpha, vrc1, vra1, Tf1);
-        T1 = Tf1;
-        bin1 = last_ids[pid];
+    for (int j = 0; j < PX; ++j) {
+        T[j] = Tf[j] = 1.f;
+        vra[j] = 0.f;
+        bin[j] = -1;
+        py[j] = (float)(ybase + j) + 0.5f;
+#pragma unroll
+        for (int k = 0; k < CDIM; ++k) vrc[j][k] = buf[j][k] = 0.f;
+        if (x < W && ybase + j < H) {
+            const size_t pid = (size_t)(ybase + j) * W + x;
+            load_pixel_cotangent<CDIM, DOUT, ED>(pid, render, alpha_in, v_render, v_alpha, vrc[j], vra[j], Tf[j]);
+            T[j] = Tf[j];
+            bin[j] = last_ids[pid];
+        }
+        maxbin = max(maxbin, bin[j]);
     }
     // last sorted index any pixel of this tile blended
-    int maxbin = __reduce_max_sync(0xffffffffu, max(bin0, bin1));
-    if (lane == 0) s_wcnt[warp] = maxbin;
+    maxbin = __reduce_max_sync(0xffffffffu, maxbin);
+    if (lane == 0) s_wcnt[0][warp] = maxbin;
     __syncthreads();
-    maxbin = max(max(s_wcnt[0], s_wcnt[1]), max(s_wcnt[2], s_wcnt[3]));
-    const int hi0 = min(tg.end - 1, maxbin);
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) maxbin = max(maxbin, s_wcnt[0][w]);
+    const int hi0 = min(end - 1, maxbin);
 
-    for (int hi = hi0; hi >= tg.start; hi -= BL_BATCH) {
+    for (int hi = hi0; hi >= start; hi -= BATCH) {
         __syncthreads();  // previous batch fully flushed before its buffers are reused
-        const int idx = hi - (int)threadIdx.x;  // back to front: slot order == descending sorted index
-        bool keep = false;
-        int g = 0;
-        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-        float2 c = make_float2(0.f, 0.f);
-        if (idx >= tg.start) {
-            g = flatten_ids[idx];
-            const float2 m = means2d[g];
-            const float4 ge = geo[g];
-            q = make_float4(m.x, m.y, 0.5f * B2S_LOG2E * ge.x, B2S_LOG2E * ge.y);
-            c = make_float2(0.5f * B2S_LOG2E * ge.z, ge.w);
-            keep = tile_keep(m.x, m.y, q.z, q.w, c.x, c.y, tg.rx0, tg.ry0, tg.rx1, tg.ry1);
+        // back to front: slot order == descending sorted index; thread stages entries hi - (q * THREADS + tid)
+        bool keep[SPT];
+        int g[SPT], idx[SPT];
+        float4 q[SPT];
+        float2 c[SPT];
+        unsigned bal[SPT];
+#pragma unroll
+        for (int u = 0; u < SPT; ++u) {
+            idx[u] = hi - (u * THREADS + (int)threadIdx.x);
+            keep[u] = false;
+            g[u] = 0;
+            q[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            c[u] = make_float2(0.f, 0.f);
+            if (idx[u] >= start) {
+                g[u] = flatten_ids[idx[u]];
+                const float2 m = means2d[g[u]];
+                const float4 ge = geo[g[u]];
+                q[u] = make_float4(m.x, m.y, 0.5f * B2S_LOG2E * ge.x, B2S_LOG2E * ge.y);
+                c[u] = make_float2(0.5f * B2S_LOG2E * ge.z, ge.w);
+                keep[u] = tile_keep(m.x, m.y, q[u].z, q[u].w, c[u].x, c[u].y, rx0, ry0, rx1, ry1);
+            }
+            bal[u] = __ballot_sync(0xffffffffu, keep[u]);
+            if (lane == 0) s_wcnt[u][warp] = __popc(bal[u]);
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) s_wcnt[warp] = __popc(bal);
         __syncthreads();
-        int off = 0, total = 0;
+        int total = 0;
 #pragma unroll
-        for (int w = 0; w < BL_WARPS; ++w) {
-            int n = s_wcnt[w];
-            off += (w < warp) ? n : 0;
-            total += n;
-        }
-        if (keep) {
-            const int slot = off + __popc(bal & lt);
-            s_q[slot] = q;
-            s_c[slot] = c;
-            s_idx[slot] = idx;
-            s_gid[slot] = g;
+        for (int u = 0; u < SPT; ++u) {
+            int off = total;
 #pragma unroll
-            for (int k = 0; k < CQ; ++k) s_col[slot][k] = colpack[(size_t)g * CQ + k];
+            for (int w = 0; w < WARPS; ++w) {
+                const int n = s_wcnt[u][w];
+                off += (w < warp) ? n : 0;
+                total += n;
+            }
+            if (keep[u]) {
+                const int slot = off + __popc(bal[u] & lt);
+                s_q[slot] = q[u];
+                s_c[slot] = c[u];
+                s_idx[slot] = idx[u];
+                s_gid[slot] = g[u];
+#pragma unroll
+                for (int k = 0; k < CQ; ++k) s_col[slot][k] = colpack[(size_t)g[u] * CQ + k];
+            }
         }
         __syncthreads();
 
@@ -405,16 +438,20 @@ k_blend_bwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
             const float4 sq = s_q[t];
             const float2 sc = s_c[t];
             const int id = s_idx[t];
-            const float dx = sq.x - tg.px;
-            const float dy0 = sq.y - tg.py0, dy1 = sq.y - tg.py1;
-            const float p0 = splat_power(sq.z, sq.w, sc.x, dx, dy0);
-            const float p1 = splat_power(sq.z, sq.w, sc.x, dx, dy1);
-            const float e0 = ex2_approx(-p0), e1 = ex2_approx(-p1);
-            const float a0 = fminf(B2S_ALPHA_MAX, __fmul_rn(sc.y, e0));
-            const float a1 = fminf(B2S_ALPHA_MAX, __fmul_rn(sc.y, e1));
-            const bool ok0 = id <= bin0 && p0 >= 0.f && a0 >= B2S_ALPHA_MIN;
-            const bool ok1 = id <= bin1 && p1 >= 0.f && a1 >= B2S_ALPHA_MIN;
-            if (!__any_sync(0xffffffffu, ok0 || ok1)) {
+            const float dx = sq.x - px;
+            float dy[PX], al[PX], ev[PX];
+            bool ok[PX];
+            bool any_ok = false;
+#pragma unroll
+            for (int j = 0; j < PX; ++j) {
+                dy[j] = sq.y - py[j];
+                const float p = splat_power(sq.z, sq.w, sc.x, dx, dy[j]);
+                ev[j] = ex2_approx(-p);
+                al[j] = fminf(B2S_ALPHA_MAX, __fmul_rn(sc.y, ev[j]));
+                ok[j] = id <= bin[j] && p >= 0.f && al[j] >= B2S_ALPHA_MIN;
+                any_ok = any_ok || ok[j];
+            }
+            if (!__any_sync(0xffffffffu, any_ok)) {
                 if (lane < 16) s_acc[warp][t][lane] = 0.f;
                 continue;
             }
@@ -427,8 +464,11 @@ k_blend_bwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
                 const float4 cv = s_col[t][k];
                 col[4 * k] = cv.x; col[4 * k + 1] = cv.y; col[4 * k + 2] = cv.z; col[4 * k + 3] = cv.w;
             }
-            if (ok0) pixel_grad<CDIM>(v, T0, buf0, vrc0, vra0, Tf0, col, sq.z, sq.w, sc.x, sc.y, dx, dy0, a0, e0);
-            if (ok1) pixel_grad<CDIM>(v, T1, buf1, vrc1, vra1, Tf1, col, sq.z, sq.w, sc.x, sc.y, dx, dy1, a1, e1);
+#pragma unroll
+            for (int j = 0; j < PX; ++j)
+                if (ok[j])
+                    pixel_grad<CDIM>(v, T[j], buf[j], vrc[j], vra[j], Tf[j], col, sq.z, sq.w, sc.x, sc.y, dx, dy[j], al[j],
+                                     ev[j]);
             const float r = warp_reduce16_transposed(v, lane);
             if (!(lane & 1)) s_acc[warp][t][lane >> 1] = r;
         }
@@ -436,13 +476,13 @@ k_blend_bwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
 
         // flush: item = (slot, quad); consecutive threads read consecutive float4s of s_acc (conflict free)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int item = (int)threadIdx.x + BL_THREADS * j;
+        for (int j = 0; j < 4 * BATCH / THREADS; ++j) {
+            const int item = (int)threadIdx.x + THREADS * j;
             const int slot = item >> 2, quad = item & 3;
             if (slot < total && quad < NQUAD) {
                 float4 s = reinterpret_cast<const float4 *>(&s_acc[0][slot][0])[quad];
 #pragma unroll
-                for (int w = 1; w < BL_WARPS; ++w) {
+                for (int w = 1; w < WARPS; ++w) {
                     const float4 o = reinterpret_cast<const float4 *>(&s_acc[w][slot][0])[quad];
                     s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
                 }
@@ -476,9 +516,19 @@ static int launch_bwd(const float *means2d, const float *geo, const float *colpa
                       const int32_t *flatten_ids, long long M, int W, int H, int tile_w, int tile_h,
                       const float *render, const float *alpha, const int32_t *last_ids, const float *v_render,
                       const float *v_alpha, float *v_xyabs, float *v_geo, float *v_colpack, cudaStream_t st) {
-    k_blend_bwd<CDIM, DOUT, ED><<<tile_w * tile_h, BL_THREADS, 0, st>>>(
-        (const float2 *)means2d, (const float4 *)geo, (const float4 *)colpack, offsets, flatten_ids, M, W, H, tile_w,
-        tile_h, render, alpha, last_ids, v_render, v_alpha, v_xyabs, v_geo, v_colpack);
+    // pixels per thread in the backward (see k_blend_bwd); B2S_BWD_PX=2 selects the 128-thread variant (tuning knob)
+    static const int px = [] {
+        const char *e = getenv("B2S_BWD_PX");
+        return (e && atoi(e) == 2) ? 2 : 4;
+    }();
+    if (px == 2)
+        k_blend_bwd<CDIM, DOUT, ED, 2><<<tile_w * tile_h, 128, 0, st>>>(
+            (const float2 *)means2d, (const float4 *)geo, (const float4 *)colpack, offsets, flatten_ids, M, W, H, tile_w,
+            tile_h, render, alpha, last_ids, v_render, v_alpha, v_xyabs, v_geo, v_colpack);
+    else
+        k_blend_bwd<CDIM, DOUT, ED, 4><<<tile_w * tile_h, 64, 0, st>>>(
+            (const float2 *)means2d, (const float4 *)geo, (const float4 *)colpack, offsets, flatten_ids, M, W, H, tile_w,
+            tile_h, render, alpha, last_ids, v_render, v_alpha, v_xyabs, v_geo, v_colpack);
     B2S_LAUNCH_CHECK();
     return B2S_OK;
 }
