@@ -44,8 +44,8 @@ const char *b2s_error_string(int code);
 long long b2s_launch_count(void);
 
 /* ---- projection + EWA covariance (upstream fully_fused_projection fwd; SURVEY A.1, A.2 pass 1) ----
- * Also emits, per Gaussian: the tile count of upstream isect_tiles pass 1, the depth sort key
- * (float bits of depth, 0xFFFFFFFF when culled), the packed blend record
+ * Also emits, per Gaussian: the tile count of upstream isect_tiles pass 1, its tile rectangle, the depth
+ * sort key (float bits of depth, 0xFFFFFFFF when culled), the packed blend record
  *   geo[g]     = (conic a, conic b, conic c, opacity * compensation)
  *   colpack[g] = (colors_in[0..d_in), depth if with_depth, zero pad) , cdim floats
  * comps may be NULL when calc_comp == 0.  colors_in is [N, d_in]. */
@@ -55,7 +55,7 @@ int b2s_project_fwd(const float *means, const float *quats, const float *scales,
                     float eps2d, float near_plane, float far_plane, float radius_clip,
                     int calc_comp, int d_in, int with_depth, int cdim, int32_t *radii,
                     float *means2d, float *depths, float *geo, float *comps, float *colpack,
-                    int32_t *tiles_per_gauss, uint32_t *sort_keys, uint32_t *sort_vals,
+                    int32_t *tiles_per_gauss, uint32_t *sort_keys,
                     int32_t *tile_rects /* [N,2]: x0 | x1 << 16, y0 | y1 << 16 */, b2s_stream_t stream);
 
 /* upstream fully_fused_projection bwd fused with the opacity*compensation and
@@ -73,18 +73,19 @@ int b2s_project_bwd(const float *means, const float *quats, const float *scales,
 
 /* ---- tile binning + depth sort (upstream isect_tiles + radix sort + isect_offset_encode; A.2) ----
  * Two-level formulation with identical results to the stable 64-bit sort:
- *   (1) b2s_bin_sort_depth : stable sort of Gaussians by depth key -> order[N];
- *       cum[i] = exclusive scan of tiles_per_gauss[order[i]];  *total (device int64) = M.
+ *   (1) b2s_bin_sort_depth : stable sort of the visible Gaussians by depth key (one cooperative kernel) ->
+ *       order[0..n_vis), cum[i] = exclusive scan of tiles_per_gauss[order[i]], *total (device int64) = M,
+ *       *n_vis (device int32).  Entries beyond n_vis are undefined.
  *   (2) b2s_bin_tiles      : ordered bucket fill of the (tile, gaussian) intersections walking the
  *       Gaussians in depth order -> flatten_ids[M], isect_offsets[tile_h*tile_w] (no sort of M items).
  *   (3) b2s_bin_isect_ids  : optional, rebuilds upstream's int64 isect_ids for inspection. */
 size_t b2s_bin_depth_workspace_bytes(int N);
-int b2s_bin_sort_depth(const uint32_t *sort_keys, const uint32_t *sort_vals,
-                       const int32_t *tiles_per_gauss, int N, int32_t *order, int32_t *cum,
-                       int64_t *total, void *workspace, size_t workspace_bytes,
-                       b2s_stream_t stream);
+int b2s_bin_sort_depth(const uint32_t *sort_keys, const int32_t *tiles_per_gauss, int N,
+                       int32_t *order, int32_t *cum, int64_t *total, int32_t *n_vis, void *workspace,
+                       size_t workspace_bytes, b2s_stream_t stream);
 size_t b2s_bin_tiles_workspace_bytes(int N, long long M, int tile_w, int tile_h);
-int b2s_bin_tiles(const int32_t *tile_rects, const int32_t *order, const int32_t *cum, int N, long long M, int tile_size, int tile_w, int tile_h,
+int b2s_bin_tiles(const int32_t *tile_rects, const int32_t *order, const int32_t *cum,
+                  const int32_t *n_vis, int N, long long M, int tile_size, int tile_w, int tile_h,
                   int32_t *flatten_ids, int32_t *isect_offsets, void *workspace,
                   size_t workspace_bytes, b2s_stream_t stream);
 int b2s_bin_isect_ids(const int32_t *isect_offsets, int n_tiles, const int32_t *flatten_ids,

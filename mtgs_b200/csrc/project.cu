@@ -96,7 +96,7 @@ k_project_fwd(const float *__restrict__ means, const float *__restrict__ quats, 
               int d_in, int with_depth, int32_t *__restrict__ radii, float2 *__restrict__ means2d,
               float *__restrict__ depths, float4 *__restrict__ geo, float *__restrict__ comps,
               float *__restrict__ colpack, int32_t *__restrict__ tiles_per_gauss,
-              uint32_t *__restrict__ sort_keys, uint32_t *__restrict__ sort_vals, int2 *__restrict__ tile_rects) {
+              uint32_t *__restrict__ sort_keys, int2 *__restrict__ tile_rects) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= N) return;
     CamParams cam;
@@ -176,7 +176,6 @@ k_project_fwd(const float *__restrict__ means, const float *__restrict__ quats, 
     tiles_per_gauss[g] = ntiles;
     tile_rects[g] = rect;
     sort_keys[g] = radius_i > 0 ? __float_as_uint(z) : 0xFFFFFFFFu;
-    sort_vals[g] = (uint32_t)g;
     if (radius_i > 0) {
         float op = opacities[g];
         if (calc_comp) {
@@ -440,7 +439,7 @@ extern "C" int b2s_project_fwd(const float *means, const float *quats, const flo
                                float eps2d, float near_plane, float far_plane, float radius_clip, int calc_comp,
                                int d_in, int with_depth, int cdim, int32_t *radii, float *means2d, float *depths,
                                float *geo, float *comps, float *colpack, int32_t *tiles_per_gauss,
-                               uint32_t *sort_keys, uint32_t *sort_vals, int32_t *tile_rects,
+                               uint32_t *sort_keys, int32_t *tile_rects,
                                b2s_stream_t stream) {
     if (N < 0 || W <= 0 || H <= 0) return B2S_ERR_ARG;
     if (tile_size != 16 || tile_w > 32767 || tile_h > 32767) return B2S_ERR_UNSUPPORTED;
@@ -454,7 +453,7 @@ extern "C" int b2s_project_fwd(const float *means, const float *quats, const flo
     k_project_fwd<CD><<<grid, block, 0, st>>>(means, quats, scales, opacities, colors_in, viewmat, K, N, W, H, \
                                               tile_w, tile_h, eps2d, near_plane, far_plane, radius_clip,     \
                                               calc_comp, d_in, with_depth, radii, (float2 *)means2d, depths, \
-                                              (float4 *)geo, comps, colpack, tiles_per_gauss, sort_keys, sort_vals, \
+                                              (float4 *)geo, comps, colpack, tiles_per_gauss, sort_keys, \
                                               (int2 *)tile_rects)
     if (cdim == 4) LAUNCH(4);
     else LAUNCH(8);

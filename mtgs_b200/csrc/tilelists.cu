@@ -42,22 +42,11 @@ __device__ __forceinline__ int lower_bound_cost(const int32_t *__restrict__ cum,
     return lo;
 }
 
-// bounds[r] (r = 0..R) = first Gaussian of chunk r in the depth-ordered stream; bounds[R] = number of Gaussians
-// that own intersections (the culled ones sort last and are never walked).
+// bounds[r] (r = 0..R) = first Gaussian of chunk r in the depth-ordered stream; bounds[R] = n_vis.
 __global__ void __launch_bounds__(1024)
-k_chunk_bounds(const int32_t *__restrict__ cum, int N, long long M, int R, int32_t *__restrict__ bounds) {
-    __shared__ int s_nv;
-    if (threadIdx.x == 0) {
-        int lo = 0, hi = N;  // first i with cum[i] >= M
-        while (lo < hi) {
-            int mid = (lo + hi) >> 1;
-            if ((long long)cum[mid] < M) lo = mid + 1;
-            else hi = mid;
-        }
-        s_nv = lo;
-    }
-    __syncthreads();
-    const int nv = s_nv;
+k_chunk_bounds(const int32_t *__restrict__ cum, const int32_t *__restrict__ n_vis, long long M, int R,
+               int32_t *__restrict__ bounds) {
+    const int nv = *n_vis;  // Gaussians that own intersections (depthsort.cu drops the culled ones)
     const long long C = M + (long long)TR_COST_C * nv;
     for (int r = threadIdx.x; r <= R; r += blockDim.x)
         bounds[r] = (r == R) ? nv : lower_bound_cost(cum, nv, TR_COST_C, ((long long)r * C + R - 1) / R);
@@ -293,8 +282,8 @@ extern "C" size_t b2s_bin_tiles_workspace_bytes(int N, long long M, int tile_w, 
            tl_align256((size_t)(p.R + 1) * 4) + 1024;
 }
 
-extern "C" int b2s_bin_tiles(const int32_t *tile_rects, const int32_t *order, const int32_t *cum, int N, long long M,
-                             int tile_size, int tile_w, int tile_h, int32_t *flatten_ids, int32_t *isect_offsets,
+extern "C" int b2s_bin_tiles(const int32_t *tile_rects, const int32_t *order, const int32_t *cum,
+                             const int32_t *n_vis, int N, long long M, int tile_size, int tile_w, int tile_h, int32_t *flatten_ids, int32_t *isect_offsets,
                              void *workspace, size_t workspace_bytes, b2s_stream_t stream) {
     if (N < 0 || M < 0 || M >= (1LL << 31) || tile_w <= 0 || tile_h <= 0) return B2S_ERR_ARG;
     if (tile_size != 16 || !tl_supported(tile_w, tile_h)) return B2S_ERR_UNSUPPORTED;
@@ -314,7 +303,7 @@ extern "C" int b2s_bin_tiles(const int32_t *tile_rects, const int32_t *order, co
     const int threads = 32 * p.rows_per_band;
     const int grid = p.R * p.row_bands * p.col_bands;
     const size_t smem_count = (size_t)(p.rows_per_band + 1) * (32 * TR_NG + 1) * sizeof(int);
-    k_chunk_bounds<<<1, 1024, 0, st>>>(cum, N, M, p.R, bounds);
+    k_chunk_bounds<<<1, 1024, 0, st>>>(cum, n_vis, M, p.R, bounds);
     B2S_LAUNCH_CHECK();
     k_tile_count<<<grid, threads, smem_count, st>>>((const int2 *)tile_rects, order, bounds, tile_w, tile_h,
                                                      p.rows_per_band, p.row_bands, p.R, table);

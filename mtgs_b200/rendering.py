@@ -109,20 +109,19 @@ class _Project(torch.autograd.Function):
         colpack = torch.empty(N, cdim, dtype=torch.float32, device=dev)
         tiles = torch.empty(N, dtype=torch.int32, device=dev)
         keys = torch.empty(N, dtype=torch.int32, device=dev)
-        vals = torch.empty(N, dtype=torch.int32, device=dev)
         rects = torch.empty(N, 2, dtype=torch.int32, device=dev)
         with _timed("project_fwd"):
             _lib.check(lib.b2s_project_fwd(_ptr(means), _ptr(quats), _ptr(scales), _ptr(opacities), _ptr(colors),
                                            _ptr(viewmat), _ptr(K), N, W, H, 16, tile_w, tile_h, eps2d, near, far,
                                            radius_clip, int(calc_comp), d_in, int(with_depth), cdim, _ptr(radii),
                                            _ptr(means2d), _ptr(depths), _ptr(geo), _ptr(comps), _ptr(colpack),
-                                           _ptr(tiles), _ptr(keys), _ptr(vals), _ptr(rects), _stream()),
+                                           _ptr(tiles), _ptr(keys), _ptr(rects), _stream()),
                        "b2s_project_fwd")
         ctx.save_for_backward(means, quats, scales, opacities, viewmat, K, radii, geo, comps)
         ctx.cfg = (W, H, eps2d, calc_comp, d_in, with_depth, cdim)
         ctx.has_colors = colors is not None
-        ctx.mark_non_differentiable(radii, depths, tiles, keys, vals, rects)
-        return means2d, geo, colpack, radii, depths, tiles, keys, vals, rects
+        ctx.mark_non_differentiable(radii, depths, tiles, keys, rects)
+        return means2d, geo, colpack, radii, depths, tiles, keys, rects
 
     @staticmethod
     def backward(ctx, v_means2d, v_geo, v_colpack, *_unused):
@@ -201,19 +200,20 @@ class _Blend(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------
-def _bin(rects: Tensor, tiles: Tensor, keys: Tensor, vals: Tensor, tile_w: int, tile_h: int) -> Tuple[Tensor, Tensor, Tensor]:
+def _bin(rects: Tensor, tiles: Tensor, keys: Tensor, tile_w: int, tile_h: int) -> Tuple[Tensor, Tensor, Tensor]:
     """Depth order + tile lists.  Returns (flatten_ids [M] int32, offsets [th,tw] int32)."""
     lib = _lib.load()
     dev = rects.device
     N = tiles.shape[0]
     order = torch.empty(N, dtype=torch.int32, device=dev)
     cum = torch.empty(N, dtype=torch.int32, device=dev)
-    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    total = torch.empty(1, dtype=torch.int64, device=dev)
+    n_vis = torch.empty(1, dtype=torch.int32, device=dev)
     wsb = int(lib.b2s_bin_depth_workspace_bytes(N))
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     with _timed("bin_sort_depth"):
-        _lib.check(lib.b2s_bin_sort_depth(_ptr(keys), _ptr(vals), _ptr(tiles), N, _ptr(order), _ptr(cum),
-                                          _ptr(total), _ptr(ws), wsb, _stream()), "b2s_bin_sort_depth")
+        _lib.check(lib.b2s_bin_sort_depth(_ptr(keys), _ptr(tiles), N, _ptr(order), _ptr(cum), _ptr(total),
+                                          _ptr(n_vis), _ptr(ws), wsb, _stream()), "b2s_bin_sort_depth")
     M = int(total.item())  # the one unavoidable device->host read: sizes the intersection buffers
     if M >= 2 ** 31:
         raise RuntimeError(f"{M} tile intersections exceed the int32 offset range (same limit as upstream)")
@@ -224,7 +224,7 @@ def _bin(rects: Tensor, tiles: Tensor, keys: Tensor, vals: Tensor, tile_w: int, 
         raise NotImplementedError(f"tile grid {tile_w}x{tile_h} not supported")
     ws2 = torch.empty(wsb2, dtype=torch.uint8, device=dev)
     with _timed("bin_tiles"):
-        _lib.check(lib.b2s_bin_tiles(_ptr(rects), _ptr(order), _ptr(cum), N, M, 16, tile_w, tile_h,
+        _lib.check(lib.b2s_bin_tiles(_ptr(rects), _ptr(order), _ptr(cum), _ptr(n_vis), N, M, 16, tile_w, tile_h,
                                      _ptr(flatten_ids), _ptr(offsets), _ptr(ws2), wsb2, _stream()),
                    "b2s_bin_tiles")
     return flatten_ids, offsets
@@ -252,10 +252,10 @@ def _rasterize_one(means, quats, scales, opacities, colors, viewmat, K, width, h
     tile_w = math.ceil(width / 16.0)
     tile_h = math.ceil(height / 16.0)
     calc_comp = rasterize_mode == "antialiased"
-    means2d, geo, colpack, radii, depths, tiles, keys, vals, rects = _Project.apply(
+    means2d, geo, colpack, radii, depths, tiles, keys, rects = _Project.apply(
         means, quats, scales, opacities, cols, viewmat, K, width, height, tile_w, tile_h, float(eps2d),
         float(near_plane), float(far_plane), float(radius_clip), calc_comp, with_depth, cdim)
-    flatten_ids, offsets = _bin(rects, tiles, keys, vals, tile_w, tile_h)
+    flatten_ids, offsets = _bin(rects, tiles, keys, tile_w, tile_h)
     render, alpha = _Blend.apply(means2d, geo, colpack, offsets, flatten_ids, width, height, tile_w, tile_h, cdim,
                                  d_out, ed, bool(absgrad))
     meta = dict(radii=radii.unsqueeze(0), means2d=means2d, depths=depths.unsqueeze(0),
