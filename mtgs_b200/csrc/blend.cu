@@ -238,15 +238,20 @@ __device__ __forceinline__ void pixel_grad(float (&v)[16], float &T, float (&buf
                                            const float B, const float C, const float opac, const float dx,
                                            const float dy, const float alpha, const float vis) {
     const float ra = rcp_approx(1.0f - alpha);  // alpha <= 0.999: well conditioned, 1 ulp is ample
-    T *= ra;
+    T *= ra;                                      // transmittance in front of this Gaussian
     const float fac = alpha * T;
-    float v_alpha = 0.f;
+    // buf[] holds R = (colour accumulated behind this Gaussian) / (transmittance behind it).  Upstream's
+    // (c T - S ra) with S the un-normalised sum equals T (c - R); R is updated as a convex combination
+    // R <- R + alpha (c - R), which needs no division and one multiply less per channel.
+    float acc = 0.f;
 #pragma unroll
     for (int k = 0; k < CDIM; ++k) {
+        const float d = col[k] - buf[k];
         v[8 + k] = fmaf(fac, vrc[k], v[8 + k]);
-        v_alpha = fmaf(fmaf(col[k], T, -buf[k] * ra), vrc[k], v_alpha);
+        acc = fmaf(d, vrc[k], acc);
+        buf[k] = fmaf(alpha, d, buf[k]);
     }
-    v_alpha = fmaf(Tf * ra, vra, v_alpha);
+    const float v_alpha = fmaf(T, acc, Tf * ra * vra);
     if (opac * vis <= B2S_ALPHA_MAX) {
         const float v_sigma = -opac * vis * v_alpha;
         v[4] = fmaf(0.5f * v_sigma * dx, dx, v[4]);
@@ -261,8 +266,6 @@ __device__ __forceinline__ void pixel_grad(float (&v)[16], float &T, float (&buf
         v[3] += fabsf(vy);
         v[7] = fmaf(vis, v_alpha, v[7]);
     }
-#pragma unroll
-    for (int k = 0; k < CDIM; ++k) buf[k] = fmaf(col[k], fac, buf[k]);
 }
 
 // Transposing butterfly: 16 values per lane -> value k summed over the warp lands in lane 2k (and 2k+1).

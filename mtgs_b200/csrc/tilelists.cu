@@ -195,6 +195,8 @@ k_tile_fill(const int2 *__restrict__ rects, const int32_t *__restrict__ order, c
                     const int4 e = s_list[j0 + src];  // broadcast
                     const int rel = bx0 + lane - (e.x & 0xffff);
                     const unsigned wdt = (unsigned)(((e.x >> 16) & 0xffff) - (e.x & 0xffff));
+                    // (a warp-uniform "single 32-tile group" fast path was measured SLOWER than these four
+                    // predicated appends: 0.45 vs 0.39 ms for the whole stage)
 #pragma unroll
                     for (int k = 0; k < TR_NG; ++k) {
                         if ((unsigned)(rel + 32 * k) < wdt) {
