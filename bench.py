@@ -407,18 +407,23 @@ def main():
         w3 = torch.randn(N, 3, device=dev)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         t_f = t_b = 0.0
-        reps = 6
+        reps, inner = 4, 5  # `inner` back-to-back calls per timing so host launch latency is not what is measured
         for it in range(reps + 2):
-            coeffs.grad = None
+            outs = []
             ev[0].record()
-            out = spherical_harmonics(3, dirs, coeffs)
+            for _ in range(inner):
+                outs.append(spherical_harmonics(3, dirs, coeffs))
             ev[1].record()
-            out.backward(w3)
+            for o in outs:
+                coeffs.grad = None
+                o.backward(w3)
             ev[2].record()
             torch.cuda.synchronize()
             if it >= 2:
-                t_f += ev[0].elapsed_time(ev[1])
-                t_b += ev[1].elapsed_time(ev[2])
+                t_f += ev[0].elapsed_time(ev[1]) / inner
+                t_b += ev[1].elapsed_time(ev[2]) / inner
+            out = outs[-1]
+            del outs
         t_f, t_b = t_f / reps, t_b / reps
         b_f = N * (12 + 12 * K_sh + 12)
         b_b = N * (12 + 12 + 12 * K_sh)  # dirs + v_colors in, v_coeffs out (dirs need no grad: coeffs are not re-read)
