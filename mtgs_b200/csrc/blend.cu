@@ -13,6 +13,10 @@
 //     pixel centres already gives alpha < 1/255 contributes to no pixel, so it is dropped from the staged batch
 //     (ballot compaction).  The isect lists stay bit-identical to upstream; only dead work disappears;
 //   * exponent evaluated in log2 units (log2e folded into the conic while staging) -> one ex2.approx per pair;
+//   * both kernels are instruction-issue bound, so the per-pixel arithmetic runs on Blackwell's packed fp32x2
+//     instructions (FFMA2 / FMUL2 / FADD2: two IEEE-rn fp32 operations per issue slot, scalar operands broadcast
+//     for free): a thread's vertically adjacent pixels travel as the two halves of a float2.  Every packed op is
+//     the same rn operation the scalar code performed, so the forward image is bit-identical to the scalar kernel;
 //   * backward: the 16 per-Gaussian partial sums (xy, |xy|, conic, opacity, <=8 colour channels) are reduced
 //     with a transposing butterfly (16 shuffles instead of 16 x 5), parked per warp in shared memory, summed
 //     over the CTA's four warps and flushed with 16-byte vector reductions (red.global.add.v4.f32): at most
@@ -30,6 +34,19 @@ constexpr int BL_BATCH = BL_THREADS;
 __device__ __forceinline__ float splat_power(float A, float B, float C, float dx, float dy) {
     float u = fmaf(B, dy, __fmul_rn(A, dx));
     return fmaf(__fmul_rn(C, dy), dy, __fmul_rn(u, dx));
+}
+
+// ---- packed fp32x2 helpers (sm_100a FFMA2 / FMUL2 / FADD2) ----
+__device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 abs2(float2 a) { return make_float2(fabsf(a.x), fabsf(a.y)); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+// splat_power for two pixels of one column (same dx): identical bits per half as the scalar function
+__device__ __forceinline__ float2 splat_power2(float A, float B, float C, float dx, float2 dy) {
+    const float2 u = fma2(bc2(B), dy, bc2(__fmul_rn(A, dx)));
+    return fma2(mul2(bc2(C), dy), dy, mul2(u, bc2(dx)));
 }
 
 // Can this Gaussian reach alpha >= 1/255 at any pixel centre of the rectangle [rx0,rx1]x[ry0,ry1]?
@@ -108,10 +125,12 @@ k_blend_fwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned lt = lanemask_lt();
 
-    float T0 = 1.f, T1 = 1.f;
-    float acc0[CDIM], acc1[CDIM];
+    // the thread's two pixels (rows y0, y0 + 1) are the halves of every float2 below
+    float2 T = make_float2(1.f, 1.f);
+    float2 acc[CDIM];
 #pragma unroll
-    for (int k = 0; k < CDIM; ++k) acc0[k] = acc1[k] = 0.f;
+    for (int k = 0; k < CDIM; ++k) acc[k] = make_float2(0.f, 0.f);
+    const float2 npy = make_float2(-tg.py0, -tg.py1);
     int cur0 = 0, cur1 = 0;
     bool done0 = !tg.in0, done1 = !tg.in1;
 
@@ -155,47 +174,42 @@ k_blend_fwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
             const float4 sq = s_q[t];
             const float2 sc = s_c[t];
             const float dx = sq.x - tg.px;
-            const float dy0 = sq.y - tg.py0, dy1 = sq.y - tg.py1;
-            const float p0 = splat_power(sq.z, sq.w, sc.x, dx, dy0);
-            const float p1 = splat_power(sq.z, sq.w, sc.x, dx, dy1);
-            const float a0 = fminf(B2S_ALPHA_MAX, __fmul_rn(sc.y, ex2_approx(-p0)));
-            const float a1 = fminf(B2S_ALPHA_MAX, __fmul_rn(sc.y, ex2_approx(-p1)));
-            const bool ok0 = !done0 && p0 >= 0.f && a0 >= B2S_ALPHA_MIN;
-            const bool ok1 = !done1 && p1 >= 0.f && a1 >= B2S_ALPHA_MIN;
+            const float2 dy = add2(bc2(sq.y), npy);
+            const float2 p = splat_power2(sq.z, sq.w, sc.x, dx, dy);
+            const float2 ov = mul2(bc2(sc.y), make_float2(ex2_approx(-p.x), ex2_approx(-p.y)));
+            const float2 al = make_float2(fminf(B2S_ALPHA_MAX, ov.x), fminf(B2S_ALPHA_MAX, ov.y));
+            const bool ok0 = !done0 && p.x >= 0.f && al.x >= B2S_ALPHA_MIN;
+            const bool ok1 = !done1 && p.y >= 0.f && al.y >= B2S_ALPHA_MIN;
             if (ok0 || ok1) {
-                float col[CDIM];
+                const float2 nT = mul2(T, fma2(al, bc2(-1.0f), bc2(1.0f)));  // T (1 - alpha)
+                float2 vis = mul2(al, T);
+                const bool ap0 = ok0 && nT.x > B2S_T_EPS, ap1 = ok1 && nT.y > B2S_T_EPS;  // Gaussian applied
+                done0 = done0 || (ok0 && !ap0);
+                done1 = done1 || (ok1 && !ap1);
+                vis.x = ap0 ? vis.x : 0.f;
+                vis.y = ap1 ? vis.y : 0.f;
+                T.x = ap0 ? nT.x : T.x;
+                T.y = ap1 ? nT.y : T.y;
+                const int id = s_idx[t];
+                cur0 = ap0 ? id : cur0;
+                cur1 = ap1 ? id : cur1;
 #pragma unroll
                 for (int k = 0; k < CQ; ++k) {
                     const float4 v = s_col[t][k];
-                    col[4 * k] = v.x; col[4 * k + 1] = v.y; col[4 * k + 2] = v.z; col[4 * k + 3] = v.w;
-                }
-                const int id = s_idx[t];
-                if (ok0) {
-                    const float nT = __fmul_rn(T0, __fsub_rn(1.0f, a0));
-                    if (nT <= B2S_T_EPS) {
-                        done0 = true;
-                    } else {
-                        const float vis = __fmul_rn(a0, T0);
-#pragma unroll
-                        for (int k = 0; k < CDIM; ++k) acc0[k] = fmaf(col[k], vis, acc0[k]);
-                        cur0 = id;
-                        T0 = nT;
-                    }
-                }
-                if (ok1) {
-                    const float nT = __fmul_rn(T1, __fsub_rn(1.0f, a1));
-                    if (nT <= B2S_T_EPS) {
-                        done1 = true;
-                    } else {
-                        const float vis = __fmul_rn(a1, T1);
-#pragma unroll
-                        for (int k = 0; k < CDIM; ++k) acc1[k] = fmaf(col[k], vis, acc1[k]);
-                        cur1 = id;
-                        T1 = nT;
-                    }
+                    acc[4 * k] = fma2(bc2(v.x), vis, acc[4 * k]);
+                    acc[4 * k + 1] = fma2(bc2(v.y), vis, acc[4 * k + 1]);
+                    acc[4 * k + 2] = fma2(bc2(v.z), vis, acc[4 * k + 2]);
+                    acc[4 * k + 3] = fma2(bc2(v.w), vis, acc[4 * k + 3]);
                 }
             }
         }
+    }
+    const float T0 = T.x, T1 = T.y;
+    float acc0[CDIM], acc1[CDIM];
+#pragma unroll
+    for (int k = 0; k < CDIM; ++k) {
+        acc0[k] = acc[k].x;
+        acc1[k] = acc[k].y;
     }
 
     // epilogue: optional expected-depth normalisation of the last written channel
@@ -230,42 +244,45 @@ k_blend_fwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-// Per-pixel gradient contribution of one Gaussian (upstream rasterize_to_pixels_bwd inner body).
-// v[0..1] = v_mean2d, v[2..3] = |v_mean2d|, v[4..6] = v_conic (a,b,c), v[7] = v_opacity, v[8..] = v_colour.
+// Gradient contribution of one Gaussian at a PAIR of pixels (upstream rasterize_to_pixels_bwd inner body), the two
+// pixels in the halves of every float2.  A pixel the Gaussian does not touch has al = 0 and g = 0, which leaves its
+// T / buf unchanged and adds exact zeros.  Accumulators (summed over the halves and the warp afterwards):
+//   v[0..1] = -v_mean2d, v[2..3] = |v_mean2d|, v[4..6] = -(2 v_conic_a, v_conic_b, 2 v_conic_c), v[7] = v_opacity,
+//   v[8..] = v_colour.  (signs and the factors 1/2 are applied once per Gaussian in the flush)
+//   al = alpha (0 if masked), g = e^-sigma where the alpha clamp is inactive (else 0), ca/cb/cc = raw conic.
 template <int CDIM>
-__device__ __forceinline__ void pixel_grad(float (&v)[16], float &T, float (&buf)[CDIM], const float (&vrc)[CDIM],
-                                           const float vra, const float Tf, const float (&col)[CDIM], const float A,
-                                           const float B, const float C, const float opac, const float dx,
-                                           const float dy, const float alpha, const float vis) {
-    const float ra = rcp_approx(1.0f - alpha);  // alpha <= 0.999: well conditioned, 1 ulp is ample
-    T *= ra;                                      // transmittance in front of this Gaussian
-    const float fac = alpha * T;
+__device__ __forceinline__ void pair_grad(float2 (&v)[16], float2 &T, float2 (&buf)[CDIM], const float2 (&vrc)[CDIM],
+                                          const float2 Tfvra, const float (&col)[CDIM], const float ca, const float cb,
+                                          const float cc, const float opac, const float dx, const float2 dy,
+                                          const float2 al, const float2 g) {
+    const float2 om = fma2(al, bc2(-1.0f), bc2(1.0f));
+    const float2 ra = make_float2(rcp_approx(om.x), rcp_approx(om.y));  // alpha <= 0.999: well conditioned
+    T = mul2(T, ra);                                                     // transmittance in front of this Gaussian
+    const float2 fac = mul2(al, T);
     // buf[] holds R = (colour accumulated behind this Gaussian) / (transmittance behind it).  Upstream's
     // (c T - S ra) with S the un-normalised sum equals T (c - R); R is updated as a convex combination
     // R <- R + alpha (c - R), which needs no division and one multiply less per channel.
-    float acc = 0.f;
+    float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < CDIM; ++k) {
-        const float d = col[k] - buf[k];
-        v[8 + k] = fmaf(fac, vrc[k], v[8 + k]);
-        acc = fmaf(d, vrc[k], acc);
-        buf[k] = fmaf(alpha, d, buf[k]);
+        const float2 d = add2(bc2(col[k]), neg2(buf[k]));
+        v[8 + k] = fma2(fac, vrc[k], v[8 + k]);
+        acc = fma2(d, vrc[k], acc);
+        buf[k] = fma2(al, d, buf[k]);
     }
-    const float v_alpha = fmaf(T, acc, Tf * ra * vra);
-    if (opac * vis <= B2S_ALPHA_MAX) {
-        const float v_sigma = -opac * vis * v_alpha;
-        v[4] = fmaf(0.5f * v_sigma * dx, dx, v[4]);
-        v[5] = fmaf(v_sigma * dx, dy, v[5]);
-        v[6] = fmaf(0.5f * v_sigma * dy, dy, v[6]);
-        const float vs = v_sigma * B2S_LN2;  // conic_raw = (2A, B, 2C) * ln2
-        const float vx = vs * fmaf(2.f * A, dx, B * dy);
-        const float vy = vs * fmaf(B, dx, 2.f * C * dy);
-        v[0] += vx;
-        v[1] += vy;
-        v[2] += fabsf(vx);
-        v[3] += fabsf(vy);
-        v[7] = fmaf(vis, v_alpha, v[7]);
-    }
+    const float2 va = fma2(T, acc, mul2(Tfvra, ra));  // v_alpha
+    v[7] = fma2(g, va, v[7]);
+    const float2 vs = mul2(mul2(bc2(opac), g), va);   // -v_sigma
+    const float2 u = mul2(vs, bc2(dx)), w = mul2(vs, dy);
+    v[4] = fma2(u, bc2(dx), v[4]);
+    v[5] = fma2(u, dy, v[5]);
+    v[6] = fma2(w, dy, v[6]);
+    const float2 vx = fma2(bc2(ca), u, mul2(bc2(cb), w));
+    const float2 vy = fma2(bc2(cb), u, mul2(bc2(cc), w));
+    v[0] = add2(v[0], vx);
+    v[1] = add2(v[1], vy);
+    v[2] = add2(v[2], abs2(vx));
+    v[3] = add2(v[3], abs2(vy));
 }
 
 // Transposing butterfly: 16 values per lane -> value k summed over the warp lands in lane 2k (and 2k+1).
@@ -360,25 +377,36 @@ k_blend_bwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
     const int start = offsets[tile];
     const int end = (tile == tile_w * tile_h - 1) ? (int)M : offsets[tile + 1];
 
-    float T[PX], Tf[PX], vra[PX], py[PX];
-    float vrc[PX][CDIM], buf[PX][CDIM];
+    static_assert(PX % 2 == 0, "pixels travel in pairs");
+    constexpr int NP = PX / 2;  // pixel pairs per thread: rows (ybase + 2 q, ybase + 2 q + 1) are the halves of a float2
+    float2 T[NP], Tfvra[NP], npy[NP];
+    float2 vrc[NP][CDIM], buf[NP][CDIM];
     int bin[PX];
     int maxbin = -1;
 #pragma unroll
     for (int j = 0; j < PX; ++j) {
-        T[j] = Tf[j] = 1.f;
-        vra[j] = 0.f;
-        bin[j] = -1;
-        py[j] = (float)(ybase + j) + 0.5f;
+        float Tj = 1.f, Tfj = 1.f, vraj = 0.f;
+        float vrcj[CDIM];
 #pragma unroll
-        for (int k = 0; k < CDIM; ++k) vrc[j][k] = buf[j][k] = 0.f;
+        for (int k = 0; k < CDIM; ++k) vrcj[k] = 0.f;
+        bin[j] = -1;
         if (x < W && ybase + j < H) {
             const size_t pid = (size_t)(ybase + j) * W + x;
-            load_pixel_cotangent<CDIM, DOUT, ED>(pid, render, alpha_in, v_render, v_alpha, vrc[j], vra[j], Tf[j]);
-            T[j] = Tf[j];
+            load_pixel_cotangent<CDIM, DOUT, ED>(pid, render, alpha_in, v_render, v_alpha, vrcj, vraj, Tfj);
+            Tj = Tfj;
             bin[j] = last_ids[pid];
         }
         maxbin = max(maxbin, bin[j]);
+        const float npyj = -((float)(ybase + j) + 0.5f);
+        if (j & 1) {
+            T[j / 2].y = Tj; Tfvra[j / 2].y = Tfj * vraj; npy[j / 2].y = npyj;
+#pragma unroll
+            for (int k = 0; k < CDIM; ++k) { vrc[j / 2][k].y = vrcj[k]; buf[j / 2][k].y = 0.f; }
+        } else {
+            T[j / 2].x = Tj; Tfvra[j / 2].x = Tfj * vraj; npy[j / 2].x = npyj;
+#pragma unroll
+            for (int k = 0; k < CDIM; ++k) { vrc[j / 2][k].x = vrcj[k]; buf[j / 2][k].x = 0.f; }
+        }
     }
     // last sorted index any pixel of this tile blended
     maxbin = __reduce_max_sync(0xffffffffu, maxbin);
@@ -442,36 +470,42 @@ k_blend_bwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
             const float2 sc = s_c[t];
             const int id = s_idx[t];
             const float dx = sq.x - px;
-            float dy[PX], al[PX], ev[PX];
-            bool ok[PX];
+            float2 dy[NP], al[NP], g[NP];
             bool any_ok = false;
 #pragma unroll
-            for (int j = 0; j < PX; ++j) {
-                dy[j] = sq.y - py[j];
-                const float p = splat_power(sq.z, sq.w, sc.x, dx, dy[j]);
-                ev[j] = ex2_approx(-p);
-                al[j] = fminf(B2S_ALPHA_MAX, __fmul_rn(sc.y, ev[j]));
-                ok[j] = id <= bin[j] && p >= 0.f && al[j] >= B2S_ALPHA_MIN;
-                any_ok = any_ok || ok[j];
+            for (int q = 0; q < NP; ++q) {
+                dy[q] = add2(bc2(sq.y), npy[q]);
+                const float2 p = splat_power2(sq.z, sq.w, sc.x, dx, dy[q]);
+                const float2 ev = make_float2(ex2_approx(-p.x), ex2_approx(-p.y));
+                const float2 ov = mul2(bc2(sc.y), ev);  // opacity * e^-sigma before the 0.999 clamp
+                const float a0 = fminf(B2S_ALPHA_MAX, ov.x), a1 = fminf(B2S_ALPHA_MAX, ov.y);
+                const bool ok0 = id <= bin[2 * q] && p.x >= 0.f && a0 >= B2S_ALPHA_MIN;
+                const bool ok1 = id <= bin[2 * q + 1] && p.y >= 0.f && a1 >= B2S_ALPHA_MIN;
+                al[q] = make_float2(ok0 ? a0 : 0.f, ok1 ? a1 : 0.f);
+                g[q] = make_float2((ok0 && ov.x <= B2S_ALPHA_MAX) ? ev.x : 0.f, (ok1 && ov.y <= B2S_ALPHA_MAX) ? ev.y : 0.f);
+                any_ok = any_ok || ok0 || ok1;
             }
             if (!__any_sync(0xffffffffu, any_ok)) {
                 if (lane < 16) s_acc[warp][t][lane] = 0.f;
                 continue;
             }
-            float v[16];
+            float2 v2[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) v[k] = 0.f;
+            for (int k = 0; k < 16; ++k) v2[k] = make_float2(0.f, 0.f);
             float col[CDIM];
 #pragma unroll
             for (int k = 0; k < CQ; ++k) {
                 const float4 cv = s_col[t][k];
                 col[4 * k] = cv.x; col[4 * k + 1] = cv.y; col[4 * k + 2] = cv.z; col[4 * k + 3] = cv.w;
             }
+            // raw conic (a, b, c) from the log2-domain coefficients: a = 2 A ln2, b = B ln2, c = 2 C ln2
+            const float ca = 2.f * B2S_LN2 * sq.z, cb = B2S_LN2 * sq.w, cc = 2.f * B2S_LN2 * sc.x;
 #pragma unroll
-            for (int j = 0; j < PX; ++j)
-                if (ok[j])
-                    pixel_grad<CDIM>(v, T[j], buf[j], vrc[j], vra[j], Tf[j], col, sq.z, sq.w, sc.x, sc.y, dx, dy[j], al[j],
-                                     ev[j]);
+            for (int q = 0; q < NP; ++q)
+                pair_grad<CDIM>(v2, T[q], buf[q], vrc[q], Tfvra[q], col, ca, cb, cc, sc.y, dx, dy[q], al[q], g[q]);
+            float v[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = v2[k].x + v2[k].y;
             const float r = warp_reduce16_transposed(v, lane);
             if (!(lane & 1)) s_acc[warp][t][lane >> 1] = r;
         }
@@ -489,6 +523,10 @@ k_blend_bwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
                     const float4 o = reinterpret_cast<const float4 *>(&s_acc[w][slot][0])[quad];
                     s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
                 }
+                // undo the accumulation convention of pair_grad: quad 0 = (-v_x, -v_y, |v_x|, |v_y|),
+                // quad 1 = (-2 v_conic_a, -v_conic_b, -2 v_conic_c, v_opacity), quads >= 2 = v_colour
+                if (quad == 0) { s.x = -s.x; s.y = -s.y; }
+                if (quad == 1) { s.x = -0.5f * s.x; s.y = -s.y; s.z = -0.5f * s.z; }
                 if (s.x != 0.f || s.y != 0.f || s.z != 0.f || s.w != 0.f) {
                     const int gid = s_gid[slot];
                     float *dst = quad == 0 ? v_xyabs + (size_t)gid * 4

@@ -5,8 +5,8 @@
 // bits) equals a stable sort of the GAUSSIANS by depth bits followed by an order-preserving bucketing of their
 // intersections by tile (tilelists.cu).  This file produces
 //     order[0 .. n_vis)  Gaussian ids in stable depth order (ties: ascending id), culled Gaussians dropped
-//     cum[0 .. n_vis)    exclusive scan of tiles_per_gauss in that order
-//     total (= M)        number of intersections,     n_vis
+//     totals[2]          M = number of tile intersections, S = number of tile-row hits (sum of rectangle heights)
+//     n_vis
 //
 // A multi-launch LSD radix sort of 2 M keys spent most of its time in launch/drain gaps between ~15 small
 // kernels.  Here a single persistent grid (one launch, cudaLaunchCooperativeKernel, all CTAs co-resident) runs
@@ -15,8 +15,8 @@
 //     -> grid.sync -> digit bases (redundantly per CTA) + stable ranking (match.any groups, per-warp counters)
 //     + scatter -> grid.sync
 // Pass 0 reads the projection's keys directly and drops the culled ones (key 0xFFFFFFFF), so the later passes and
-// everything downstream only touch n_vis items; the value payload of pass 0 is the index itself.  The tile-count
-// scan rides on the same grid (two more barriers).  Integer work on L2-resident data; no tensor cores.
+// everything downstream only touch n_vis items; the value payload of pass 0 is the index itself.  The M / S totals
+// ride on the same grid.  Integer work on L2-resident data; no tensor cores.
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -66,7 +66,7 @@ __device__ __forceinline__ int ds_block_excl_scan(int v, int *total, int *s_w) {
 __global__ void __launch_bounds__(DS_THREADS)
 k_depth_sort_coop(const uint32_t *__restrict__ keys_in, const int32_t *__restrict__ tiles_per_gauss, int N,
                   uint32_t *kA, uint32_t *vA, uint32_t *kB, uint32_t *vB /* == order */, int32_t *table /* [BINS][G] */,
-                  int32_t *digit_tot /* [BINS] */, int32_t *blk_sums /* [G] */, int32_t *cum, int64_t *total_out,
+                  int32_t *digit_tot /* [BINS] */, const int2 *__restrict__ rects, int64_t *totals_out /* [2]: M, S */,
                   int32_t *nvis_out) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ int ds_smem[];
@@ -76,6 +76,7 @@ k_depth_sort_coop(const uint32_t *__restrict__ keys_in, const int32_t *__restric
     const int G = gridDim.x, b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = lanemask_lt();
+    if (b == 0 && tid == 0) totals_out[0] = totals_out[1] = 0;  // accumulated after the last grid barrier
 
     int n = N;  // items entering the current pass
     for (int pass = 0; pass < DS_PASSES; ++pass) {
@@ -188,60 +189,25 @@ k_depth_sort_coop(const uint32_t *__restrict__ keys_in, const int32_t *__restric
         grid.sync();
     }
 
-    // ---- exclusive scan of the tile counts in depth order (order == vB) over the same grid
+    // ---- totals over the visible Gaussians: M = tile intersections, S = tile-row hits (sum of rectangle heights)
     const uint32_t *order = vB;
     const int per = (n + G - 1) / G;
     const int begin = min(n, b * per), end = min(n, begin + per);
-    {
-        int sum = 0;
-        for (int i = begin + tid; i < end; i += DS_THREADS) sum += tiles_per_gauss[order[i]];
-        int tot;
-        ds_block_excl_scan(sum, &tot, s_w);
-        if (tid == 0) blk_sums[b] = tot;
+    long long m = 0, rows = 0;
+    for (int i = begin + tid; i < end; i += DS_THREADS) {
+        const int g = (int)order[i];
+        m += tiles_per_gauss[g];
+        const int ry = rects[g].y;
+        rows += max(0, ((ry >> 16) & 0xffff) - (ry & 0xffff));
     }
-    grid.sync();
-    long long base = 0, all = 0;
-    {
-        long long mine = 0, tot_all = 0;
-        for (int x = tid; x < G; x += DS_THREADS) {
-            const int v = blk_sums[x];
-            tot_all += v;
-            if (x < b) mine += v;
-        }
-        // block reduce of two 64-bit sums through shared memory
-        long long *s_ll = reinterpret_cast<long long *>(s_cnt);
-        s_ll[tid] = mine;
-        s_ll[DS_THREADS + tid] = tot_all;
-        __syncthreads();
-        for (int o = DS_THREADS / 2; o > 0; o >>= 1) {
-            if (tid < o) {
-                s_ll[tid] += s_ll[tid + o];
-                s_ll[DS_THREADS + tid] += s_ll[DS_THREADS + tid + o];
-            }
-            __syncthreads();
-        }
-        base = s_ll[0];
-        all = s_ll[DS_THREADS];
-        __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m += __shfl_xor_sync(0xffffffffu, m, o);
+        rows += __shfl_xor_sync(0xffffffffu, rows, o);
     }
-    if (b == 0 && tid == 0) *total_out = all;
-    int running = (int)base;
-    for (int sub = begin; sub < end; sub += DS_THREADS * 8) {
-        const int i0 = sub + tid * 8;  // thread-contiguous so the serial part is in memory order
-        int v[8], sum = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            v[k] = (i0 + k < end) ? tiles_per_gauss[order[i0 + k]] : 0;
-            sum += v[k];
-        }
-        int tot;
-        int ex = ds_block_excl_scan(sum, &tot, s_w) + running;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (i0 + k < end) cum[i0 + k] = ex;
-            ex += v[k];
-        }
-        running += tot;
+    if (lane == 0 && (m | rows)) {
+        atomicAdd(reinterpret_cast<unsigned long long *>(totals_out), (unsigned long long)m);
+        atomicAdd(reinterpret_cast<unsigned long long *>(totals_out) + 1, (unsigned long long)rows);
     }
 }
 
@@ -263,19 +229,18 @@ static int ds_max_grid(int device) {
 
 extern "C" size_t b2s_bin_depth_workspace_bytes(int N) {
     size_t n = (size_t)(N > 0 ? N : 1);
-    // kA, vA, kB + table [BINS][G<=2048] + digit totals + block sums
-    return 3 * ds_align256(n * 4) + ds_align256((size_t)DS_BINS * 2048 * 4) + ds_align256(DS_BINS * 4) +
-           ds_align256(2048 * 4) + 1024;
+    // kA, vA, kB + table [BINS][G<=2048] + digit totals
+    return 3 * ds_align256(n * 4) + ds_align256((size_t)DS_BINS * 2048 * 4) + ds_align256(DS_BINS * 4) + 1024;
 }
 
-extern "C" int b2s_bin_sort_depth(const uint32_t *sort_keys, const int32_t *tiles_per_gauss, int N, int32_t *order,
-                                  int32_t *cum, int64_t *total, int32_t *n_vis, void *workspace,
+extern "C" int b2s_bin_sort_depth(const uint32_t *sort_keys, const int32_t *tiles_per_gauss, const int32_t *tile_rects,
+                                  int N, int32_t *order, int64_t *totals, int32_t *n_vis, void *workspace,
                                   size_t workspace_bytes, b2s_stream_t stream) {
     if (N < 0) return B2S_ERR_ARG;
     if (workspace_bytes < b2s_bin_depth_workspace_bytes(N)) return B2S_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     if (N == 0) {
-        cudaMemsetAsync(total, 0, sizeof(int64_t), st);
+        cudaMemsetAsync(totals, 0, 2 * sizeof(int64_t), st);
         cudaMemsetAsync(n_vis, 0, sizeof(int32_t), st);
         return B2S_OK;
     }
@@ -291,12 +256,11 @@ extern "C" int b2s_bin_sort_depth(const uint32_t *sort_keys, const int32_t *tile
     uint32_t *vA = (uint32_t *)w; w += n4;
     uint32_t *kB = (uint32_t *)w; w += n4;
     int32_t *table = (int32_t *)w; w += ds_align256((size_t)DS_BINS * 2048 * 4);
-    int32_t *digit_tot = (int32_t *)w; w += ds_align256(DS_BINS * 4);
-    int32_t *blk_sums = (int32_t *)w;
+    int32_t *digit_tot = (int32_t *)w;
     uint32_t *vB = (uint32_t *)order;
+    const int2 *rects = (const int2 *)tile_rects;
     void *args[] = {(void *)&sort_keys, (void *)&tiles_per_gauss, (void *)&N, (void *)&kA, (void *)&vA, (void *)&kB,
-                    (void *)&vB, (void *)&table, (void *)&digit_tot, (void *)&blk_sums, (void *)&cum, (void *)&total,
-                    (void *)&n_vis};
+                    (void *)&vB, (void *)&table, (void *)&digit_tot, (void *)&rects, (void *)&totals, (void *)&n_vis};
     cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_depth_sort_coop, dim3(G), dim3(DS_THREADS), args,
                                                 DS_SMEM, st);
     ++g_b2s_launches;

@@ -1,229 +1,267 @@
 // Per-tile depth-ordered Gaussian lists without sorting the intersections (sm_100a).
 //
-// Replaces, together with binning.cu's depth sort, upstream gsplat v1.4.0 isect_tiles pass 2 + the 64-bit
-// cub radix sort + isect_offset_encode reached from mtgs_scene_graph.py:641-662.
+// Replaces, together with depthsort.cu, upstream gsplat v1.4.0 isect_tiles pass 2 + the 64-bit cub radix sort +
+// isect_offset_encode reached from mtgs_scene_graph.py:641-662.
 //
-// Input: Gaussians in stable depth order (order[], from b2s_bin_sort_depth), the exclusive scan cum[] of
-// their tile counts in that order, and each Gaussian's tile rectangle (tile_rects, from the projection kernel).
-// The (Gaussian x tile) incidence is a sparse matrix given row by row (row = rectangle of one Gaussian);
-// upstream's sorted list is its column-major transpose with rows kept in order.  We build it directly with
-// "tile-owner lanes":
-//   * the depth-ordered Gaussian stream is cut into R chunks of equal cost (k_chunk_bounds);
-//   * the tile grid is cut into bands of <= 24 tile rows x 128 tile columns; a CTA handles one (chunk, band):
-//     warp w owns tile row w of the band, lane l owns the tiles (row, l + 32 k), k = 0..3, and keeps their list
-//     cursors in REGISTERS -- no shared-memory counters, no atomics, no ranking;
-//   * the CTA streams its chunk through shared memory in batches (one coalesced gather of the 8-byte
-//     rectangles per batch, software-pipelined); every warp ballots the batch entries that cover its row and,
-//     for each hit, the lanes whose column lies in [x0, x1) append the Gaussian id at their own cursor.
-//     Entries are visited in stream order, so every tile list is in depth order (ties: ascending id):
-//     bit-identical to the stable global sort.
-//   * pass 1 (k_tile_count) gets count[chunk][tile] from a 2-D difference array (4 corner updates per Gaussian,
-//     independent of its size); k_tile_prefix turns it into per-chunk bases and per-tile totals; their
-//     exclusive scan IS isect_offsets; pass 2 (k_tile_fill) writes flatten_ids.
-// Work ~ (rows covered by the rectangles) ~ M / mean width instead of M; M x 4 B written once.
-// Integer work, issue-bound at full occupancy; no tensor cores.
+// Input: the Gaussians in stable depth order (order[], from b2s_bin_sort_depth) and each Gaussian's tile
+// rectangle (tile_rects, from the projection kernel).  The (Gaussian x tile) incidence is a sparse matrix given
+// row by row (row = rectangle of one Gaussian); upstream's sorted list is its column-major transpose with the
+// rows kept in order.  It is built by two order-preserving "interval multisplits", each perfectly load balanced:
+//   stage 1 (rows):  the depth-ordered stream is cut into chunks of TL_G1 Gaussians (one warp each); every
+//                    Gaussian is appended to the list of each tile ROW its rectangle covers, as an 8-byte hit
+//                    (gaussian id, x0 | x1 << 16).  S = sum of rectangle heights hits in total (~ M / mean width).
+//   stage 2 (tiles): every row list is cut into chunks of TL_G2 hits (one warp each); every hit is appended to
+//                    the list of each TILE of that row in [x0, x1) -> flatten_ids.
+// Both stages are count (difference array in shared memory: 2 atomics per item, independent of its extent) ->
+// exclusive prefix over the chunks -> fill.  The fill never ranks or sorts: a warp takes 32 items, every lane ORs
+// its lane bit into the shared-memory word of each bin its interval covers (transposing the 32 x bins incidence),
+// then lane l OWNS bins l, l+32, ... with their list cursors in registers and appends the items of its words in
+// bit order.  Items are visited in stream order, so every list is in depth order (ties: ascending id): bit-identical
+// to the stable global sort, with M x 4 B written exactly once and no atomics on global memory.
+// Because chunks are cut from the row LISTS (not from the image), tile rows near the horizon that carry several
+// times the mean load simply get more warps.  Integer work; no tensor cores.
 #include <cstdlib>
 
 #include "common.cuh"
 
-constexpr int TR_MAX_ROWS = 24;  // tile rows per band = warps per CTA
-constexpr int TR_NG = 4;         // 32-tile column groups per lane -> 128 tile columns per band
-constexpr int TR_COST_C = 16;    // chunk cost = tiles + TR_COST_C per Gaussian
-constexpr int TR_TARGET_CTAS = 148 * 12;  // chunks per band: rows near the horizon carry most hits, so many short chunks
+constexpr int TL_G1 = 256;      // Gaussians per stage-1 chunk (one warp)
+constexpr int TL_G2 = 512;      // row hits per stage-2 chunk (one warp)
+constexpr int TL_WARPS = 4;     // warps (= chunks) per CTA
+constexpr int TL_NG = 8;        // bins owned per lane -> 256 bins per pass over a chunk (4096 px); more bins: more passes
+constexpr int TL_BAND = 32 * TL_NG;
 
-// f(i) = cum[i] + c * i is the cost of the stream before Gaussian i; first i in [0, nv) with f(i) >= target, else nv
-__device__ __forceinline__ int lower_bound_cost(const int32_t *__restrict__ cum, int nv, long long c, long long target) {
-    int lo = 0, hi = nv;
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if ((long long)cum[mid] + c * mid < target) lo = mid + 1;
-        else hi = mid;
+__device__ __forceinline__ int tl_warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += n;
     }
-    return lo;
+    return v;
 }
 
-// bounds[r] (r = 0..R) = first Gaussian of chunk r in the depth-ordered stream; bounds[R] = n_vis.
-__global__ void __launch_bounds__(1024)
-k_chunk_bounds(const int32_t *__restrict__ cum, const int32_t *__restrict__ n_vis, long long M, int R,
-               int32_t *__restrict__ bounds) {
-    const int nv = *n_vis;  // Gaussians that own intersections (depthsort.cu drops the culled ones)
-    const long long C = M + (long long)TR_COST_C * nv;
-    for (int r = threadIdx.x; r <= R; r += blockDim.x)
-        bounds[r] = (r == R) ? nv : lower_bound_cost(cum, nv, TR_COST_C, ((long long)r * C + R - 1) / R);
+// ---- interval counting: one warp, items [begin, end), interval of item i over bins = iv(i) -> (lo, hi).
+// s_d: nbins + 1 ints of this warp's shared memory.  Afterwards lane-strided s_d[b] = number of items covering bin b.
+template <class IV>
+__device__ __forceinline__ void tl_warp_count(int *s_d, int nbins, int begin, int end, int lane, IV iv) {
+    for (int b = lane; b <= nbins; b += 32) s_d[b] = 0;
+    __syncwarp();
+    for (int i = begin + lane; i < end; i += 32) {
+        int lo, hi;
+        iv(i, lo, hi);
+        if (hi > lo) {
+            atomicAdd(&s_d[lo], 1);
+            atomicAdd(&s_d[hi], -1);
+        }
+    }
+    __syncwarp();
+    int carry = 0;
+    for (int b0 = 0; b0 < nbins; b0 += 32) {
+        const int v = (b0 + lane < nbins) ? s_d[b0 + lane] : 0;
+        const int incl = tl_warp_incl_scan(v, lane) + carry;
+        if (b0 + lane < nbins) s_d[b0 + lane] = incl;
+        carry = __shfl_sync(0xffffffffu, incl, 31);
+    }
+    __syncwarp();
 }
 
-// ------------------------------------------------------------------------------------------------
-// pass 1: count[chunk][tile] for one (chunk, band) through a 2-D difference array in shared memory:
-// every thread adds ONE rectangle (4 corner updates), independent of how many tiles it covers.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32 * TR_MAX_ROWS)
-k_tile_count(const int2 *__restrict__ rects, const int32_t *__restrict__ order, const int32_t *__restrict__ bounds,
-             int tile_w, int tile_h, int rows_per_band, int row_bands, int R, int32_t *__restrict__ table /* [R][T] */) {
-    constexpr int CW = 32 * TR_NG + 1;  // difference array width (columns of the band + 1)
-    extern __shared__ int s_d[];        // (rows_per_band + 1) x CW
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int chunk = blockIdx.x % R;
-    const int band = blockIdx.x / R;
-    const int band_y = band % row_bands, band_x = band / row_bands;
-    const int T = tile_w * tile_h;
-    const int by0 = band_y * rows_per_band, by1 = min(tile_h, by0 + rows_per_band);
-    const int bx0 = band_x * (32 * TR_NG), bx1 = min(tile_w, bx0 + 32 * TR_NG);
-    const int rows = by1 - by0, cols = bx1 - bx0;
-    for (int t = tid; t < (rows_per_band + 1) * CW; t += blockDim.x) s_d[t] = 0;
-    __syncthreads();
-    const int i_begin = bounds[chunk], i_end = bounds[chunk + 1];
-    for (int i = i_begin + tid; i < i_end; i += blockDim.x) {
-        const int2 rc = rects[order[i]];
-        const int x0 = max(rc.x & 0xffff, bx0), x1 = min((rc.x >> 16) & 0xffff, bx1);
-        const int y0 = max(rc.y & 0xffff, by0), y1 = min((rc.y >> 16) & 0xffff, by1);
-        if (x1 > x0 && y1 > y0) {
-            atomicAdd(&s_d[(y0 - by0) * CW + (x0 - bx0)], 1);
-            atomicAdd(&s_d[(y0 - by0) * CW + (x1 - bx0)], -1);
-            atomicAdd(&s_d[(y1 - by0) * CW + (x0 - bx0)], -1);
-            atomicAdd(&s_d[(y1 - by0) * CW + (x1 - bx0)], 1);
-        }
-    }
-    __syncthreads();
-    // integrate along x: warp w owns row w (warp scan with carry)
-    if (warp < rows) {
-        int carry = 0;
-        for (int x = 0; x < cols; x += 32) {
-            int v = (x + lane < cols) ? s_d[warp * CW + x + lane] : 0;
+// ---- ordered fill: one warp, items [begin, end) in stream order.  load(i, lo, hi, payload) describes item i;
+// cursor0(bin) is the output index of the first item this chunk appends to `bin`; out receives the payloads.
+// s_words: TL_BAND ints, s_pay: 32 payloads (this warp's shared memory).
+template <class PAY, class LOAD, class CUR>
+__device__ __forceinline__ void tl_warp_fill(unsigned *s_words, PAY *s_pay, int nbins, int begin, int end, int lane,
+                                             LOAD load, CUR cursor0, PAY *__restrict__ out) {
+    for (int band = 0; band < nbins; band += TL_BAND) {  // one pass unless there are more than 256 bins
+        int cur[TL_NG];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int n = __shfl_up_sync(0xffffffffu, v, o);
-                if (lane >= o) v += n;
-            }
-            v += carry;
-            if (x + lane < cols) s_d[warp * CW + x + lane] = v;
-            carry = __shfl_sync(0xffffffffu, v, 31);
+        for (int k = 0; k < TL_NG; ++k) {
+            const int b = band + lane + 32 * k;
+            cur[k] = b < nbins ? cursor0(b) : 0;
         }
-    }
-    __syncthreads();
-    // integrate along y: thread x owns a column; table rows are written coalesced
-    for (int x = tid; x < cols; x += blockDim.x) {
-        int run = 0;
-        for (int r = 0; r < rows; ++r) {
-            run += s_d[r * CW + x];
-            table[(size_t)chunk * T + (size_t)(by0 + r) * tile_w + bx0 + x] = run;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// pass 2: ordered fill.  Phase A compacts (in stream order) the chunk's rectangles that touch the band into a
-// shared-memory list; phase B lets every warp (= tile row) walk that list on its own, lanes appending at
-// register cursors.  The two phases alternate until the chunk is consumed.
-// ------------------------------------------------------------------------------------------------
-constexpr int TR_LIST_CAP = 2048;  // band-filtered entries buffered per round (32 KB)
-
-__global__ void __launch_bounds__(32 * TR_MAX_ROWS)
-k_tile_fill(const int2 *__restrict__ rects, const int32_t *__restrict__ order, const int32_t *__restrict__ bounds,
-            int tile_w, int tile_h, int rows_per_band, int row_bands, int R, const int32_t *__restrict__ table,
-            const int32_t *__restrict__ offsets, int32_t *__restrict__ flatten_ids) {
-    __shared__ int4 s_list[TR_LIST_CAP];       // (x0 | x1 << 16, y0 | y1 << 16, gid, -), band-filtered, in order
-    __shared__ int s_wcnt[2][TR_MAX_ROWS];
-    const int B = blockDim.x, nwarps = B >> 5;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned lt = lanemask_lt();
-    const int chunk = blockIdx.x % R;
-    const int band = blockIdx.x / R;
-    const int band_y = band % row_bands, band_x = band / row_bands;
-    const int T = tile_w * tile_h;
-    const int by0 = band_y * rows_per_band, by1 = min(tile_h, by0 + rows_per_band);
-    const int bx0 = band_x * (32 * TR_NG), bx1 = min(tile_w, bx0 + 32 * TR_NG);
-    const int y = by0 + warp;
-    const bool row_ok = y < by1;
-
-    int cur[TR_NG];
+        const int nk = min(TL_NG, (nbins - band + 31) >> 5);  // word groups in use (warp-uniform)
+        for (int i0 = begin; i0 < end; i0 += 32) {
+            int lo = 0, hi = 0;
+            PAY pay = PAY();
+            if (i0 + lane < end) load(i0 + lane, lo, hi, pay);
+            lo = max(lo - band, 0);
+            hi = min(hi - band, TL_BAND);
+            s_pay[lane] = pay;
 #pragma unroll
-    for (int k = 0; k < TR_NG; ++k) {
-        const int x = bx0 + lane + 32 * k;
-        cur[k] = 0;
-        if (row_ok && x < bx1) cur[k] = offsets[y * tile_w + x] + table[(size_t)chunk * T + y * tile_w + x];
-    }
-    const int i_begin = bounds[chunk], i_end = bounds[chunk + 1];
-
-    int base = i_begin;
-    int2 rc = make_int2(0, 0);
-    int gid = 0;
-    if (base + tid < i_end) {
-        gid = order[base + tid];
-        rc = rects[gid];
-    }
-    int par = 0;
-    while (true) {
-        // ---- phase A: append whole batches while they fit
-        int fill = 0;
-        while (base < i_end) {
-            const bool keep = (base + tid < i_end) && (rc.x & 0xffff) < bx1 && ((rc.x >> 16) & 0xffff) > bx0 &&
-                              (rc.y & 0xffff) < by1 && ((rc.y >> 16) & 0xffff) > by0;
-            const unsigned bal = __ballot_sync(0xffffffffu, keep);
-            if (lane == 0) s_wcnt[par][warp] = __popc(bal);
-            __syncthreads();
-            int off = 0, tot = 0;
-            for (int w = 0; w < nwarps; ++w) {
-                const int n = s_wcnt[par][w];
-                off += (w < warp) ? n : 0;
-                tot += n;
-            }
-            par ^= 1;
-            if (fill + tot > TR_LIST_CAP) break;  // uniform: this batch stays in registers for the next round
-            if (keep) s_list[fill + off + __popc(bal & lt)] = make_int4(rc.x, rc.y, gid, 0);
-            fill += tot;
-            base += B;
-            rc = make_int2(0, 0);
-            gid = 0;
-            if (base + tid < i_end) {
-                gid = order[base + tid];
-                rc = rects[gid];
-            }
-        }
-        __syncthreads();
-        // ---- phase B: every warp walks the list for its own tile row, no barriers
-        if (row_ok) {
-            for (int j0 = 0; j0 < fill; j0 += 32) {
-                bool hit = false;
-                if (j0 + lane < fill) {
-                    const int ey = s_list[j0 + lane].y;
-                    hit = y >= (ey & 0xffff) && y < ((ey >> 16) & 0xffff);
-                }
-                unsigned m = __ballot_sync(0xffffffffu, hit);
-                while (m) {
-                    const int src = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int4 e = s_list[j0 + src];  // broadcast
-                    const int rel = bx0 + lane - (e.x & 0xffff);
-                    const unsigned wdt = (unsigned)(((e.x >> 16) & 0xffff) - (e.x & 0xffff));
-                    // (a warp-uniform "single 32-tile group" fast path was measured SLOWER than these four
-                    // predicated appends: 0.45 vs 0.39 ms for the whole stage)
+            for (int k = 0; k < TL_NG; ++k)
+                if (k < nk) s_words[lane + 32 * k] = 0u;
+            __syncwarp();
+            for (int b = lo; b < hi; ++b) atomicOr(&s_words[b], 1u << lane);
+            __syncwarp();
 #pragma unroll
-                    for (int k = 0; k < TR_NG; ++k) {
-                        if ((unsigned)(rel + 32 * k) < wdt) {
-                            flatten_ids[cur[k]] = e.z;
-                            ++cur[k];
-                        }
+            for (int k = 0; k < TL_NG; ++k) {
+                if (k < nk) {
+                    unsigned w = s_words[lane + 32 * k];
+                    while (w) {
+                        const int j = __ffs(w) - 1;
+                        w &= w - 1;
+                        out[cur[k]++] = s_pay[j];
                     }
                 }
             }
+            __syncwarp();
         }
-        if (base >= i_end) break;
-        __syncthreads();  // list fully consumed before phase A overwrites it
     }
 }
 
-// For every tile: exclusive prefix of table[.][tile] over the chunks (in place) and the tile's total.
-// Block = 8 warps x 32 consecutive tiles; warp w owns the chunks [w*R/8, (w+1)*R/8).
+// ------------------------------------------------------------------------------------------------
+// stage 1: rows
+// ------------------------------------------------------------------------------------------------
+// count1[y * nc1s + c] = number of Gaussians of chunk c whose rectangle covers tile row y
+__global__ void __launch_bounds__(32 * TL_WARPS)
+k_rows_count(const int2 *__restrict__ rects, const int32_t *__restrict__ order, const int32_t *__restrict__ n_vis,
+             int tile_h, int nc1s, int32_t *__restrict__ count1) {
+    extern __shared__ int s_dyn[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nv = *n_vis;
+    const int c = blockIdx.x * TL_WARPS + warp;
+    const int begin = c * TL_G1;
+    if (begin >= nv) return;
+    const int end = min(nv, begin + TL_G1);
+    int *s_d = s_dyn + warp * (tile_h + 1);
+    tl_warp_count(s_d, tile_h, begin, end, lane, [&](int i, int &lo, int &hi) {
+        const int ry = rects[order[i]].y;
+        lo = ry & 0xffff;
+        hi = min((ry >> 16) & 0xffff, tile_h);
+    });
+    for (int y = lane; y < tile_h; y += 32) count1[(size_t)y * nc1s + c] = s_d[y];
+}
+
+// one CTA per tile row: in-place exclusive scan of count1[y][0 .. nc1) over the chunks; row_len[y] = total
 __global__ void __launch_bounds__(256)
-k_tile_prefix(int32_t *__restrict__ table, int R, int T, int32_t *__restrict__ tile_total) {
+k_rows_prefix(int32_t *__restrict__ count1, const int32_t *__restrict__ n_vis, int nc1s, int32_t *__restrict__ row_len) {
+    __shared__ int s_w[9];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nc1 = (*n_vis + TL_G1 - 1) / TL_G1;
+    int32_t *r = count1 + (size_t)blockIdx.x * nc1s;
+    const int per = (nc1 + 255) / 256;
+    const int b = min(nc1, tid * per), e = min(nc1, b + per);
+    int sum = 0;
+    for (int i = b; i < e; ++i) sum += r[i];
+    const int incl = tl_warp_incl_scan(sum, lane);
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int w = lane < 8 ? s_w[lane] : 0;
+        const int wi = tl_warp_incl_scan(w, lane);
+        if (lane < 8) s_w[lane] = wi - w;
+        if (lane == 7) s_w[8] = wi;
+    }
+    __syncthreads();
+    int run = s_w[warp] + incl - sum;
+    for (int i = b; i < e; ++i) {
+        const int v = r[i];
+        r[i] = run;
+        run += v;
+    }
+    if (tid == 0) row_len[blockIdx.x] = s_w[8];
+}
+
+// one warp: row_off = exclusive scan of row_len, chunk_off = exclusive scan of ceil(row_len / TL_G2); entry
+// [tile_h] holds the totals (S and the number of stage-2 chunks).
+__global__ void __launch_bounds__(32)
+k_rows_offsets(const int32_t *__restrict__ row_len, int tile_h, int32_t *__restrict__ row_off,
+               int32_t *__restrict__ chunk_off) {
+    const int lane = threadIdx.x;
+    int carry_r = 0, carry_c = 0;
+    for (int y0 = 0; y0 < tile_h; y0 += 32) {
+        const int y = y0 + lane;
+        const int len = y < tile_h ? row_len[y] : 0;
+        const int nch = (len + TL_G2 - 1) / TL_G2;
+        const int ir = tl_warp_incl_scan(len, lane), ic = tl_warp_incl_scan(nch, lane);
+        if (y < tile_h) {
+            row_off[y] = carry_r + ir - len;
+            chunk_off[y] = carry_c + ic - nch;
+        }
+        carry_r += __shfl_sync(0xffffffffu, ir, 31);
+        carry_c += __shfl_sync(0xffffffffu, ic, 31);
+    }
+    if (lane == 0) {
+        row_off[tile_h] = carry_r;
+        chunk_off[tile_h] = carry_c;
+    }
+}
+
+// row_list[row_off[y] ..) = the Gaussians covering tile row y, in depth order, as (id, x0 | x1 << 16)
+__global__ void __launch_bounds__(32 * TL_WARPS)
+k_rows_fill(const int2 *__restrict__ rects, const int32_t *__restrict__ order, const int32_t *__restrict__ n_vis,
+            int tile_h, int nc1s, const int32_t *__restrict__ count1, const int32_t *__restrict__ row_off,
+            int2 *__restrict__ row_list) {
+    __shared__ unsigned s_words[TL_WARPS][TL_BAND];
+    __shared__ int2 s_pay[TL_WARPS][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nv = *n_vis;
+    const int c = blockIdx.x * TL_WARPS + warp;
+    const int begin = c * TL_G1;
+    if (begin >= nv) return;
+    const int end = min(nv, begin + TL_G1);
+    tl_warp_fill<int2>(
+        s_words[warp], s_pay[warp], tile_h, begin, end, lane,
+        [&](int i, int &lo, int &hi, int2 &pay) {
+            const int g = order[i];
+            const int2 rc = rects[g];
+            lo = rc.y & 0xffff;
+            hi = min((rc.y >> 16) & 0xffff, tile_h);
+            pay = make_int2(g, rc.x);
+        },
+        [&](int y) { return row_off[y] + count1[(size_t)y * nc1s + c]; }, row_list);
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage 2: tiles.  Stage-2 chunk c2 = hits [row_off[y] + k * TL_G2, ...) of row y, where chunk_off[y] <= c2 <
+// chunk_off[y + 1] and k = c2 - chunk_off[y].
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool tl_chunk2(int c2, int tile_h, const int32_t *__restrict__ row_off,
+                                          const int32_t *__restrict__ chunk_off, int &y, int &begin, int &end) {
+    if (c2 >= chunk_off[tile_h]) return false;
+    int lo = 0, hi = tile_h;  // last y with chunk_off[y] <= c2
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (chunk_off[mid] <= c2) lo = mid;
+        else hi = mid;
+    }
+    y = lo;
+    begin = row_off[y] + (c2 - chunk_off[y]) * TL_G2;
+    end = min(row_off[y + 1], begin + TL_G2);
+    return true;
+}
+
+// table2[c2 * tile_w + x] = number of hits of chunk c2 covering tile x of its row
+__global__ void __launch_bounds__(32 * TL_WARPS)
+k_tiles_count(const int2 *__restrict__ row_list, const int32_t *__restrict__ row_off,
+              const int32_t *__restrict__ chunk_off, int tile_w, int tile_h, int32_t *__restrict__ table2) {
+    extern __shared__ int s_dyn[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c2 = blockIdx.x * TL_WARPS + warp;
+    int y, begin, end;
+    if (!tl_chunk2(c2, tile_h, row_off, chunk_off, y, begin, end)) return;
+    int *s_d = s_dyn + warp * (tile_w + 1);
+    tl_warp_count(s_d, tile_w, begin, end, lane, [&](int i, int &lo, int &hi) {
+        const int rx = row_list[i].y;
+        lo = rx & 0xffff;
+        hi = min((rx >> 16) & 0xffff, tile_w);
+    });
+    for (int x = lane; x < tile_w; x += 32) table2[(size_t)c2 * tile_w + x] = s_d[x];
+}
+
+// CTA = (tile row y, 32 consecutive tiles of it); 8 warps split the row's chunks.  In-place exclusive prefix of
+// table2[.][x] over the chunks of row y, and the tile's total.
+__global__ void __launch_bounds__(256)
+k_tiles_prefix(int32_t *__restrict__ table2, const int32_t *__restrict__ chunk_off, int tile_w,
+               int32_t *__restrict__ tile_total) {
     __shared__ int s_part[8][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int t = blockIdx.x * 32 + lane;
-    const int r0 = (int)((long long)w * R / 8), r1 = (int)((long long)(w + 1) * R / 8);
+    const int y = blockIdx.y;
+    const int x = blockIdx.x * 32 + lane;
+    const int c0 = chunk_off[y], nc = chunk_off[y + 1] - c0;
+    const int r0 = c0 + (int)((long long)w * nc / 8), r1 = c0 + (int)((long long)(w + 1) * nc / 8);
     int sum = 0;
-    if (t < T) {
+    if (x < tile_w) {
 #pragma unroll 4
-        for (int r = r0; r < r1; ++r) sum += table[(size_t)r * T + t];
+        for (int r = r0; r < r1; ++r) sum += table2[(size_t)r * tile_w + x];
     }
     s_part[w][lane] = sum;
     __syncthreads();
@@ -234,88 +272,155 @@ k_tile_prefix(int32_t *__restrict__ table, int R, int T, int32_t *__restrict__ t
         run += (k < w) ? v : 0;
         tot += v;
     }
-    if (t < T) {
-        if (w == 0) tile_total[t] = tot;
+    if (x < tile_w) {
+        if (w == 0) tile_total[y * tile_w + x] = tot;
         for (int r = r0; r < r1; ++r) {
-            const size_t a = (size_t)r * T + t;
-            const int v = table[a];
-            table[a] = run;
+            const size_t a = (size_t)r * tile_w + x;
+            const int v = table2[a];
+            table2[a] = run;
             run += v;
         }
     }
 }
 
-static inline size_t tl_align256(size_t x) { return (x + 255) & ~(size_t)255; }
-
-struct TlPlan {
-    int rows_per_band, row_bands, col_bands, R;
-};
-
-static TlPlan tl_plan(int N, int tile_w, int tile_h) {
-    TlPlan p;
-    p.row_bands = (tile_h + 19) / 20;                         // ~20 rows per band ...
-    p.rows_per_band = (tile_h + p.row_bands - 1) / p.row_bands;  // ... evenly split (1080p: 4 x 17)
-    p.col_bands = (tile_w + 32 * TR_NG - 1) / (32 * TR_NG);
-    int bands = p.row_bands * p.col_bands;
-    static const int target_ctas = [] {  // tuning knob (read once): B2S_TL_CTAS overrides the CTA budget
-        const char *e = getenv("B2S_TL_CTAS");
-        int v = e ? atoi(e) : 0;
-        return v > 0 ? v : TR_TARGET_CTAS;
-    }();
-    int r = target_ctas / bands;
-    int by_work = N / 512;  // no point in chunks shorter than a batch
-    if (r > by_work) r = by_work;
-    if (r > 1023) r = 1023;
-    if (r < 1) r = 1;
-    p.R = r;
-    return p;
+// single CTA: isect_offsets = exclusive scan of tile_total (T = 8160 at 1080p, 32400 at 4K)
+__global__ void __launch_bounds__(1024)
+k_tiles_offsets(const int32_t *__restrict__ tile_total, int T, int32_t *__restrict__ offsets) {
+    __shared__ int s_w[33];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int carry = 0;
+    for (int base = 0; base < T; base += 1024 * 8) {
+        const int i0 = base + tid * 8;
+        int v[8], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            v[k] = (i0 + k < T) ? tile_total[i0 + k] : 0;
+            sum += v[k];
+        }
+        const int incl = tl_warp_incl_scan(sum, lane);
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int wv = s_w[lane];
+            const int wi = tl_warp_incl_scan(wv, lane);
+            s_w[lane] = wi - wv;
+            if (lane == 31) s_w[32] = wi;
+        }
+        __syncthreads();
+        int ex = carry + s_w[warp] + incl - sum;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (i0 + k < T) offsets[i0 + k] = ex;
+            ex += v[k];
+        }
+        carry += s_w[32];
+        __syncthreads();
+    }
 }
+
+// flatten_ids[isect_offsets[t] ..) = the Gaussians intersecting tile t, in depth order
+__global__ void __launch_bounds__(32 * TL_WARPS)
+k_tiles_fill(const int2 *__restrict__ row_list, const int32_t *__restrict__ row_off,
+             const int32_t *__restrict__ chunk_off, int tile_w, int tile_h, const int32_t *__restrict__ table2,
+             const int32_t *__restrict__ offsets, int32_t *__restrict__ flatten_ids) {
+    __shared__ unsigned s_words[TL_WARPS][TL_BAND];
+    __shared__ int s_pay[TL_WARPS][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c2 = blockIdx.x * TL_WARPS + warp;
+    int y, begin, end;
+    if (!tl_chunk2(c2, tile_h, row_off, chunk_off, y, begin, end)) return;
+    tl_warp_fill<int>(
+        s_words[warp], s_pay[warp], tile_w, begin, end, lane,
+        [&](int i, int &lo, int &hi, int &pay) {
+            const int2 h = row_list[i];
+            lo = h.y & 0xffff;
+            hi = min((h.y >> 16) & 0xffff, tile_w);
+            pay = h.x;
+        },
+        [&](int x) { return offsets[y * tile_w + x] + table2[(size_t)c2 * tile_w + x]; }, flatten_ids);
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+static inline size_t tl_align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static inline bool tl_supported(int tile_w, int tile_h) {
     return tile_w > 0 && tile_h > 0 && tile_w <= 32767 && tile_h <= 32767;
 }
 
-extern "C" size_t b2s_bin_tiles_workspace_bytes(int N, long long M, int tile_w, int tile_h) {
-    (void)M;
-    if (!tl_supported(tile_w, tile_h)) return 0;
-    TlPlan p = tl_plan(N, tile_w, tile_h);
-    size_t T = (size_t)tile_w * tile_h;
-    return tl_align256((size_t)p.R * T * 4) + tl_align256(T * 4) + tl_align256(b2s_scan_ws_ints((int)T) * 4) +
-           tl_align256((size_t)(p.R + 1) * 4) + 1024;
+struct TlLayout {
+    int nc1s;        // stage-1 chunks (upper bound from N)
+    long long nc2s;  // stage-2 chunks (upper bound from S)
+    size_t count1, row_len, row_off, chunk_off, row_list, table2, tile_total, total;
+};
+
+static TlLayout tl_layout(int N, long long S, int tile_w, int tile_h) {
+    TlLayout L;
+    L.nc1s = b2s_div_up(N > 0 ? N : 1, TL_G1);
+    L.nc2s = S / TL_G2 + tile_h;
+    size_t o = 0;
+    L.count1 = o; o += tl_align256((size_t)tile_h * L.nc1s * 4);
+    L.row_len = o; o += tl_align256((size_t)tile_h * 4);
+    L.row_off = o; o += tl_align256((size_t)(tile_h + 1) * 4);
+    L.chunk_off = o; o += tl_align256((size_t)(tile_h + 1) * 4);
+    L.row_list = o; o += tl_align256((size_t)(S > 0 ? S : 1) * 8);
+    L.table2 = o; o += tl_align256((size_t)L.nc2s * tile_w * 4);
+    L.tile_total = o; o += tl_align256((size_t)tile_w * tile_h * 4);
+    L.total = o + 1024;
+    return L;
 }
 
-extern "C" int b2s_bin_tiles(const int32_t *tile_rects, const int32_t *order, const int32_t *cum,
-                             const int32_t *n_vis, int N, long long M, int tile_size, int tile_w, int tile_h, int32_t *flatten_ids, int32_t *isect_offsets,
-                             void *workspace, size_t workspace_bytes, b2s_stream_t stream) {
-    if (N < 0 || M < 0 || M >= (1LL << 31) || tile_w <= 0 || tile_h <= 0) return B2S_ERR_ARG;
+extern "C" size_t b2s_bin_tiles_workspace_bytes(int N, long long M, long long S, int tile_w, int tile_h) {
+    (void)M;
+    if (!tl_supported(tile_w, tile_h) || S < 0) return 0;
+    return tl_layout(N, S, tile_w, tile_h).total;
+}
+
+extern "C" int b2s_bin_tiles(const int32_t *tile_rects, const int32_t *order, const int32_t *n_vis, int N, long long M,
+                             long long S, int tile_size, int tile_w, int tile_h, int32_t *flatten_ids,
+                             int32_t *isect_offsets, void *workspace, size_t workspace_bytes, b2s_stream_t stream) {
+    if (N < 0 || M < 0 || S < 0 || S >= (1LL << 31) || M >= (1LL << 31) || tile_w <= 0 || tile_h <= 0) return B2S_ERR_ARG;
     if (tile_size != 16 || !tl_supported(tile_w, tile_h)) return B2S_ERR_UNSUPPORTED;
-    if (workspace_bytes < b2s_bin_tiles_workspace_bytes(N, M, tile_w, tile_h)) return B2S_ERR_WORKSPACE;
+    if (workspace_bytes < b2s_bin_tiles_workspace_bytes(N, M, S, tile_w, tile_h)) return B2S_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const int T = tile_w * tile_h;
     if (M == 0 || N == 0) {
         cudaMemsetAsync(isect_offsets, 0, sizeof(int32_t) * (size_t)T, st);
         return B2S_OK;
     }
-    const TlPlan p = tl_plan(N, tile_w, tile_h);
+    const TlLayout L = tl_layout(N, S, tile_w, tile_h);
     char *w = (char *)workspace;
-    int32_t *table = (int32_t *)w; w += tl_align256((size_t)p.R * T * 4);
-    int32_t *tile_total = (int32_t *)w; w += tl_align256((size_t)T * 4);
-    int32_t *sws = (int32_t *)w; w += tl_align256(b2s_scan_ws_ints(T) * 4);
-    int32_t *bounds = (int32_t *)w;
-    const int threads = 32 * p.rows_per_band;
-    const int grid = p.R * p.row_bands * p.col_bands;
-    const size_t smem_count = (size_t)(p.rows_per_band + 1) * (32 * TR_NG + 1) * sizeof(int);
-    k_chunk_bounds<<<1, 1024, 0, st>>>(cum, n_vis, M, p.R, bounds);
+    int32_t *count1 = (int32_t *)(w + L.count1);
+    int32_t *row_len = (int32_t *)(w + L.row_len);
+    int32_t *row_off = (int32_t *)(w + L.row_off);
+    int32_t *chunk_off = (int32_t *)(w + L.chunk_off);
+    int2 *row_list = (int2 *)(w + L.row_list);
+    int32_t *table2 = (int32_t *)(w + L.table2);
+    int32_t *tile_total = (int32_t *)(w + L.tile_total);
+    const int2 *rects = (const int2 *)tile_rects;
+
+    const int grid1 = b2s_div_up(L.nc1s, TL_WARPS);
+    const int grid2 = b2s_div_up(L.nc2s, TL_WARPS);
+    const size_t smem1 = (size_t)TL_WARPS * (tile_h + 1) * sizeof(int);
+    const size_t smem2 = (size_t)TL_WARPS * (tile_w + 1) * sizeof(int);
+    if (smem1 > 48 * 1024 || smem2 > 48 * 1024) return B2S_ERR_UNSUPPORTED;
+    k_rows_count<<<grid1, 32 * TL_WARPS, smem1, st>>>(rects, order, n_vis, tile_h, L.nc1s, count1);
     B2S_LAUNCH_CHECK();
-    k_tile_count<<<grid, threads, smem_count, st>>>((const int2 *)tile_rects, order, bounds, tile_w, tile_h,
-                                                     p.rows_per_band, p.row_bands, p.R, table);
+    k_rows_prefix<<<tile_h, 256, 0, st>>>(count1, n_vis, L.nc1s, row_len);
     B2S_LAUNCH_CHECK();
-    k_tile_prefix<<<b2s_div_up(T, 32), 256, 0, st>>>(table, p.R, T, tile_total);
+    k_rows_offsets<<<1, 32, 0, st>>>(row_len, tile_h, row_off, chunk_off);
     B2S_LAUNCH_CHECK();
-    int rc = b2s_device_excl_scan(tile_total, nullptr, T, isect_offsets, nullptr, sws, st);
-    if (rc != B2S_OK) return rc;
-    k_tile_fill<<<grid, threads, 0, st>>>((const int2 *)tile_rects, order, bounds, tile_w, tile_h, p.rows_per_band,
-                                           p.row_bands, p.R, table, isect_offsets, flatten_ids);
+    k_rows_fill<<<grid1, 32 * TL_WARPS, 0, st>>>(rects, order, n_vis, tile_h, L.nc1s, count1, row_off, row_list);
+    B2S_LAUNCH_CHECK();
+    k_tiles_count<<<grid2, 32 * TL_WARPS, smem2, st>>>(row_list, row_off, chunk_off, tile_w, tile_h, table2);
+    B2S_LAUNCH_CHECK();
+    k_tiles_prefix<<<dim3(b2s_div_up(tile_w, 32), tile_h), 256, 0, st>>>(table2, chunk_off, tile_w, tile_total);
+    B2S_LAUNCH_CHECK();
+    k_tiles_offsets<<<1, 1024, 0, st>>>(tile_total, T, isect_offsets);
+    B2S_LAUNCH_CHECK();
+    k_tiles_fill<<<grid2, 32 * TL_WARPS, 0, st>>>(row_list, row_off, chunk_off, tile_w, tile_h, table2, isect_offsets,
+                                                  flatten_ids);
     B2S_LAUNCH_CHECK();
     return B2S_OK;
 }
