@@ -5,6 +5,7 @@
 // bits) equals a stable sort of the GAUSSIANS by depth bits followed by an order-preserving bucketing of their
 // intersections by tile (tilelists.cu).  This file produces
 //     order[0 .. n_vis)  Gaussian ids in stable depth order (ties: ascending id), culled Gaussians dropped
+//     cum_rows[0 .. n_vis)  exclusive scan, in that order, of the rectangle heights (tile rows a Gaussian covers)
 //     totals[2]          M = number of tile intersections, S = number of tile-row hits (sum of rectangle heights)
 //     n_vis
 //
@@ -66,8 +67,8 @@ __device__ __forceinline__ int ds_block_excl_scan(int v, int *total, int *s_w) {
 __global__ void __launch_bounds__(DS_THREADS)
 k_depth_sort_coop(const uint32_t *__restrict__ keys_in, const int32_t *__restrict__ tiles_per_gauss, int N,
                   uint32_t *kA, uint32_t *vA, uint32_t *kB, uint32_t *vB /* == order */, int32_t *table /* [BINS][G] */,
-                  int32_t *digit_tot /* [BINS] */, const int2 *__restrict__ rects, int64_t *totals_out /* [2]: M, S */,
-                  int32_t *nvis_out) {
+                  int32_t *digit_tot /* [BINS] */, int32_t *blk_sums /* [G] */, const int2 *__restrict__ rects,
+                  int32_t *cum_rows, int64_t *totals_out /* [2]: M, S */, int32_t *nvis_out) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ int ds_smem[];
     int *s_cnt = ds_smem;                           // [DS_WARPS][DS_BINS]
@@ -76,7 +77,7 @@ k_depth_sort_coop(const uint32_t *__restrict__ keys_in, const int32_t *__restric
     const int G = gridDim.x, b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = lanemask_lt();
-    if (b == 0 && tid == 0) totals_out[0] = totals_out[1] = 0;  // accumulated after the last grid barrier
+    if (b == 0 && tid == 0) totals_out[0] = 0;  // accumulated after the last radix pass
 
     int n = N;  // items entering the current pass
     for (int pass = 0; pass < DS_PASSES; ++pass) {
@@ -189,25 +190,74 @@ k_depth_sort_coop(const uint32_t *__restrict__ keys_in, const int32_t *__restric
         grid.sync();
     }
 
-    // ---- totals over the visible Gaussians: M = tile intersections, S = tile-row hits (sum of rectangle heights)
+    // ---- exclusive scan of the rectangle heights (= tile-row hits) in depth order over the same grid, and the
+    // totals M (tile intersections) and S (tile-row hits)
     const uint32_t *order = vB;
     const int per = (n + G - 1) / G;
     const int begin = min(n, b * per), end = min(n, begin + per);
-    long long m = 0, rows = 0;
-    for (int i = begin + tid; i < end; i += DS_THREADS) {
-        const int g = (int)order[i];
-        m += tiles_per_gauss[g];
-        const int ry = rects[g].y;
-        rows += max(0, ((ry >> 16) & 0xffff) - (ry & 0xffff));
-    }
+    {
+        int sum = 0;
+        long long m = 0;
+        for (int i = begin + tid; i < end; i += DS_THREADS) {
+            const int g = (int)order[i];
+            m += tiles_per_gauss[g];
+            const int ry = rects[g].y;
+            sum += max(0, ((ry >> 16) & 0xffff) - (ry & 0xffff));
+        }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        m += __shfl_xor_sync(0xffffffffu, m, o);
-        rows += __shfl_xor_sync(0xffffffffu, rows, o);
+        for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
+        if (lane == 0 && m) atomicAdd(reinterpret_cast<unsigned long long *>(totals_out), (unsigned long long)m);
+        int tot;
+        ds_block_excl_scan(sum, &tot, s_w);
+        if (tid == 0) blk_sums[b] = tot;
     }
-    if (lane == 0 && (m | rows)) {
-        atomicAdd(reinterpret_cast<unsigned long long *>(totals_out), (unsigned long long)m);
-        atomicAdd(reinterpret_cast<unsigned long long *>(totals_out) + 1, (unsigned long long)rows);
+    grid.sync();
+    long long base = 0, all = 0;
+    {
+        long long mine = 0, tot_all = 0;
+        for (int x = tid; x < G; x += DS_THREADS) {
+            const int v = blk_sums[x];
+            tot_all += v;
+            if (x < b) mine += v;
+        }
+        // block reduce of two 64-bit sums through shared memory
+        long long *s_ll = reinterpret_cast<long long *>(s_cnt);
+        s_ll[tid] = mine;
+        s_ll[DS_THREADS + tid] = tot_all;
+        __syncthreads();
+        for (int o = DS_THREADS / 2; o > 0; o >>= 1) {
+            if (tid < o) {
+                s_ll[tid] += s_ll[tid + o];
+                s_ll[DS_THREADS + tid] += s_ll[DS_THREADS + tid + o];
+            }
+            __syncthreads();
+        }
+        base = s_ll[0];
+        all = s_ll[DS_THREADS];
+        __syncthreads();
+    }
+    if (b == 0 && tid == 0) totals_out[1] = all;
+    int running = (int)base;
+    for (int sub = begin; sub < end; sub += DS_THREADS * 8) {
+        const int i0 = sub + tid * 8;  // thread-contiguous so the serial part is in memory order
+        int v[8], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            v[k] = 0;
+            if (i0 + k < end) {
+                const int ry = rects[order[i0 + k]].y;
+                v[k] = max(0, ((ry >> 16) & 0xffff) - (ry & 0xffff));
+            }
+            sum += v[k];
+        }
+        int tot;
+        int ex = ds_block_excl_scan(sum, &tot, s_w) + running;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (i0 + k < end) cum_rows[i0 + k] = ex;
+            ex += v[k];
+        }
+        running += tot;
     }
 }
 
@@ -229,13 +279,14 @@ static int ds_max_grid(int device) {
 
 extern "C" size_t b2s_bin_depth_workspace_bytes(int N) {
     size_t n = (size_t)(N > 0 ? N : 1);
-    // kA, vA, kB + table [BINS][G<=2048] + digit totals
-    return 3 * ds_align256(n * 4) + ds_align256((size_t)DS_BINS * 2048 * 4) + ds_align256(DS_BINS * 4) + 1024;
+    // kA, vA, kB + table [BINS][G<=2048] + digit totals + block sums
+    return 3 * ds_align256(n * 4) + ds_align256((size_t)DS_BINS * 2048 * 4) + ds_align256(DS_BINS * 4) +
+           ds_align256(2048 * 4) + 1024;
 }
 
 extern "C" int b2s_bin_sort_depth(const uint32_t *sort_keys, const int32_t *tiles_per_gauss, const int32_t *tile_rects,
-                                  int N, int32_t *order, int64_t *totals, int32_t *n_vis, void *workspace,
-                                  size_t workspace_bytes, b2s_stream_t stream) {
+                                  int N, int32_t *order, int32_t *cum_rows, int64_t *totals, int32_t *n_vis,
+                                  void *workspace, size_t workspace_bytes, b2s_stream_t stream) {
     if (N < 0) return B2S_ERR_ARG;
     if (workspace_bytes < b2s_bin_depth_workspace_bytes(N)) return B2S_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
@@ -256,11 +307,14 @@ extern "C" int b2s_bin_sort_depth(const uint32_t *sort_keys, const int32_t *tile
     uint32_t *vA = (uint32_t *)w; w += n4;
     uint32_t *kB = (uint32_t *)w; w += n4;
     int32_t *table = (int32_t *)w; w += ds_align256((size_t)DS_BINS * 2048 * 4);
-    int32_t *digit_tot = (int32_t *)w;
+    int32_t *digit_tot = (int32_t *)w; w += ds_align256(DS_BINS * 4);
+    int32_t *blk_sums = (int32_t *)w;
     uint32_t *vB = (uint32_t *)order;
     const int2 *rects = (const int2 *)tile_rects;
-    void *args[] = {(void *)&sort_keys, (void *)&tiles_per_gauss, (void *)&N, (void *)&kA, (void *)&vA, (void *)&kB,
-                    (void *)&vB, (void *)&table, (void *)&digit_tot, (void *)&rects, (void *)&totals, (void *)&n_vis};
+    void *args[] = {(void *)&sort_keys, (void *)&tiles_per_gauss, (void *)&N,         (void *)&kA,
+                    (void *)&vA,        (void *)&kB,              (void *)&vB,        (void *)&table,
+                    (void *)&digit_tot, (void *)&blk_sums,        (void *)&rects,     (void *)&cum_rows,
+                    (void *)&totals,    (void *)&n_vis};
     cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_depth_sort_coop, dim3(G), dim3(DS_THREADS), args,
                                                 DS_SMEM, st);
     ++g_b2s_launches;

@@ -7,28 +7,27 @@
 // rectangle (tile_rects, from the projection kernel).  The (Gaussian x tile) incidence is a sparse matrix given
 // row by row (row = rectangle of one Gaussian); upstream's sorted list is its column-major transpose with the
 // rows kept in order.  It is built by two order-preserving "interval multisplits", each perfectly load balanced:
-//   stage 1 (rows):  the depth-ordered stream is cut into chunks of TL_G1 Gaussians (one warp each); every
-//                    Gaussian is appended to the list of each tile ROW its rectangle covers, as an 8-byte hit
-//                    (gaussian id, x0 | x1 << 16).  S = sum of rectangle heights hits in total (~ M / mean width).
-//   stage 2 (tiles): every row list is cut into chunks of TL_G2 hits (one warp each); every hit is appended to
-//                    the list of each TILE of that row in [x0, x1) -> flatten_ids.
+//   stage 1 (rows):  the depth-ordered stream is cut into chunks of equal WORK (TL_C1 appended hits; one warp
+//                    each); every Gaussian is appended to the list of each tile ROW its rectangle covers, as an
+//                    8-byte hit (gaussian id, x0 | x1 << 16).  S = sum of rectangle heights hits in total.
+//   stage 2 (tiles): every row list is cut into chunks of equal work (~TL_C2 appended entries; one warp each);
+//                    every hit is appended to the list of each TILE of that row in [x0, x1) -> flatten_ids.
 // Both stages are count (difference array in shared memory: 2 atomics per item, independent of its extent) ->
 // exclusive prefix over the chunks -> fill.  The fill never ranks or sorts: a warp takes 32 items, every lane ORs
 // its lane bit into the shared-memory word of each bin its interval covers (transposing the 32 x bins incidence),
 // then lane l OWNS bins l, l+32, ... with their list cursors in registers and appends the items of its words in
 // bit order.  Items are visited in stream order, so every list is in depth order (ties: ascending id): bit-identical
 // to the stable global sort, with M x 4 B written exactly once and no atomics on global memory.
-// Because chunks are cut from the row LISTS (not from the image), tile rows near the horizon that carry several
-// times the mean load simply get more warps.  Integer work; no tensor cores.
+// Chunks are cut by appended entries, not by items or image area, so neither tile rows near the horizon (several
+// times the mean load) nor screen-filling Gaussians close to the camera (hundreds of tiles each, all at the front
+// of every list) unbalance the warps.  Integer work; no tensor cores.
 #include <cstdlib>
 
 #include "common.cuh"
 
-constexpr int TL_G1 = 256;      // Gaussians per stage-1 chunk (one warp)
-constexpr int TL_G2 = 512;      // row hits per stage-2 chunk (one warp)
-constexpr int TL_WARPS = 4;     // warps (= chunks) per CTA
-constexpr int TL_NG = 8;        // bins owned per lane -> 256 bins per pass over a chunk (4096 px); more bins: more passes
-constexpr int TL_BAND = 32 * TL_NG;
+constexpr int TL_C1 = 1024;     // tile-row hits appended per stage-1 chunk (one warp)
+constexpr int TL_C2 = 2048;     // tile-list entries appended per stage-2 chunk (one warp)
+constexpr int TL_WARPS = 2;     // warps (= chunks) per CTA: small CTAs so that every chunk is resident at once
 
 __device__ __forceinline__ int tl_warp_incl_scan(int v, int lane) {
 #pragma unroll
@@ -64,42 +63,60 @@ __device__ __forceinline__ void tl_warp_count(int *s_d, int nbins, int begin, in
     __syncwarp();
 }
 
-// ---- ordered fill: one warp, items [begin, end) in stream order.  load(i, lo, hi, payload) describes item i;
-// cursor0(bin) is the output index of the first item this chunk appends to `bin`; out receives the payloads.
-// s_words: TL_BAND ints, s_pay: 32 payloads (this warp's shared memory).
-template <class PAY, class LOAD, class CUR>
+// ---- ordered fill: one warp, items [begin, end) in stream order.  fetch(i) loads the raw item i and
+// decode(item, lo, hi, payload) turns it into its bin interval and payload; cursor0(bin) is the output index of
+// the first item this chunk appends to `bin`; out receives the payloads.
+// s_words: 32 * NG ints, s_pay: 32 payloads (this warp's shared memory).  NG = bins owned per lane (32 * NG bins
+// per pass over the chunk; more bins: more passes).  The next batch's raw items are fetched while the current one
+// is expanded (decoded only when needed, so the load latency is hidden), and the expansion is a warp-convergent,
+// branch-free loop in which a lane pops one bit from each of its NG words per round (NG independent
+// shared-load -> predicated-store chains).
+template <class PAY, int NG, class ITEM, class FETCH, class DECODE, class CUR>
 __device__ __forceinline__ void tl_warp_fill(unsigned *s_words, PAY *s_pay, int nbins, int begin, int end, int lane,
-                                             LOAD load, CUR cursor0, PAY *__restrict__ out) {
-    for (int band = 0; band < nbins; band += TL_BAND) {  // one pass unless there are more than 256 bins
-        int cur[TL_NG];
+                                             FETCH fetch, DECODE decode, CUR cursor0, PAY *__restrict__ out) {
+    constexpr int BAND = 32 * NG;
+    for (int band = 0; band < nbins; band += BAND) {  // one pass unless there are more than 32 * NG bins
+        PAY *cur[NG];
 #pragma unroll
-        for (int k = 0; k < TL_NG; ++k) {
+        for (int k = 0; k < NG; ++k) {
             const int b = band + lane + 32 * k;
-            cur[k] = b < nbins ? cursor0(b) : 0;
+            cur[k] = out + (b < nbins ? cursor0(b) : 0);
         }
-        const int nk = min(TL_NG, (nbins - band + 31) >> 5);  // word groups in use (warp-uniform)
+        ITEM nxt = ITEM();
+        bool nvalid = begin + lane < end;
+        if (nvalid) nxt = fetch(begin + lane);
         for (int i0 = begin; i0 < end; i0 += 32) {
             int lo = 0, hi = 0;
             PAY pay = PAY();
-            if (i0 + lane < end) load(i0 + lane, lo, hi, pay);
+            if (nvalid) decode(nxt, lo, hi, pay);
             lo = max(lo - band, 0);
-            hi = min(hi - band, TL_BAND);
+            hi = min(hi - band, BAND);
             s_pay[lane] = pay;
 #pragma unroll
-            for (int k = 0; k < TL_NG; ++k)
-                if (k < nk) s_words[lane + 32 * k] = 0u;
+            for (int k = 0; k < NG; ++k) s_words[lane + 32 * k] = 0u;
+            nvalid = i0 + 32 + lane < end;
+            if (nvalid) nxt = fetch(i0 + 32 + lane);  // prefetch the next batch (raw; decoded next round)
             __syncwarp();
             for (int b = lo; b < hi; ++b) atomicOr(&s_words[b], 1u << lane);
             __syncwarp();
+            unsigned w[NG];
+            unsigned any = 0u;
 #pragma unroll
-            for (int k = 0; k < TL_NG; ++k) {
-                if (k < nk) {
-                    unsigned w = s_words[lane + 32 * k];
-                    while (w) {
-                        const int j = __ffs(w) - 1;
-                        w &= w - 1;
-                        out[cur[k]++] = s_pay[j];
-                    }
+            for (int k = 0; k < NG; ++k) {
+                w[k] = s_words[lane + 32 * k];
+                any |= w[k];
+            }
+            while (__any_sync(0xffffffffu, any != 0u)) {
+                PAY v[NG];
+#pragma unroll
+                for (int k = 0; k < NG; ++k) v[k] = s_pay[(__ffs(w[k]) - 1) & 31];
+                any = 0u;
+#pragma unroll
+                for (int k = 0; k < NG; ++k) {
+                    if (w[k]) *cur[k] = v[k];
+                    cur[k] += w[k] ? 1 : 0;
+                    w[k] &= w[k] - 1;  // 0 stays 0
+                    any |= w[k];
                 }
             }
             __syncwarp();
@@ -108,35 +125,73 @@ __device__ __forceinline__ void tl_warp_fill(unsigned *s_words, PAY *s_pay, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// stage 1: rows
+// stage 1: rows.  Chunk c = the Gaussians whose exclusive row-hit prefix cum_rows[i] lies in
+// [c * TL_C1, (c + 1) * TL_C1): equal WORK (appends) per warp, whatever the sizes of the Gaussians.
 // ------------------------------------------------------------------------------------------------
-// count1[y * nc1s + c] = number of Gaussians of chunk c whose rectangle covers tile row y
-__global__ void __launch_bounds__(32 * TL_WARPS)
-k_rows_count(const int2 *__restrict__ rects, const int32_t *__restrict__ order, const int32_t *__restrict__ n_vis,
-             int tile_h, int nc1s, int32_t *__restrict__ count1) {
-    extern __shared__ int s_dyn[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__global__ void __launch_bounds__(256)
+k_bounds1(const int32_t *__restrict__ cum_rows, const int32_t *__restrict__ n_vis, int nc1,
+          int32_t *__restrict__ bounds1 /* [nc1 + 1] */) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > nc1) return;
     const int nv = *n_vis;
-    const int c = blockIdx.x * TL_WARPS + warp;
-    const int begin = c * TL_G1;
-    if (begin >= nv) return;
-    const int end = min(nv, begin + TL_G1);
-    int *s_d = s_dyn + warp * (tile_h + 1);
-    tl_warp_count(s_d, tile_h, begin, end, lane, [&](int i, int &lo, int &hi) {
-        const int ry = rects[order[i]].y;
-        lo = ry & 0xffff;
-        hi = min((ry >> 16) & 0xffff, tile_h);
-    });
-    for (int y = lane; y < tile_h; y += 32) count1[(size_t)y * nc1s + c] = s_d[y];
+    int lo = 0, hi = nv;  // first i with cum_rows[i] >= c * TL_C1
+    if (c == nc1) lo = nv;
+    const long long target = (long long)c * TL_C1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (cum_rows[mid] < target) lo = mid + 1;
+        else hi = mid;
+    }
+    bounds1[c] = lo;
 }
 
-// one CTA per tile row: in-place exclusive scan of count1[y][0 .. nc1) over the chunks; row_len[y] = total
+// count1[y * nc1s + c] = Gaussians of chunk c covering tile row y; count1w[..] = tiles of row y they cover
+__global__ void __launch_bounds__(32 * TL_WARPS)
+k_rows_count(const int2 *__restrict__ rects, const int32_t *__restrict__ order, const int32_t *__restrict__ bounds1,
+             int nc1, int tile_w, int tile_h, int nc1s, int32_t *__restrict__ count1, int32_t *__restrict__ count1w) {
+    extern __shared__ int s_dyn[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * TL_WARPS + warp;
+    if (c >= nc1) return;
+    const int begin = bounds1[c], end = bounds1[c + 1];
+    int *s_d = s_dyn + warp * 2 * (tile_h + 1);
+    int *s_w = s_d + tile_h + 1;
+    for (int b = lane; b <= tile_h; b += 32) s_d[b] = s_w[b] = 0;
+    __syncwarp();
+    for (int i = begin + lane; i < end; i += 32) {
+        const int2 rc = rects[order[i]];
+        const int lo = rc.y & 0xffff, hi = min((rc.y >> 16) & 0xffff, tile_h);
+        const int wd = max(0, min((rc.x >> 16) & 0xffff, tile_w) - (rc.x & 0xffff));
+        if (hi > lo) {
+            atomicAdd(&s_d[lo], 1);
+            atomicAdd(&s_d[hi], -1);
+            atomicAdd(&s_w[lo], wd);
+            atomicAdd(&s_w[hi], -wd);
+        }
+    }
+    __syncwarp();
+    int carry = 0, carry_w = 0;
+    for (int b0 = 0; b0 < tile_h; b0 += 32) {
+        const int y = b0 + lane;
+        const int v = y < tile_h ? s_d[y] : 0, vw = y < tile_h ? s_w[y] : 0;
+        const int incl = tl_warp_incl_scan(v, lane) + carry, incl_w = tl_warp_incl_scan(vw, lane) + carry_w;
+        if (y < tile_h) {
+            count1[(size_t)y * nc1s + c] = incl;
+            count1w[(size_t)y * nc1s + c] = incl_w;
+        }
+        carry = __shfl_sync(0xffffffffu, incl, 31);
+        carry_w = __shfl_sync(0xffffffffu, incl_w, 31);
+    }
+}
+
+// CTA (y, which): in-place exclusive scan over the chunks of count1[y][.] (which = 0; total -> row_len[y]) or
+// count1w[y][.] (which = 1; total -> row_app[y])
 __global__ void __launch_bounds__(256)
-k_rows_prefix(int32_t *__restrict__ count1, const int32_t *__restrict__ n_vis, int nc1s, int32_t *__restrict__ row_len) {
+k_rows_prefix(int32_t *__restrict__ count1, int32_t *__restrict__ count1w, int nc1, int nc1s,
+              int32_t *__restrict__ row_len, int32_t *__restrict__ row_app) {
     __shared__ int s_w[9];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nc1 = (*n_vis + TL_G1 - 1) / TL_G1;
-    int32_t *r = count1 + (size_t)blockIdx.x * nc1s;
+    int32_t *r = (blockIdx.y ? count1w : count1) + (size_t)blockIdx.x * nc1s;
     const int per = (nc1 + 255) / 256;
     const int b = min(nc1, tid * per), e = min(nc1, b + per);
     int sum = 0;
@@ -157,20 +212,20 @@ k_rows_prefix(int32_t *__restrict__ count1, const int32_t *__restrict__ n_vis, i
         r[i] = run;
         run += v;
     }
-    if (tid == 0) row_len[blockIdx.x] = s_w[8];
+    if (tid == 0) (blockIdx.y ? row_app : row_len)[blockIdx.x] = s_w[8];
 }
 
-// one warp: row_off = exclusive scan of row_len, chunk_off = exclusive scan of ceil(row_len / TL_G2); entry
+// one warp: row_off = exclusive scan of row_len, chunk_off = exclusive scan of ceil(row_app / TL_C2); entry
 // [tile_h] holds the totals (S and the number of stage-2 chunks).
 __global__ void __launch_bounds__(32)
-k_rows_offsets(const int32_t *__restrict__ row_len, int tile_h, int32_t *__restrict__ row_off,
-               int32_t *__restrict__ chunk_off) {
+k_rows_offsets(const int32_t *__restrict__ row_len, const int32_t *__restrict__ row_app, int tile_h,
+               int32_t *__restrict__ row_off, int32_t *__restrict__ chunk_off) {
     const int lane = threadIdx.x;
     int carry_r = 0, carry_c = 0;
     for (int y0 = 0; y0 < tile_h; y0 += 32) {
         const int y = y0 + lane;
         const int len = y < tile_h ? row_len[y] : 0;
-        const int nch = (len + TL_G2 - 1) / TL_G2;
+        const int nch = y < tile_h ? (row_app[y] + TL_C2 - 1) / TL_C2 : 0;
         const int ir = tl_warp_incl_scan(len, lane), ic = tl_warp_incl_scan(nch, lane);
         if (y < tile_h) {
             row_off[y] = carry_r + ir - len;
@@ -186,58 +241,83 @@ k_rows_offsets(const int32_t *__restrict__ row_len, int tile_h, int32_t *__restr
 }
 
 // row_list[row_off[y] ..) = the Gaussians covering tile row y, in depth order, as (id, x0 | x1 << 16)
+template <int NG>
 __global__ void __launch_bounds__(32 * TL_WARPS)
-k_rows_fill(const int2 *__restrict__ rects, const int32_t *__restrict__ order, const int32_t *__restrict__ n_vis,
-            int tile_h, int nc1s, const int32_t *__restrict__ count1, const int32_t *__restrict__ row_off,
-            int2 *__restrict__ row_list) {
-    __shared__ unsigned s_words[TL_WARPS][TL_BAND];
+k_rows_fill(const int2 *__restrict__ rects, const int32_t *__restrict__ order, const int32_t *__restrict__ bounds1,
+            int nc1, int tile_h, int nc1s, const int32_t *__restrict__ count1,
+            const int32_t *__restrict__ row_off, int2 *__restrict__ row_list) {
+    __shared__ unsigned s_words[TL_WARPS][32 * NG];
     __shared__ int2 s_pay[TL_WARPS][32];
+
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nv = *n_vis;
     const int c = blockIdx.x * TL_WARPS + warp;
-    const int begin = c * TL_G1;
-    if (begin >= nv) return;
-    const int end = min(nv, begin + TL_G1);
-    tl_warp_fill<int2>(
+    if (c >= nc1) return;
+    const int begin = bounds1[c], end = bounds1[c + 1];
+    tl_warp_fill<int2, NG, int4>(
         s_words[warp], s_pay[warp], tile_h, begin, end, lane,
-        [&](int i, int &lo, int &hi, int2 &pay) {
+        [&](int i) {
             const int g = order[i];
             const int2 rc = rects[g];
-            lo = rc.y & 0xffff;
-            hi = min((rc.y >> 16) & 0xffff, tile_h);
-            pay = make_int2(g, rc.x);
+            return make_int4(g, rc.x, rc.y, 0);
+        },
+        [&](const int4 &it, int &lo, int &hi, int2 &pay) {
+            lo = it.z & 0xffff;
+            hi = min((it.z >> 16) & 0xffff, tile_h);
+            pay = make_int2(it.x, it.y);
         },
         [&](int y) { return row_off[y] + count1[(size_t)y * nc1s + c]; }, row_list);
 }
 
 // ------------------------------------------------------------------------------------------------
-// stage 2: tiles.  Stage-2 chunk c2 = hits [row_off[y] + k * TL_G2, ...) of row y, where chunk_off[y] <= c2 <
-// chunk_off[y + 1] and k = c2 - chunk_off[y].
+// stage 2: tiles.  The list of row y is cut at stage-1 cell boundaries (cell = hits of one stage-1 chunk in
+// row y, a handful of hits) into chunks of ~TL_C2 appends: chunk k of row y = the cells whose exclusive append
+// prefix count1w[y][c] lies in [k * TL_C2, (k + 1) * TL_C2).  bounds2[c2] = (first hit, row) of chunk c2.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool tl_chunk2(int c2, int tile_h, const int32_t *__restrict__ row_off,
-                                          const int32_t *__restrict__ chunk_off, int &y, int &begin, int &end) {
-    if (c2 >= chunk_off[tile_h]) return false;
+__global__ void __launch_bounds__(256)
+k_bounds2(const int32_t *__restrict__ count1, const int32_t *__restrict__ count1w, int nc1, int nc1s, int tile_h,
+          const int32_t *__restrict__ row_off, const int32_t *__restrict__ chunk_off, int2 *__restrict__ bounds2) {
+    const int c2 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c2 >= chunk_off[tile_h]) return;
     int lo = 0, hi = tile_h;  // last y with chunk_off[y] <= c2
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
         if (chunk_off[mid] <= c2) lo = mid;
         else hi = mid;
     }
-    y = lo;
-    begin = row_off[y] + (c2 - chunk_off[y]) * TL_G2;
-    end = min(row_off[y + 1], begin + TL_G2);
+    const int y = lo;
+    const long long target = (long long)(c2 - chunk_off[y]) * TL_C2;
+    const int32_t *rw = count1w + (size_t)y * nc1s;
+    int a = 0, b = nc1;  // first cell with append prefix >= target
+    while (a < b) {
+        const int mid = (a + b) >> 1;
+        if (rw[mid] < target) a = mid + 1;
+        else b = mid;
+    }
+    const int first = a < nc1 ? row_off[y] + count1[(size_t)y * nc1s + a] : row_off[y + 1];
+    bounds2[c2] = make_int2(first, y);
+}
+
+__device__ __forceinline__ bool tl_chunk2(int c2, int tile_h, const int32_t *__restrict__ row_off,
+                                          const int32_t *__restrict__ chunk_off, const int2 *__restrict__ bounds2,
+                                          int &y, int &begin, int &end) {
+    if (c2 >= chunk_off[tile_h]) return false;
+    const int2 b = bounds2[c2];
+    y = b.y;
+    begin = b.x;
+    end = (c2 + 1 < chunk_off[y + 1]) ? bounds2[c2 + 1].x : row_off[y + 1];
     return true;
 }
 
 // table2[c2 * tile_w + x] = number of hits of chunk c2 covering tile x of its row
 __global__ void __launch_bounds__(32 * TL_WARPS)
 k_tiles_count(const int2 *__restrict__ row_list, const int32_t *__restrict__ row_off,
-              const int32_t *__restrict__ chunk_off, int tile_w, int tile_h, int32_t *__restrict__ table2) {
+              const int32_t *__restrict__ chunk_off, const int2 *__restrict__ bounds2, int tile_w, int tile_h,
+              int32_t *__restrict__ table2) {
     extern __shared__ int s_dyn[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c2 = blockIdx.x * TL_WARPS + warp;
     int y, begin, end;
-    if (!tl_chunk2(c2, tile_h, row_off, chunk_off, y, begin, end)) return;
+    if (!tl_chunk2(c2, tile_h, row_off, chunk_off, bounds2, y, begin, end)) return;
     int *s_d = s_dyn + warp * (tile_w + 1);
     tl_warp_count(s_d, tile_w, begin, end, lane, [&](int i, int &lo, int &hi) {
         const int rx = row_list[i].y;
@@ -319,20 +399,22 @@ k_tiles_offsets(const int32_t *__restrict__ tile_total, int T, int32_t *__restri
 }
 
 // flatten_ids[isect_offsets[t] ..) = the Gaussians intersecting tile t, in depth order
+template <int NG>
 __global__ void __launch_bounds__(32 * TL_WARPS)
 k_tiles_fill(const int2 *__restrict__ row_list, const int32_t *__restrict__ row_off,
-             const int32_t *__restrict__ chunk_off, int tile_w, int tile_h, const int32_t *__restrict__ table2,
-             const int32_t *__restrict__ offsets, int32_t *__restrict__ flatten_ids) {
-    __shared__ unsigned s_words[TL_WARPS][TL_BAND];
+             const int32_t *__restrict__ chunk_off, const int2 *__restrict__ bounds2, int tile_w, int tile_h,
+             const int32_t *__restrict__ table2, const int32_t *__restrict__ offsets,
+             int32_t *__restrict__ flatten_ids) {
+    __shared__ unsigned s_words[TL_WARPS][32 * NG];
     __shared__ int s_pay[TL_WARPS][32];
+
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c2 = blockIdx.x * TL_WARPS + warp;
     int y, begin, end;
-    if (!tl_chunk2(c2, tile_h, row_off, chunk_off, y, begin, end)) return;
-    tl_warp_fill<int>(
-        s_words[warp], s_pay[warp], tile_w, begin, end, lane,
-        [&](int i, int &lo, int &hi, int &pay) {
-            const int2 h = row_list[i];
+    if (!tl_chunk2(c2, tile_h, row_off, chunk_off, bounds2, y, begin, end)) return;
+    tl_warp_fill<int, NG, int2>(
+        s_words[warp], s_pay[warp], tile_w, begin, end, lane, [&](int i) { return row_list[i]; },
+        [&](const int2 &h, int &lo, int &hi, int &pay) {
             lo = h.y & 0xffff;
             hi = min((h.y >> 16) & 0xffff, tile_w);
             pay = h.x;
@@ -350,21 +432,25 @@ static inline bool tl_supported(int tile_w, int tile_h) {
 }
 
 struct TlLayout {
-    int nc1s;        // stage-1 chunks (upper bound from N)
-    long long nc2s;  // stage-2 chunks (upper bound from S)
-    size_t count1, row_len, row_off, chunk_off, row_list, table2, tile_total, total;
+    int nc1;         // stage-1 chunks
+    long long nc2s;  // stage-2 chunks (upper bound from M)
+    size_t bounds1, count1, count1w, row_len, row_app, row_off, chunk_off, row_list, bounds2, table2, tile_total, total;
 };
 
-static TlLayout tl_layout(int N, long long S, int tile_w, int tile_h) {
+static TlLayout tl_layout(long long M, long long S, int tile_w, int tile_h) {
     TlLayout L;
-    L.nc1s = b2s_div_up(N > 0 ? N : 1, TL_G1);
-    L.nc2s = S / TL_G2 + tile_h;
+    L.nc1 = (int)(S / TL_C1) + 1;
+    L.nc2s = M / TL_C2 + tile_h;
     size_t o = 0;
-    L.count1 = o; o += tl_align256((size_t)tile_h * L.nc1s * 4);
+    L.bounds1 = o; o += tl_align256((size_t)(L.nc1 + 1) * 4);
+    L.count1 = o; o += tl_align256((size_t)tile_h * L.nc1 * 4);
+    L.count1w = o; o += tl_align256((size_t)tile_h * L.nc1 * 4);
     L.row_len = o; o += tl_align256((size_t)tile_h * 4);
+    L.row_app = o; o += tl_align256((size_t)tile_h * 4);
     L.row_off = o; o += tl_align256((size_t)(tile_h + 1) * 4);
     L.chunk_off = o; o += tl_align256((size_t)(tile_h + 1) * 4);
     L.row_list = o; o += tl_align256((size_t)(S > 0 ? S : 1) * 8);
+    L.bounds2 = o; o += tl_align256((size_t)(L.nc2s + 1) * 8);
     L.table2 = o; o += tl_align256((size_t)L.nc2s * tile_w * 4);
     L.tile_total = o; o += tl_align256((size_t)tile_w * tile_h * 4);
     L.total = o + 1024;
@@ -372,14 +458,15 @@ static TlLayout tl_layout(int N, long long S, int tile_w, int tile_h) {
 }
 
 extern "C" size_t b2s_bin_tiles_workspace_bytes(int N, long long M, long long S, int tile_w, int tile_h) {
-    (void)M;
-    if (!tl_supported(tile_w, tile_h) || S < 0) return 0;
-    return tl_layout(N, S, tile_w, tile_h).total;
+    (void)N;
+    if (!tl_supported(tile_w, tile_h) || S < 0 || M < 0) return 0;
+    return tl_layout(M, S, tile_w, tile_h).total;
 }
 
-extern "C" int b2s_bin_tiles(const int32_t *tile_rects, const int32_t *order, const int32_t *n_vis, int N, long long M,
-                             long long S, int tile_size, int tile_w, int tile_h, int32_t *flatten_ids,
-                             int32_t *isect_offsets, void *workspace, size_t workspace_bytes, b2s_stream_t stream) {
+extern "C" int b2s_bin_tiles(const int32_t *tile_rects, const int32_t *order, const int32_t *cum_rows,
+                             const int32_t *n_vis, int N, long long M, long long S, int tile_size, int tile_w,
+                             int tile_h, int32_t *flatten_ids, int32_t *isect_offsets, void *workspace,
+                             size_t workspace_bytes, b2s_stream_t stream) {
     if (N < 0 || M < 0 || S < 0 || S >= (1LL << 31) || M >= (1LL << 31) || tile_w <= 0 || tile_h <= 0) return B2S_ERR_ARG;
     if (tile_size != 16 || !tl_supported(tile_w, tile_h)) return B2S_ERR_UNSUPPORTED;
     if (workspace_bytes < b2s_bin_tiles_workspace_bytes(N, M, S, tile_w, tile_h)) return B2S_ERR_WORKSPACE;
@@ -389,38 +476,55 @@ extern "C" int b2s_bin_tiles(const int32_t *tile_rects, const int32_t *order, co
         cudaMemsetAsync(isect_offsets, 0, sizeof(int32_t) * (size_t)T, st);
         return B2S_OK;
     }
-    const TlLayout L = tl_layout(N, S, tile_w, tile_h);
+    const TlLayout L = tl_layout(M, S, tile_w, tile_h);
     char *w = (char *)workspace;
+    int32_t *bounds1 = (int32_t *)(w + L.bounds1);
     int32_t *count1 = (int32_t *)(w + L.count1);
+    int32_t *count1w = (int32_t *)(w + L.count1w);
     int32_t *row_len = (int32_t *)(w + L.row_len);
+    int32_t *row_app = (int32_t *)(w + L.row_app);
     int32_t *row_off = (int32_t *)(w + L.row_off);
     int32_t *chunk_off = (int32_t *)(w + L.chunk_off);
     int2 *row_list = (int2 *)(w + L.row_list);
+    int2 *bounds2 = (int2 *)(w + L.bounds2);
     int32_t *table2 = (int32_t *)(w + L.table2);
     int32_t *tile_total = (int32_t *)(w + L.tile_total);
     const int2 *rects = (const int2 *)tile_rects;
 
-    const int grid1 = b2s_div_up(L.nc1s, TL_WARPS);
+    const int nc1 = L.nc1;
+    const int grid1 = b2s_div_up(nc1, TL_WARPS);
     const int grid2 = b2s_div_up(L.nc2s, TL_WARPS);
-    const size_t smem1 = (size_t)TL_WARPS * (tile_h + 1) * sizeof(int);
+    const size_t smem1 = (size_t)TL_WARPS * 2 * (tile_h + 1) * sizeof(int);
     const size_t smem2 = (size_t)TL_WARPS * (tile_w + 1) * sizeof(int);
     if (smem1 > 48 * 1024 || smem2 > 48 * 1024) return B2S_ERR_UNSUPPORTED;
-    k_rows_count<<<grid1, 32 * TL_WARPS, smem1, st>>>(rects, order, n_vis, tile_h, L.nc1s, count1);
+    k_bounds1<<<b2s_div_up(nc1 + 1, 256), 256, 0, st>>>(cum_rows, n_vis, nc1, bounds1);
     B2S_LAUNCH_CHECK();
-    k_rows_prefix<<<tile_h, 256, 0, st>>>(count1, n_vis, L.nc1s, row_len);
+    k_rows_count<<<grid1, 32 * TL_WARPS, smem1, st>>>(rects, order, bounds1, nc1, tile_w, tile_h, nc1, count1, count1w);
     B2S_LAUNCH_CHECK();
-    k_rows_offsets<<<1, 32, 0, st>>>(row_len, tile_h, row_off, chunk_off);
+    k_rows_prefix<<<dim3(tile_h, 2), 256, 0, st>>>(count1, count1w, nc1, nc1, row_len, row_app);
     B2S_LAUNCH_CHECK();
-    k_rows_fill<<<grid1, 32 * TL_WARPS, 0, st>>>(rects, order, n_vis, tile_h, L.nc1s, count1, row_off, row_list);
+    k_rows_offsets<<<1, 32, 0, st>>>(row_len, row_app, tile_h, row_off, chunk_off);
     B2S_LAUNCH_CHECK();
-    k_tiles_count<<<grid2, 32 * TL_WARPS, smem2, st>>>(row_list, row_off, chunk_off, tile_w, tile_h, table2);
+    // bins owned per lane: 4 (<= 128 tile rows / columns, i.e. <= 2048 px) or 8; larger grids take several passes
+    if (tile_h <= 128)
+        k_rows_fill<4><<<grid1, 32 * TL_WARPS, 0, st>>>(rects, order, bounds1, nc1, tile_h, nc1, count1, row_off, row_list);
+    else
+        k_rows_fill<8><<<grid1, 32 * TL_WARPS, 0, st>>>(rects, order, bounds1, nc1, tile_h, nc1, count1, row_off, row_list);
+    B2S_LAUNCH_CHECK();
+    k_bounds2<<<b2s_div_up(L.nc2s, 256), 256, 0, st>>>(count1, count1w, nc1, nc1, tile_h, row_off, chunk_off, bounds2);
+    B2S_LAUNCH_CHECK();
+    k_tiles_count<<<grid2, 32 * TL_WARPS, smem2, st>>>(row_list, row_off, chunk_off, bounds2, tile_w, tile_h, table2);
     B2S_LAUNCH_CHECK();
     k_tiles_prefix<<<dim3(b2s_div_up(tile_w, 32), tile_h), 256, 0, st>>>(table2, chunk_off, tile_w, tile_total);
     B2S_LAUNCH_CHECK();
     k_tiles_offsets<<<1, 1024, 0, st>>>(tile_total, T, isect_offsets);
     B2S_LAUNCH_CHECK();
-    k_tiles_fill<<<grid2, 32 * TL_WARPS, 0, st>>>(row_list, row_off, chunk_off, tile_w, tile_h, table2, isect_offsets,
-                                                  flatten_ids);
+    if (tile_w <= 128)
+        k_tiles_fill<4><<<grid2, 32 * TL_WARPS, 0, st>>>(row_list, row_off, chunk_off, bounds2, tile_w, tile_h, table2,
+                                                         isect_offsets, flatten_ids);
+    else
+        k_tiles_fill<8><<<grid2, 32 * TL_WARPS, 0, st>>>(row_list, row_off, chunk_off, bounds2, tile_w, tile_h, table2,
+                                                         isect_offsets, flatten_ids);
     B2S_LAUNCH_CHECK();
     return B2S_OK;
 }

@@ -185,9 +185,11 @@ class _Blend(torch.autograd.Function):
         M = flatten_ids.shape[0]
         v_render = torch.zeros_like(render) if v_render is None else v_render.contiguous()
         v_alpha = torch.zeros_like(alpha) if v_alpha is None else v_alpha.contiguous()
-        v_xyabs = torch.zeros(N, 4, dtype=torch.float32, device=dev)
-        v_geo = torch.zeros(N, 4, dtype=torch.float32, device=dev)
-        v_colpack = torch.zeros(N, cdim, dtype=torch.float32, device=dev)
+        # one zero-filled arena (one memset launch) holding the three 16-byte-row accumulation buffers
+        arena = torch.zeros(N * (8 + cdim), dtype=torch.float32, device=dev)
+        v_xyabs = arena[: 4 * N].view(N, 4)
+        v_geo = arena[4 * N: 8 * N].view(N, 4)
+        v_colpack = arena[8 * N:].view(N, cdim)
         with _timed("blend_bwd"):
             _lib.check(lib.b2s_blend_bwd(_ptr(means2d), _ptr(geo), _ptr(colpack), _ptr(offsets), _ptr(flatten_ids),
                                          M, W, H, tile_w, tile_h, cdim, d_out, int(ed), _ptr(render), _ptr(alpha),
@@ -206,12 +208,13 @@ def _bin(rects: Tensor, tiles: Tensor, keys: Tensor, tile_w: int, tile_h: int) -
     dev = rects.device
     N = tiles.shape[0]
     order = torch.empty(N, dtype=torch.int32, device=dev)
+    cum_rows = torch.empty(N, dtype=torch.int32, device=dev)
     totals = torch.empty(2, dtype=torch.int64, device=dev)
     n_vis = torch.empty(1, dtype=torch.int32, device=dev)
     wsb = int(lib.b2s_bin_depth_workspace_bytes(N))
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     with _timed("bin_sort_depth"):
-        _lib.check(lib.b2s_bin_sort_depth(_ptr(keys), _ptr(tiles), _ptr(rects), N, _ptr(order), _ptr(totals),
+        _lib.check(lib.b2s_bin_sort_depth(_ptr(keys), _ptr(tiles), _ptr(rects), N, _ptr(order), _ptr(cum_rows), _ptr(totals),
                                           _ptr(n_vis), _ptr(ws), wsb, _stream()), "b2s_bin_sort_depth")
     # the one unavoidable device->host read: M sizes flatten_ids, S (tile-row hits) the tile-list workspace
     M, S = (int(v) for v in totals.tolist())
@@ -224,7 +227,7 @@ def _bin(rects: Tensor, tiles: Tensor, keys: Tensor, tile_w: int, tile_h: int) -
         raise NotImplementedError(f"tile grid {tile_w}x{tile_h} not supported")
     ws2 = torch.empty(wsb2, dtype=torch.uint8, device=dev)
     with _timed("bin_tiles"):
-        _lib.check(lib.b2s_bin_tiles(_ptr(rects), _ptr(order), _ptr(n_vis), N, M, S, 16, tile_w, tile_h,
+        _lib.check(lib.b2s_bin_tiles(_ptr(rects), _ptr(order), _ptr(cum_rows), _ptr(n_vis), N, M, S, 16, tile_w, tile_h,
                                      _ptr(flatten_ids), _ptr(offsets), _ptr(ws2), wsb2, _stream()),
                    "b2s_bin_tiles")
     return flatten_ids, offsets
