@@ -71,6 +71,41 @@ int b2s_project_bwd(const float *means, const float *quats, const float *scales,
                     float *v_means, float *v_quats, float *v_scales, float *v_opacities,
                     float *v_viewmat, b2s_stream_t stream);
 
+/* ---- multi-GPU: projection backward fused with the exchange of the shared-node gradients ----
+ * One traversal camera per GPU over replicated shared Gaussians (mtgs_scene_graph.py:548 renders one camera per
+ * call); rows [0, n_shared) of the rasterizer inputs are the replicated ones, rows [n_shared, N) are rank-local.
+ * Each rank owns shard = b2s_exchange_shard_rows(n_shared, world) consecutive rows.  Buffers (peer-mapped through
+ * CUDA IPC, allocated with b2s_peer_alloc so that they are exportable):
+ *   stage  [world][(11 + d_in) * shard] floats  partial gradient rows of MY shard, one slot per source rank
+ *   arena  [(11 + d_in) * rows_cap]     floats  reduced gradient, SoA blocks: means at 0, quats at 3 rows_cap,
+ *                                               scales at 7 rows_cap, opacities at 10 rows_cap, colours at 11 rows_cap
+ *   flags  [2][8] uint32 (zero-initialised)     phase-0 / phase-1 arrival flags, written by the peers
+ * The call enqueues: projection backward storing its rows straight into the owners' stage slots (peer stores), the
+ * plain projection backward for the rank-local rows, the reduce of my shard + store of the result into every rank's
+ * arena, and a stream-ordered wait.  When it has run, arena holds scale * sum over ranks for the shared rows and the
+ * local gradient for the others.  *_ptrs_host are HOST arrays of `world` device pointers (this rank's own buffers at
+ * index `rank`); epoch must increase by one per call on every rank; *status (device word) becomes non-zero if a
+ * wait timed out (~2 s) instead of hanging the GPU.  Colour gradients of the rank-local rows are left in v_colpack.
+ * phases: bit 0 = projection backward + peer stores, bit 1 = reduce + broadcast, bit 2 = final wait (7 = all; the
+ * split exists so that a test can play several ranks on one GPU from one stream). */
+int b2s_exchange_shard_rows(int n_shared, int world);
+int b2s_peer_alloc(size_t bytes, void **dev_ptr); /* cudaMalloc + zero fill (set-up only) */
+int b2s_peer_free(void *dev_ptr);
+int b2s_ipc_export(void *dev_ptr, unsigned char handle_out[64]);
+int b2s_ipc_import(const unsigned char handle[64], void **peer_ptr);
+int b2s_ipc_close(void *peer_ptr);
+int b2s_project_bwd_exchange(const float *means, const float *quats, const float *scales,
+                             const float *opacities, const float *viewmat, const float *K, int N, int W,
+                             int H, float eps2d, int calc_comp, int d_in, int with_depth, int cdim,
+                             const int32_t *radii, const float *geo, const float *comps,
+                             const float *v_means2d, int v_means2d_stride, const float *v_geo,
+                             const float *v_colpack, float *v_viewmat, int n_shared, int world, int rank,
+                             long long rows_cap, float scale, unsigned epoch, int phases,
+                             const unsigned long long *stage_ptrs_host,
+                             const unsigned long long *arena_ptrs_host,
+                             const unsigned long long *flag_ptrs_host, unsigned *ticket, unsigned *status,
+                             b2s_stream_t stream);
+
 /* ---- tile binning + depth sort (upstream isect_tiles + radix sort + isect_offset_encode; A.2) ----
  * Two-level formulation with identical results to the stable 64-bit sort:
  *   (1) b2s_bin_sort_depth : stable sort of the visible Gaussians by depth key (one cooperative kernel) ->

@@ -21,6 +21,14 @@ SIGNATURES = {
     "b2s_launch_count": (_ll, []),
     "b2s_project_fwd": (_i, [_vp] * 7 + [_i] * 6 + [_f] * 4 + [_i] * 4 + [_vp] * 9 + [_vp]),
     "b2s_project_bwd": (_i, [_vp] * 6 + [_i] * 3 + [_f] + [_i] * 4 + [_vp] * 4 + [_i] + [_vp] * 7 + [_vp]),
+    "b2s_exchange_shard_rows": (_i, [_i, _i]),
+    "b2s_peer_alloc": (_i, [_sz, C.POINTER(C.c_void_p)]),
+    "b2s_peer_free": (_i, [_vp]),
+    "b2s_ipc_export": (_i, [_vp, C.c_char_p]),
+    "b2s_ipc_import": (_i, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "b2s_ipc_close": (_i, [_vp]),
+    "b2s_project_bwd_exchange": (_i, [_vp] * 6 + [_i] * 3 + [_f] + [_i] * 4 + [_vp] * 4 + [_i] + [_vp] * 3 +
+                                 [_i, _i, _i, _ll, _f, C.c_uint, _i] + [_vp] * 5 + [_vp]),
     "b2s_bin_depth_workspace_bytes": (_sz, [_i]),
     "b2s_bin_sort_depth": (_i, [_vp] * 3 + [_i] + [_vp] * 5 + [_sz, _vp]),
     "b2s_bin_tiles_workspace_bytes": (_sz, [_i, _ll, _ll, _i, _i]),

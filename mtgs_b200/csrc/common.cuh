@@ -57,6 +57,19 @@ __device__ __forceinline__ float4 ldg_stream4(const float4 *p) {
     return v;
 }
 
+// Peer-memory description of the multi-GPU gradient exchange (exchange.cu), passed to kernels by value.
+#define B2S_MAX_WORLD 8
+struct B2sExchange {
+    int world, rank;
+    int shard;              // Gaussians (rows) owned per rank; multiple of 256
+    long long slot_floats;  // floats per (owner, source) staging slot = (11 + d_in) * shard
+    unsigned epoch;         // step counter written into the flags
+    float *stage[B2S_MAX_WORLD];     // stage[r]: rank r's staging buffer [world][slot_floats] (peer-mapped)
+    float *arena[B2S_MAX_WORLD];     // arena[r]: rank r's reduced-gradient arena (peer-mapped)
+    unsigned *flags[B2S_MAX_WORLD];  // flags[r]: rank r's flag words [2 phases][B2S_MAX_WORLD] (peer-mapped)
+    unsigned *ticket;                // local CTA ticket counter (zero between launches)
+};
+
 // device-wide exclusive scan of int32 (binning.cu); `in` may alias `out`; gather may be null.
 // ws must hold b2s_scan_ws_ints(n) ints.  Grand total (int64) is written to *total_out when non-null.
 size_t b2s_scan_ws_ints(int n);

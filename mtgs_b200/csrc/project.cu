@@ -236,7 +236,14 @@ __device__ __forceinline__ void mat3_mul_at(const float *A, const float *B, floa
             C[i * 3 + j] = A[0 * 3 + i] * B[0 * 3 + j] + A[1 * 3 + i] * B[1 * 3 + j] + A[2 * 3 + i] * B[2 * 3 + j];
 }
 
-template <int CDIM>
+// EXCH = false: gradients are written to this GPU's v_means / v_quats / v_scales / v_opacities.
+// EXCH = true (multi-GPU): the CTA's 256 gradient rows (means 3, quats 4, scales 3, opacity 1, colours
+// d_in floats per Gaussian) are transposed through shared memory and stored with 16-byte coalesced stores straight
+// into the staging slot of the rank that OWNS these rows (peer memory over NVLink) -- the reduce-scatter half of
+// the shared-gradient all-reduce happens while the projection backward is still computing, and this GPU never
+// writes (or later re-reads) a local copy of its partial gradient.  The last CTA to finish raises this rank's
+// flag at every peer (exchange.cu holds the reduce + all-gather half).
+template <int CDIM, bool EXCH>
 __global__ void __launch_bounds__(256)
 k_project_bwd(const float *__restrict__ means, const float *__restrict__ quats, const float *__restrict__ scales,
               const float *__restrict__ opacities, const float *__restrict__ viewmat, const float *__restrict__ K,
@@ -244,19 +251,17 @@ k_project_bwd(const float *__restrict__ means, const float *__restrict__ quats, 
               const int32_t *__restrict__ radii, const float4 *__restrict__ geo, const float *__restrict__ comps,
               const float *__restrict__ v_means2d, int v_m2d_stride, const float4 *__restrict__ v_geo,
               const float *__restrict__ v_colpack, float *__restrict__ v_means, float4 *__restrict__ v_quats,
-              float *__restrict__ v_scales, float *__restrict__ v_opacities, float *__restrict__ v_viewmat) {
+              float *__restrict__ v_scales, float *__restrict__ v_opacities, float *__restrict__ v_viewmat,
+              const B2sExchange ex) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     float vR[9], vt[3];
 #pragma unroll
     for (int k = 0; k < 9; ++k) vR[k] = 0.f;
     vt[0] = vt[1] = vt[2] = 0.f;
     const bool live = g < N && radii[g] > 0;
-    if (g < N && !live) {
-        v_means[3 * g] = v_means[3 * g + 1] = v_means[3 * g + 2] = 0.f;
-        v_scales[3 * g] = v_scales[3 * g + 1] = v_scales[3 * g + 2] = 0.f;
-        v_quats[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-        v_opacities[g] = 0.f;
-    }
+    // this Gaussian's gradient row (zeros when it is culled)
+    float o_means[3] = {0.f, 0.f, 0.f}, o_scales[3] = {0.f, 0.f, 0.f}, o_opac = 0.f;
+    float4 o_quat = make_float4(0.f, 0.f, 0.f, 0.f);
     if (live) {
         CamParams cam;
         load_camera(viewmat, K, W, H, cam);
@@ -278,7 +283,7 @@ k_project_bwd(const float *__restrict__ means, const float *__restrict__ quats, 
         if (calc_comp) {
             float comp = comps[g];
             float v_comp = v_op_eff * op;
-            v_opacities[g] = v_op_eff * comp;
+            o_opac = v_op_eff * comp;
             float det_conic = ia * ic - ib * ib;
             float v_sqr_comp = v_comp * 0.5f / (comp + 1e-6f);
             float one_minus = 1.0f - comp * comp;
@@ -287,7 +292,7 @@ k_project_bwd(const float *__restrict__ means, const float *__restrict__ quats, 
             G[2] += v_sqr_comp * (one_minus * ib);
             G[3] += v_sqr_comp * (one_minus * ic - eps2d * det_conic);
         } else {
-            v_opacities[g] = v_op_eff;
+            o_opac = v_op_eff;
         }
         float v_depth = with_depth ? v_colpack[(size_t)g * CDIM + d_in] : 0.f;
 
@@ -366,7 +371,7 @@ k_project_bwd(const float *__restrict__ means, const float *__restrict__ quats, 
             for (int j = 0; j < 3; ++j) vR[i * 3 + j] = vpc[i] * p[j];
         }
 #pragma unroll
-        for (int j = 0; j < 3; ++j) v_means[3 * g + j] = R[0 * 3 + j] * vpc[0] + R[1 * 3 + j] * vpc[1] + R[2 * 3 + j] * vpc[2];
+        for (int j = 0; j < 3; ++j) o_means[j] = R[0 * 3 + j] * vpc[0] + R[1 * 3 + j] * vpc[1] + R[2 * 3 + j] * vpc[2];
         // v_R += vSc (R Sigma^T) + vSc^T (R Sigma)
         float tmp[9];
         mat3_mul(vSc, RS, tmp);
@@ -394,15 +399,55 @@ k_project_bwd(const float *__restrict__ means, const float *__restrict__ quats, 
             for (int j = 0; j < 3; ++j) Gq[i * 3 + j] = vM[i * 3 + j] * s[j];
 #pragma unroll
         for (int j = 0; j < 3; ++j)
-            v_scales[3 * g + j] = Rq[0 * 3 + j] * vM[0 * 3 + j] + Rq[1 * 3 + j] * vM[1 * 3 + j] + Rq[2 * 3 + j] * vM[2 * 3 + j];
+            o_scales[j] = Rq[0 * 3 + j] * vM[0 * 3 + j] + Rq[1 * 3 + j] * vM[1 * 3 + j] + Rq[2 * 3 + j] * vM[2 * 3 + j];
         float vqn[4];
         vqn[0] = 2.f * (qx * (Gq[7] - Gq[5]) + qy * (Gq[2] - Gq[6]) + qz * (Gq[3] - Gq[1]));
         vqn[1] = 2.f * (-2.f * qx * (Gq[4] + Gq[8]) + qy * (Gq[1] + Gq[3]) + qz * (Gq[2] + Gq[6]) + qw * (Gq[7] - Gq[5]));
         vqn[2] = 2.f * (qx * (Gq[1] + Gq[3]) - 2.f * qy * (Gq[0] + Gq[8]) + qz * (Gq[5] + Gq[7]) + qw * (Gq[2] - Gq[6]));
         vqn[3] = 2.f * (qx * (Gq[2] + Gq[6]) + qy * (Gq[5] + Gq[7]) - 2.f * qz * (Gq[0] + Gq[4]) + qw * (Gq[3] - Gq[1]));
         float dotp = vqn[0] * qw + vqn[1] * qx + vqn[2] * qy + vqn[3] * qz;
-        v_quats[g] = make_float4((vqn[0] - dotp * qw) * inv_norm, (vqn[1] - dotp * qx) * inv_norm,
-                                 (vqn[2] - dotp * qy) * inv_norm, (vqn[3] - dotp * qz) * inv_norm);
+        o_quat = make_float4((vqn[0] - dotp * qw) * inv_norm, (vqn[1] - dotp * qx) * inv_norm,
+                             (vqn[2] - dotp * qy) * inv_norm, (vqn[3] - dotp * qz) * inv_norm);
+    }
+    if (!EXCH) {
+        if (g < N) {
+            v_means[3 * g] = o_means[0]; v_means[3 * g + 1] = o_means[1]; v_means[3 * g + 2] = o_means[2];
+            v_scales[3 * g] = o_scales[0]; v_scales[3 * g + 1] = o_scales[1]; v_scales[3 * g + 2] = o_scales[2];
+            v_quats[g] = o_quat;
+            v_opacities[g] = o_opac;
+        }
+    } else {
+        // ---- transpose the CTA's rows through shared memory, then 16-byte coalesced stores into the owner's slot
+        extern __shared__ __align__(16) float s_ex[];  // [768 means | 1024 quats | 768 scales | 256 opac | d_in * 256 colours]
+        const int t = threadIdx.x;
+        s_ex[3 * t] = o_means[0]; s_ex[3 * t + 1] = o_means[1]; s_ex[3 * t + 2] = o_means[2];
+        reinterpret_cast<float4 *>(s_ex + 768)[t] = o_quat;
+        s_ex[1792 + 3 * t] = o_scales[0]; s_ex[1792 + 3 * t + 1] = o_scales[1]; s_ex[1792 + 3 * t + 2] = o_scales[2];
+        s_ex[2560 + t] = o_opac;
+        for (int k = 0; k < d_in; ++k) s_ex[2816 + d_in * t + k] = live ? v_colpack[(size_t)g * CDIM + k] : 0.f;
+        __syncthreads();
+        const int g0 = blockIdx.x * 256;
+        const int owner = g0 / ex.shard, l0 = g0 - owner * ex.shard;
+        const int rows = min(256, N - g0);
+        float *slot = ex.stage[owner] + (size_t)ex.rank * ex.slot_floats;
+        const int widths[5] = {3, 4, 3, 1, d_in};
+        int s_off = 0, a_p = 0;
+#pragma unroll
+        for (int p = 0; p < 5; ++p) {
+            const int wp = widths[p];
+            float *dst = slot + (size_t)a_p * ex.shard + (size_t)wp * l0;
+            const float *src = s_ex + s_off;
+            const int nvalid = wp * rows;
+            for (int e = 4 * t; e < nvalid; e += 1024) {
+                if (e + 3 < nvalid) {
+                    *reinterpret_cast<float4 *>(dst + e) = *reinterpret_cast<const float4 *>(src + e);
+                } else {
+                    for (int k = e; k < nvalid; ++k) dst[k] = src[k];
+                }
+            }
+            s_off += wp * 256;
+            a_p += wp;
+        }
     }
     // viewmat gradient: 12 sums over all Gaussians -> warp butterfly, smem across warps, 12 atomics / CTA
     if (v_viewmat != nullptr) {
@@ -429,6 +474,23 @@ k_project_bwd(const float *__restrict__ means, const float *__restrict__ quats, 
             int k = threadIdx.x;
             int dst = k < 9 ? (k / 3) * 4 + (k % 3) : (k - 9) * 4 + 3;
             if (a != 0.f) atomicAdd(v_viewmat + dst, a);
+        }
+    }
+    if (EXCH) {
+        // every CTA: make its peer stores visible system-wide, then take a ticket; the last CTA raises this rank's
+        // "partials delivered" flag (phase 0) at every rank and re-arms the ticket for the next launch
+        __shared__ unsigned s_last;
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = atomicAdd(ex.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+        __syncthreads();
+        if (s_last) {
+            __threadfence_system();
+            if (threadIdx.x < ex.world) {
+                volatile unsigned *f = ex.flags[threadIdx.x] + ex.rank;  // phase 0 row
+                *f = ex.epoch;
+            }
+            if (threadIdx.x == 0) *ex.ticket = 0u;
         }
     }
 }
@@ -476,11 +538,35 @@ extern "C" int b2s_project_bwd(const float *means, const float *quats, const flo
     if (N == 0) return B2S_OK;
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(b2s_div_up(N, 256)), block(256);
-#define LAUNCH(CD)                                                                                            \
-    k_project_bwd<CD><<<grid, block, 0, st>>>(means, quats, scales, opacities, viewmat, K, N, W, H, eps2d,     \
-                                              calc_comp, d_in, with_depth, radii, (const float4 *)geo, comps, \
-                                              v_means2d, v_means2d_stride, (const float4 *)v_geo, v_colpack, \
-                                              v_means, (float4 *)v_quats, v_scales, v_opacities, v_viewmat)
+    B2sExchange none = {};
+#define LAUNCH(CD)                                                                                                \
+    k_project_bwd<CD, false><<<grid, block, 0, st>>>(means, quats, scales, opacities, viewmat, K, N, W, H, eps2d,  \
+                                                     calc_comp, d_in, with_depth, radii, (const float4 *)geo,     \
+                                                     comps, v_means2d, v_means2d_stride, (const float4 *)v_geo,   \
+                                                     v_colpack, v_means, (float4 *)v_quats, v_scales, v_opacities, \
+                                                     v_viewmat, none)
+    if (cdim == 4) LAUNCH(4);
+    else LAUNCH(8);
+#undef LAUNCH
+    B2S_LAUNCH_CHECK();
+    return B2S_OK;
+}
+
+// Exchange variant (called by b2s_project_bwd_exchange in exchange.cu): rows [0, n_rows) go to their owners' slots.
+int b2s_launch_project_bwd_exchange(const float *means, const float *quats, const float *scales, const float *opacities,
+                                    const float *viewmat, const float *K, int n_rows, int W, int H, float eps2d,
+                                    int calc_comp, int d_in, int with_depth, int cdim, const int32_t *radii,
+                                    const float *geo, const float *comps, const float *v_means2d, int v_means2d_stride,
+                                    const float *v_geo, const float *v_colpack, float *v_viewmat, const B2sExchange &ex,
+                                    cudaStream_t st) {
+    dim3 grid(b2s_div_up(n_rows, 256)), block(256);
+    const size_t smem = (size_t)(11 + d_in) * 256 * sizeof(float);
+#define LAUNCH(CD)                                                                                               \
+    k_project_bwd<CD, true><<<grid, block, smem, st>>>(means, quats, scales, opacities, viewmat, K, n_rows, W, H, \
+                                                       eps2d, calc_comp, d_in, with_depth, radii,                \
+                                                       (const float4 *)geo, comps, v_means2d, v_means2d_stride,  \
+                                                       (const float4 *)v_geo, v_colpack, nullptr, nullptr,       \
+                                                       nullptr, nullptr, v_viewmat, ex)
     if (cdim == 4) LAUNCH(4);
     else LAUNCH(8);
 #undef LAUNCH

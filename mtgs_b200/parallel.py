@@ -116,3 +116,196 @@ def seed_everything_identically(seed: int, step: int) -> torch.Generator:
     g = torch.Generator()
     g.manual_seed(int(seed) * 1_000_003 + int(step))
     return g
+
+
+# ------------------------------------------------------------------------------------------------
+# Fused gradient exchange (projection backward + reduce-scatter / all-gather over NVLink peer memory)
+# ------------------------------------------------------------------------------------------------
+_ACTIVE_EXCHANGE = None
+
+
+def current_exchange():
+    """The GradExchange that ``rasterization``'s backward should route the gradients of its Gaussian inputs
+    through (None = plain single-GPU backward)."""
+    return _ACTIVE_EXCHANGE
+
+
+class _DevMem:
+    """``__cuda_array_interface__`` view of library-owned device memory (torch.as_tensor aliases it)."""
+
+    def __init__(self, ptr: int, n_floats: int):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+class GradExchange:
+    """Sum (or mean) over ranks of the gradients w.r.t. the rasterizer's Gaussian inputs, produced INSIDE the
+    projection backward instead of by an all-reduce after it (``include/b200splat.h``: b2s_project_bwd_exchange;
+    kernels in csrc/project.cu and csrc/exchange.cu).
+
+    Rows ``[0, n_shared)`` of means / quats / scales / opacities / colors are the replicated shared-node Gaussians
+    (identical values on every rank); rows beyond are rank-local (the vehicles of the rank's own traversal,
+    reference rigid_node.py:87, 259-261) and stay on the GPU.  Because the activations MTGS applies before the
+    rasterizer (vanilla_gaussian_splatting.py:299-307) are elementwise functions of replicated parameters, reducing
+    at the rasterizer inputs and then back-propagating the reduced gradient locally gives the same leaf gradients
+    as reducing at the leaves.
+
+    Usage (one process per GPU, ``torch.distributed`` initialised with NCCL)::
+
+        ex = GradExchange(n_shared=N, d_in=3, rows_cap=N)
+        render, alpha, info = rasterization(...)
+        with ex.active():
+            loss.backward()          # .grad of the inputs already holds the mean over all ranks
+    """
+
+    MAX_WORLD = 8
+
+    def __init__(self, n_shared: int, d_in: int, rows_cap: Optional[int] = None, group=None, average: bool = True,
+                 device: Optional[torch.device] = None, _local: Optional[tuple] = None):
+        from . import _lib
+        import ctypes as C
+        self._lib = lib = _lib.load()
+        self._check = _lib.check
+        if _local is not None:            # test harness: several ranks played by one process on one GPU
+            self.world, self.rank = _local
+        elif dist.is_available() and dist.is_initialized():
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        else:
+            self.world, self.rank = 1, 0
+        if self.world > self.MAX_WORLD:
+            raise NotImplementedError(f"GradExchange supports up to {self.MAX_WORLD} ranks (one NVSwitch domain)")
+        self.group = group
+        self.n_shared, self.d_in = int(n_shared), int(d_in)
+        self.rows_cap = (int(rows_cap if rows_cap is not None else n_shared) + 3) // 4 * 4
+        if self.rows_cap < self.n_shared:
+            raise ValueError("rows_cap < n_shared")
+        self.scale = 1.0 / self.world if average else 1.0
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.shard = int(lib.b2s_exchange_shard_rows(self.n_shared, self.world))
+        self.F = 11 + self.d_in
+        self._sizes = (self.world * self.F * self.shard * 4, self.F * self.rows_cap * 4, 256)
+        self._own = []
+        with torch.cuda.device(self.device):
+            for nbytes in self._sizes:
+                p = C.c_void_p()
+                self._check(lib.b2s_peer_alloc(nbytes, C.byref(p)), "b2s_peer_alloc")
+                self._own.append(int(p.value))
+        self.stage_ptrs = [0] * self.world
+        self.arena_ptrs = [0] * self.world
+        self.flag_ptrs = [0] * self.world
+        self.stage_ptrs[self.rank], self.arena_ptrs[self.rank], self.flag_ptrs[self.rank] = self._own
+        self._imported = []
+        self.arena = torch.as_tensor(_DevMem(self._own[1], self.F * self.rows_cap), device=self.device)
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.epoch = 0
+        if _local is None and self.world > 1:
+            self._rendezvous()
+
+    # -- set-up ---------------------------------------------------------------------------------
+    def _rendezvous(self) -> None:
+        """Exchange CUDA IPC handles of the three buffers and map every peer's copies."""
+        import ctypes as C
+        mine = []
+        with torch.cuda.device(self.device):
+            for p in self._own:
+                buf = C.create_string_buffer(64)
+                self._check(self._lib.b2s_ipc_export(C.c_void_p(p), buf), "b2s_ipc_export")
+                mine.append(bytes(buf.raw))
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, mine, group=self.group)
+        with torch.cuda.device(self.device):
+            for r, handles in enumerate(gathered):
+                if r == self.rank:
+                    continue
+                ptrs = []
+                for h in handles:
+                    q = C.c_void_p()
+                    self._check(self._lib.b2s_ipc_import(C.create_string_buffer(h, 64), C.byref(q)), "b2s_ipc_import")
+                    ptrs.append(int(q.value))
+                    self._imported.append(int(q.value))
+                self.stage_ptrs[r], self.arena_ptrs[r], self.flag_ptrs[r] = ptrs
+        dist.barrier(group=self.group)
+
+    @staticmethod
+    def local_ranks(world: int, n_shared: int, d_in: int, rows_cap: Optional[int] = None, average: bool = True,
+                    device: Optional[torch.device] = None) -> List["GradExchange"]:
+        """``world`` exchanges living in ONE process on ONE GPU, wired to each other's buffers (tests only:
+        every rank's backward runs phase 1, then ``finish_all`` plays the remaining phases, all on one stream)."""
+        exs = [GradExchange(n_shared, d_in, rows_cap, average=average, device=device, _local=(world, r))
+               for r in range(world)]
+        for a in exs:
+            for b in exs:
+                a.stage_ptrs[b.rank], a.arena_ptrs[b.rank], a.flag_ptrs[b.rank] = b._own
+        for a in exs:
+            a._phases = 1
+        return exs
+
+    _phases = 7
+
+    def close(self) -> None:
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            for p in self._imported:
+                self._lib.b2s_ipc_close(p)
+            for p in self._own:
+                self._lib.b2s_peer_free(p)
+        self._imported, self._own = [], []
+
+    # -- per step -------------------------------------------------------------------------------
+    def active(self):
+        ex = self
+
+        class _Ctx:
+            def __enter__(self_inner):
+                global _ACTIVE_EXCHANGE
+                self_inner.prev = _ACTIVE_EXCHANGE
+                _ACTIVE_EXCHANGE = ex
+                return ex
+
+            def __exit__(self_inner, *exc):
+                global _ACTIVE_EXCHANGE
+                _ACTIVE_EXCHANGE = self_inner.prev
+                return False
+
+        return _Ctx()
+
+    def grad_views(self, N: int) -> Dict[str, Tensor]:
+        """Views of the arena holding the gradients of an N-row call (rows < n_shared: reduced over ranks)."""
+        c, a = self.rows_cap, self.arena
+        return {"means": a[0:3 * N].view(N, 3), "quats": a[3 * c:3 * c + 4 * N].view(N, 4),
+                "scales": a[7 * c:7 * c + 3 * N].view(N, 3), "opacities": a[10 * c:10 * c + N],
+                "colors": a[11 * c:11 * c + self.d_in * N].view(N, self.d_in)}
+
+    def _ptr_array(self, ptrs):
+        import ctypes as C
+        return (C.c_ulonglong * self.MAX_WORLD)(*(list(ptrs) + [0] * (self.MAX_WORLD - len(ptrs))))
+
+    def launch(self, phases: int, args: Optional[tuple] = None) -> None:
+        """Enqueue the selected phases on the current stream (``args`` = the projection-backward operands)."""
+        import ctypes as C
+        if phases & 1:
+            self.epoch += 1
+        if args is None:
+            args = self._last_args
+        self._last_args = args
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        self._check(self._lib.b2s_project_bwd_exchange(
+            *args, self.n_shared, self.world, self.rank, self.rows_cap, self.scale, self.epoch, phases,
+            self._ptr_array(self.stage_ptrs), self._ptr_array(self.arena_ptrs), self._ptr_array(self.flag_ptrs),
+            C.c_void_p(self.ticket.data_ptr()), C.c_void_p(self.status.data_ptr()), stream),
+            "b2s_project_bwd_exchange")
+
+    @staticmethod
+    def finish_all(exs: Sequence["GradExchange"]) -> None:
+        """Test harness (see ``local_ranks``): the reduce / broadcast phase of every rank, then every rank's wait."""
+        for e in exs:
+            e.launch(2)
+        for e in exs:
+            e.launch(4)
+
+    def check(self) -> None:
+        """Synchronise and raise if a peer never arrived (a spin loop timed out)."""
+        code = int(self.status.item())
+        if code:
+            raise RuntimeError(f"gradient exchange timed out waiting for a peer (phase code {code})")

@@ -138,12 +138,28 @@ class _Project(torch.autograd.Function):
         v_geo = torch.zeros(N, 4, dtype=torch.float32, device=dev) if v_geo is None else v_geo.contiguous()
         v_colpack = (torch.zeros(N, cdim, dtype=torch.float32, device=dev) if v_colpack is None
                      else v_colpack.contiguous())
+        need_view = ctx.needs_input_grad[5]
+        v_view = torch.zeros(4, 4, dtype=torch.float32, device=dev) if need_view else None
+        from . import parallel
+        ex = parallel.current_exchange()
+        if ex is not None:
+            # multi-GPU: gradients leave the kernel straight into the owners' peer memory and come back reduced
+            if ex.d_in != d_in or N > ex.rows_cap or N < ex.n_shared or not ctx.has_colors:
+                raise RuntimeError(f"GradExchange(n_shared={ex.n_shared}, d_in={ex.d_in}, rows_cap={ex.rows_cap}) "
+                                   f"does not match this call (N={N}, d_in={d_in})")
+            args = (_ptr(means), _ptr(quats), _ptr(scales), _ptr(opacities), _ptr(viewmat), _ptr(K), N, W, H, eps2d,
+                    int(calc_comp), d_in, int(with_depth), cdim, _ptr(radii), _ptr(geo), _ptr(comps), _ptr(v_means2d),
+                    int(v_means2d.stride(0)), _ptr(v_geo), _ptr(v_colpack), _ptr(v_view))
+            with _timed("project_bwd_exchange"):
+                ex.launch(ex._phases, args)
+            gv = ex.grad_views(N)
+            if N > ex.n_shared:
+                gv["colors"][ex.n_shared:] = v_colpack[ex.n_shared:, :d_in]
+            return (gv["means"], gv["quats"], gv["scales"], gv["opacities"], gv["colors"], v_view) + (None,) * 12
         v_means = torch.empty_like(means)
         v_quats = torch.empty_like(quats)
         v_scales = torch.empty_like(scales)
         v_opac = torch.empty_like(opacities)
-        need_view = ctx.needs_input_grad[5]
-        v_view = torch.zeros(4, 4, dtype=torch.float32, device=dev) if need_view else None
         with _timed("project_bwd"):
             _lib.check(lib.b2s_project_bwd(_ptr(means), _ptr(quats), _ptr(scales), _ptr(opacities), _ptr(viewmat),
                                            _ptr(K), N, W, H, eps2d, int(calc_comp), d_in, int(with_depth), cdim,
