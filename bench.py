@@ -166,6 +166,9 @@ def main():
     ap.add_argument("--variant", default="rgbed")
     ap.add_argument("--cpu-sample", type=int, default=400_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="multi-GPU gradient exchange: fused into the projection backward over peer memory "
+                         "(default) or an NCCL all-reduce after the backward (the baseline it replaces)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -178,7 +181,9 @@ def main():
                 f"{vcfg['render_mode']} {vcfg['rasterize_mode']} absgrad d_in={vcfg['d_in']}")
     config = {"workload": workload, "n_gaussians": args.n_gauss, "width": args.width, "height": args.height,
               "variant": args.variant, "cameras_per_rank": 1,
-              "parallelism": f"traversal-per-gpu x{world}" if world > 1 else "single-gpu",
+              "parallelism": (f"traversal-per-gpu x{world}, shared-gradient exchange: " +
+                              ("fused into projection backward (NVLink peer stores)" if args.exchange == "fused"
+                               else "NCCL all-reduce")) if world > 1 else "single-gpu",
               "l2_policy": "per-step working set (>1 GB) exceeds the 126 MB L2; no explicit flush"}
 
     from mtgs_b200 import scenes
@@ -208,7 +213,7 @@ def main():
     from mtgs_b200 import _lib
     from mtgs_b200 import rendering
     from mtgs_b200.rendering import rasterization
-    from mtgs_b200.parallel import SharedGradArena
+    from mtgs_b200.parallel import GradExchange, SharedGradArena
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback in the product path)"
     torch.cuda.set_device(local_rank)
@@ -230,7 +235,9 @@ def main():
     gen.manual_seed(1234 + rank)
     w_c = torch.randn(1, H, W, d_out, device=dev, generator=gen)
     w_a = torch.randn(1, H, W, 1, device=dev, generator=gen)
-    arena = SharedGradArena([params[k] for k in names], average=True) if world > 1 else None
+    fused = world > 1 and args.exchange == "fused"
+    arena = SharedGradArena([params[k] for k in names], average=True) if (world > 1 and not fused) else None
+    exch = GradExchange(n_shared=N, d_in=vcfg["d_in"], rows_cap=N, average=True) if fused else None
 
     def step(p):
         with rendering._timed("phase_forward"):
@@ -245,7 +252,11 @@ def main():
             for t in p.values():
                 t.grad = None
         with rendering._timed("phase_backward"):
-            loss.backward()
+            if exch is not None:
+                with exch.active():  # gradients come back already averaged over the ranks
+                    loss.backward()
+            else:
+                loss.backward()
         if arena is not None:
             with rendering._timed("phase_allreduce"):
                 arena.all_reduce()
@@ -318,7 +329,7 @@ def main():
         issue_copy(1 - j)
         torch.cuda.current_stream().wait_event(copied[j])
         p = {k: dbuf[j][k].detach().requires_grad_(True) for k in names}
-        l, _ = step(p) if arena is None else step_e2e_multi(p)
+        l, _ = step_e2e_multi(p) if arena is not None else step(p)
         gn = p["means"].grad.norm()
         return torch.stack([l.detach(), gn]).cpu()  # D2H read of the step's result (8 bytes), synchronises
 
@@ -353,6 +364,9 @@ def main():
            "ms_per_step": e2e_ms, "steps": e2e_steps}
 
     if rank != 0:
+        if exch is not None:
+            exch.check()
+            exch.close()
         if dist is not None:
             dist.destroy_process_group()
         return
@@ -361,8 +375,10 @@ def main():
     peak, peak_src = measured_peaks()
     ab = algorithmic_bytes(N, N_vis, M, W * H, vcfg["d_in"], 4 if d_out <= 4 else 8, vcfg["absgrad"])
     stage_bytes = {"project_fwd": ab["project_fwd"], "bin_sort_depth": N * 8 * 8, "bin_tiles": ab["bin"],
-                   "blend_fwd": ab["blend_fwd"], "blend_bwd": ab["blend_bwd"], "project_bwd": ab["project_bwd"]}
-    phase_ms = {k: stage_ms.pop(k) for k in list(stage_ms) if k.startswith("phase_")}
+                   "blend_fwd": ab["blend_fwd"], "blend_bwd": ab["blend_bwd"], "project_bwd": ab["project_bwd"],
+                   # + partial rows out, `world` partial slots in, reduced rows out to every rank
+                   "project_bwd_exchange": ab["project_bwd"] + N * (44 + 4 * vcfg["d_in"]) * 2}
+    phase_ms = {k: stage_ms.pop(k) for k in list(stage_ms) if k.startswith("phase_") or k.startswith("exch_")}
     dom = max(stage_ms, key=stage_ms.get) if stage_ms else None
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -395,7 +411,7 @@ def main():
 
     # ---- HBM-bound stages: achieved algorithmic GB/s of the streaming kernels + the SH operator (row a9)
     hbm_stages = {}
-    for k in ("project_fwd", "project_bwd"):
+    for k in ("project_fwd", "project_bwd", "project_bwd_exchange"):
         if k in stage_ms:
             gbs = stage_bytes[k] / (stage_ms[k] * 1e-3) / 1e9
             hbm_stages[k] = {"ms": stage_ms[k], "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peak}
@@ -445,6 +461,9 @@ def main():
             "stats": {"N_vis": N_vis, "M": M, "stage_ms": stage_ms, "phase_ms": phase_ms, "hbm_bound_stages": hbm_stages,
                       "loss": float(loss.item()) if math.isfinite(float(loss.item())) else None}}
     print(json.dumps(line))
+    if exch is not None:
+        exch.check()
+        exch.close()
     if dist is not None:
         dist.destroy_process_group()
 

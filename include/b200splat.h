@@ -86,8 +86,9 @@ int b2s_project_bwd(const float *means, const float *quats, const float *scales,
  * local gradient for the others.  *_ptrs_host are HOST arrays of `world` device pointers (this rank's own buffers at
  * index `rank`); epoch must increase by one per call on every rank; *status (device word) becomes non-zero if a
  * wait timed out (~2 s) instead of hanging the GPU.  Colour gradients of the rank-local rows are left in v_colpack.
- * phases: bit 0 = projection backward + peer stores, bit 1 = reduce + broadcast, bit 2 = final wait (7 = all; the
- * split exists so that a test can play several ranks on one GPU from one stream). */
+ * phases: bit 0 = projection backward + peer stores + "partials delivered" flags, bit 1 = reduce + broadcast,
+ * bit 2 = "result delivered" flags, bit 3 = final wait (15 = all; the split exists so that a test can play several
+ * ranks on one GPU from one stream). */
 int b2s_exchange_shard_rows(int n_shared, int world);
 int b2s_peer_alloc(size_t bytes, void **dev_ptr); /* cudaMalloc + zero fill (set-up only) */
 int b2s_peer_free(void *dev_ptr);

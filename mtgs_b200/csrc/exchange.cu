@@ -9,11 +9,13 @@
 //   K1  k_project_bwd<.., EXCH = true>  (project.cu)   every rank computes its partial gradient rows and stores them
 //       straight into the staging slot [owner][source] of the rank that owns the rows (16-byte coalesced peer stores)
 //       -- the reduce-scatter traffic overlaps the projection backward's arithmetic; no local partial-gradient
-//       buffer is written, zero-filled or re-read.  The last CTA raises flag[phase 0][rank] at every peer.
+//       buffer is written, zero-filled or re-read.  A one-warp kernel then raises flag[phase 0][rank] at every peer
+//       (the kernel boundary has completed the peer stores, so no CTA pays a system fence).
 //   K2  k_grad_reduce_bcast             every rank waits for all phase-0 flags, sums the `world` partial slots of ITS
 //       rows from local HBM, scales (1 / world for the mean) and stores the result into EVERY rank's gradient arena
-//       (peer stores: the all-gather half).  The last CTA raises flag[phase 1][rank] at every peer.
-//   K3  k_exchange_wait                 stream-ordered wait for all phase-1 flags: afterwards this rank's arena holds
+//       (peer stores: the all-gather half).
+//   K3  k_exchange_signal + k_exchange_wait   raise flag[phase 1][rank] at every peer, then wait for all phase-1
+//       flags in stream order: afterwards this rank's arena holds
 //       the reduced gradient of every shared row and the stream continues (activations' VJPs, optimizer).
 //
 // Rows at or beyond n_shared (rank-local nodes, e.g. the vehicles of this rank's traversal; reference
@@ -89,22 +91,20 @@ k_grad_reduce_bcast(const B2sExchange ex, int n_shared, int d_in, long long rows
             }
         }
     }
-    // completion: last CTA raises this rank's phase-1 flag everywhere (also after a timeout, so peers do not hang)
-    __shared__ unsigned s_last;
+}
+
+// One warp: raise this rank's flag of `phase` at every rank.  Launched right after the kernel whose peer stores it
+// publishes: the kernel boundary has completed those stores system-wide, so no CTA of the producer ever fences.
+__global__ void __launch_bounds__(32)
+k_exchange_signal(const B2sExchange ex, int phase) {
     __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(ex.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
-    __syncthreads();
-    if (s_last) {
-        __threadfence_system();
-        if (threadIdx.x < ex.world) {
-            volatile unsigned *f = ex.flags[threadIdx.x] + B2S_MAX_WORLD + ex.rank;  // phase 1 row
-            *f = ex.epoch;
-        }
-        if (threadIdx.x == 0) *ex.ticket = 0u;
+    if (threadIdx.x < ex.world) {
+        volatile unsigned *f = ex.flags[threadIdx.x] + phase * B2S_MAX_WORLD + ex.rank;
+        *f = ex.epoch;
     }
 }
 
+// One warp: wait until every rank has published "my reduced rows are in every arena" (phase 1).
 __global__ void __launch_bounds__(32)
 k_exchange_wait(const B2sExchange ex, unsigned *__restrict__ status) {
     if (threadIdx.x < ex.world) {
@@ -201,6 +201,10 @@ extern "C" int b2s_project_bwd_exchange(
                              arena + 7 * rows_cap + 3 * o, arena + 10 * rows_cap + o, v_viewmat, stream);
         if (rc != B2S_OK) return rc;
     }
+    if (n_shared > 0 && (phases & 1)) {
+        k_exchange_signal<<<1, 32, 0, st>>>(ex, 0);
+        B2S_LAUNCH_CHECK();
+    }
     if (n_shared > 0 && (phases & 2)) {
         int device = 0, sms = 148;
         cudaGetDevice(&device);
@@ -209,6 +213,10 @@ extern "C" int b2s_project_bwd_exchange(
         B2S_LAUNCH_CHECK();
     }
     if (n_shared > 0 && (phases & 4)) {
+        k_exchange_signal<<<1, 32, 0, st>>>(ex, 1);
+        B2S_LAUNCH_CHECK();
+    }
+    if (n_shared > 0 && (phases & 8)) {
         k_exchange_wait<<<1, 32, 0, st>>>(ex, status);
         B2S_LAUNCH_CHECK();
     }

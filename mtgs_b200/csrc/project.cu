@@ -241,8 +241,10 @@ __device__ __forceinline__ void mat3_mul_at(const float *A, const float *B, floa
 // d_in floats per Gaussian) are transposed through shared memory and stored with 16-byte coalesced stores straight
 // into the staging slot of the rank that OWNS these rows (peer memory over NVLink) -- the reduce-scatter half of
 // the shared-gradient all-reduce happens while the projection backward is still computing, and this GPU never
-// writes (or later re-reads) a local copy of its partial gradient.  The last CTA to finish raises this rank's
-// flag at every peer (exchange.cu holds the reduce + all-gather half).
+// writes (or later re-reads) a local copy of its partial gradient.  The peer stores are fire-and-forget (no
+// per-CTA system fence: that exposed one NVLink round trip per CTA); the kernel boundary completes them and a
+// one-warp kernel then raises this rank's flag at every peer (exchange.cu, which also holds the reduce +
+// all-gather half).
 template <int CDIM, bool EXCH>
 __global__ void __launch_bounds__(256)
 k_project_bwd(const float *__restrict__ means, const float *__restrict__ quats, const float *__restrict__ scales,
@@ -474,23 +476,6 @@ k_project_bwd(const float *__restrict__ means, const float *__restrict__ quats, 
             int k = threadIdx.x;
             int dst = k < 9 ? (k / 3) * 4 + (k % 3) : (k - 9) * 4 + 3;
             if (a != 0.f) atomicAdd(v_viewmat + dst, a);
-        }
-    }
-    if (EXCH) {
-        // every CTA: make its peer stores visible system-wide, then take a ticket; the last CTA raises this rank's
-        // "partials delivered" flag (phase 0) at every rank and re-arms the ticket for the next launch
-        __shared__ unsigned s_last;
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) s_last = atomicAdd(ex.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
-        __syncthreads();
-        if (s_last) {
-            __threadfence_system();
-            if (threadIdx.x < ex.world) {
-                volatile unsigned *f = ex.flags[threadIdx.x] + ex.rank;  // phase 0 row
-                *f = ex.epoch;
-            }
-            if (threadIdx.x == 0) *ex.ticket = 0u;
         }
     }
 }

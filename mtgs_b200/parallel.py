@@ -241,7 +241,7 @@ class GradExchange:
             a._phases = 1
         return exs
 
-    _phases = 7
+    _phases = 15
 
     def close(self) -> None:
         with torch.cuda.device(self.device):
@@ -300,9 +300,9 @@ class GradExchange:
     def finish_all(exs: Sequence["GradExchange"]) -> None:
         """Test harness (see ``local_ranks``): the reduce / broadcast phase of every rank, then every rank's wait."""
         for e in exs:
-            e.launch(2)
+            e.launch(2 | 4)
         for e in exs:
-            e.launch(4)
+            e.launch(8)
 
     def check(self) -> None:
         """Synchronise and raise if a peer never arrived (a spin loop timed out)."""

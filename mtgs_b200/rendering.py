@@ -150,7 +150,15 @@ class _Project(torch.autograd.Function):
             args = (_ptr(means), _ptr(quats), _ptr(scales), _ptr(opacities), _ptr(viewmat), _ptr(K), N, W, H, eps2d,
                     int(calc_comp), d_in, int(with_depth), cdim, _ptr(radii), _ptr(geo), _ptr(comps), _ptr(v_means2d),
                     int(v_means2d.stride(0)), _ptr(v_geo), _ptr(v_colpack), _ptr(v_view))
-            with _timed("project_bwd_exchange"):
+            if PROFILE is not None and ex._phases == 15:  # per-phase timing for bench.py
+                with _timed("project_bwd_exchange"):
+                    with _timed("exch_k1_project_bwd_peer_stores"):
+                        ex.launch(1, args)
+                    with _timed("exch_k2_reduce_bcast"):
+                        ex.launch(2)
+                    with _timed("exch_k3_wait"):
+                        ex.launch(4 | 8)
+            else:
                 ex.launch(ex._phases, args)
             gv = ex.grad_views(N)
             if N > ex.n_shared:
