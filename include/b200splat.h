@@ -110,23 +110,22 @@ int b2s_project_bwd_exchange(const float *means, const float *quats, const float
 /* ---- tile binning + depth sort (upstream isect_tiles + radix sort + isect_offset_encode; A.2) ----
  * Two-level formulation with identical results to the stable 64-bit sort:
  *   (1) b2s_bin_sort_depth : stable sort of the visible Gaussians by depth key (one cooperative kernel) ->
- *       order[0..n_vis), cum_rows[i] = exclusive scan of the rectangle heights (tile rows covered) in that
- *       order, totals[0] = M (tile intersections), totals[1] = S (tile-row hits = sum of the rectangle
- *       heights; sizes the workspace of (2)), *n_vis (device int32).  totals is a device int64[2]: the
- *       caller reads it back once to size flatten_ids.  Entries beyond n_vis are undefined.
- *   (2) b2s_bin_tiles      : two order-preserving interval multisplits (Gaussians -> tile-row lists ->
- *       tile lists) walking the Gaussians in depth order -> flatten_ids[M], isect_offsets[tile_h*tile_w]
- *       (no sort of the M intersections).
+ *       order[0..n_vis), *n_vis (device int32) and totals (device int64[5]) = {M tile intersections, S tile-row
+ *       hits, E1 row-group hits, E3 (row, column-group) hits, n_vis}: the list sizes of every level of (2).  The
+ *       caller reads totals back once (the one device->host read of the path; it sizes flatten_ids and the
+ *       workspace of (2)).  Entries of order beyond n_vis are undefined.
+ *   (2) b2s_bin_tiles      : hierarchy of order-preserving filters (Gaussians -> row groups -> tile rows ->
+ *       column groups -> tiles) walking the Gaussians in depth order -> flatten_ids[M],
+ *       isect_offsets[tile_h*tile_w] (no sort of the M intersections).  totals_host = the five values of (1).
  *   (3) b2s_bin_isect_ids  : optional, rebuilds upstream's int64 isect_ids for inspection. */
 size_t b2s_bin_depth_workspace_bytes(int N);
 int b2s_bin_sort_depth(const uint32_t *sort_keys, const int32_t *tiles_per_gauss,
-                       const int32_t *tile_rects, int N, int32_t *order, int32_t *cum_rows,
+                       const int32_t *tile_rects, int N, int tile_w, int tile_h, int32_t *order,
                        int64_t *totals, int32_t *n_vis, void *workspace, size_t workspace_bytes,
                        b2s_stream_t stream);
-size_t b2s_bin_tiles_workspace_bytes(int N, long long M, long long S, int tile_w, int tile_h);
-int b2s_bin_tiles(const int32_t *tile_rects, const int32_t *order, const int32_t *cum_rows,
-                  const int32_t *n_vis, int N, long long M, long long S, int tile_size, int tile_w,
-                  int tile_h,
+size_t b2s_bin_tiles_workspace_bytes(const long long *totals_host, int tile_w, int tile_h);
+int b2s_bin_tiles(const int32_t *tile_rects, const int32_t *order, const int32_t *n_vis,
+                  const long long *totals_host, int N, int tile_size, int tile_w, int tile_h,
                   int32_t *flatten_ids, int32_t *isect_offsets, void *workspace,
                   size_t workspace_bytes, b2s_stream_t stream);
 int b2s_bin_isect_ids(const int32_t *isect_offsets, int n_tiles, const int32_t *flatten_ids,

@@ -30,9 +30,9 @@ SIGNATURES = {
     "b2s_project_bwd_exchange": (_i, [_vp] * 6 + [_i] * 3 + [_f] + [_i] * 4 + [_vp] * 4 + [_i] + [_vp] * 3 +
                                  [_i, _i, _i, _ll, _f, C.c_uint, _i] + [_vp] * 5 + [_vp]),
     "b2s_bin_depth_workspace_bytes": (_sz, [_i]),
-    "b2s_bin_sort_depth": (_i, [_vp] * 3 + [_i] + [_vp] * 5 + [_sz, _vp]),
-    "b2s_bin_tiles_workspace_bytes": (_sz, [_i, _ll, _ll, _i, _i]),
-    "b2s_bin_tiles": (_i, [_vp] * 4 + [_i, _ll, _ll, _i, _i, _i] + [_vp] * 3 + [_sz, _vp]),
+    "b2s_bin_sort_depth": (_i, [_vp] * 3 + [_i, _i, _i] + [_vp] * 4 + [_sz, _vp]),
+    "b2s_bin_tiles_workspace_bytes": (_sz, [C.POINTER(_ll), _i, _i]),
+    "b2s_bin_tiles": (_i, [_vp] * 3 + [C.POINTER(_ll), _i, _i, _i, _i] + [_vp] * 3 + [_sz, _vp]),
     "b2s_bin_isect_ids": (_i, [_vp, _i, _vp, _vp, _ll, _vp, _vp]),
     "b2s_blend_fwd": (_i, [_vp] * 5 + [_ll] + [_i] * 7 + [_vp] * 3 + [_vp]),
     "b2s_blend_bwd": (_i, [_vp] * 5 + [_ll] + [_i] * 7 + [_vp] * 8 + [_vp]),

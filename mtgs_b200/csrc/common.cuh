@@ -70,6 +70,9 @@ struct B2sExchange {
     unsigned *ticket;                // local CTA ticket counter (zero between launches)
 };
 
+// tile rows per row group / tile columns per column group of the tile-list hierarchy (tilelists.cu)
+int b2s_tl_shifts(int tile_w, int tile_h, int *rg_shift, int *cg_shift);
+
 // device-wide exclusive scan of int32 (binning.cu); `in` may alias `out`; gather may be null.
 // ws must hold b2s_scan_ws_ints(n) ints.  Grand total (int64) is written to *total_out when non-null.
 size_t b2s_scan_ws_ints(int n);

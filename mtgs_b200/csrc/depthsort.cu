@@ -5,8 +5,8 @@
 // bits) equals a stable sort of the GAUSSIANS by depth bits followed by an order-preserving bucketing of their
 // intersections by tile (tilelists.cu).  This file produces
 //     order[0 .. n_vis)  Gaussian ids in stable depth order (ties: ascending id), culled Gaussians dropped
-//     cum_rows[0 .. n_vis)  exclusive scan, in that order, of the rectangle heights (tile rows a Gaussian covers)
-//     totals[2]          M = number of tile intersections, S = number of tile-row hits (sum of rectangle heights)
+//     totals[5]          M = tile intersections, S = tile-row hits, E1 / E3 = row-group and (row, column-group) hits
+//                        (the list sizes of the tile-list hierarchy, tilelists.cu), n_vis
 //     n_vis
 //
 // A multi-launch LSD radix sort of 2 M keys spent most of its time in launch/drain gaps between ~15 small
@@ -67,8 +67,8 @@ __device__ __forceinline__ int ds_block_excl_scan(int v, int *total, int *s_w) {
 __global__ void __launch_bounds__(DS_THREADS)
 k_depth_sort_coop(const uint32_t *__restrict__ keys_in, const int32_t *__restrict__ tiles_per_gauss, int N,
                   uint32_t *kA, uint32_t *vA, uint32_t *kB, uint32_t *vB /* == order */, int32_t *table /* [BINS][G] */,
-                  int32_t *digit_tot /* [BINS] */, int32_t *blk_sums /* [G] */, const int2 *__restrict__ rects,
-                  int32_t *cum_rows, int64_t *totals_out /* [2]: M, S */, int32_t *nvis_out) {
+                  int32_t *digit_tot /* [BINS] */, const int2 *__restrict__ rects, int rg_shift, int cg_shift,
+                  int64_t *totals_out /* [5]: M, S, E1, E3, n_vis */, int32_t *nvis_out) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ int ds_smem[];
     int *s_cnt = ds_smem;                           // [DS_WARPS][DS_BINS]
@@ -77,7 +77,7 @@ k_depth_sort_coop(const uint32_t *__restrict__ keys_in, const int32_t *__restric
     const int G = gridDim.x, b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = lanemask_lt();
-    if (b == 0 && tid == 0) totals_out[0] = 0;  // accumulated after the last radix pass
+    if (b == 0 && tid == 0) totals_out[0] = totals_out[1] = totals_out[2] = totals_out[3] = 0;  // summed at the end
 
     int n = N;  // items entering the current pass
     for (int pass = 0; pass < DS_PASSES; ++pass) {
@@ -132,7 +132,10 @@ k_depth_sort_coop(const uint32_t *__restrict__ keys_in, const int32_t *__restric
                 ex += loc[k];
             }
             if (pass == 0) {
-                if (b == 0 && tid == 0) *nvis_out = tot;
+                if (b == 0 && tid == 0) {
+                    *nvis_out = tot;
+                    totals_out[4] = tot;
+                }
                 n = tot;  // later passes (and their slices) only see the visible Gaussians
             }
         }
@@ -190,74 +193,37 @@ k_depth_sort_coop(const uint32_t *__restrict__ keys_in, const int32_t *__restric
         grid.sync();
     }
 
-    // ---- exclusive scan of the rectangle heights (= tile-row hits) in depth order over the same grid, and the
-    // totals M (tile intersections) and S (tile-row hits)
+    // ---- totals over the visible Gaussians (sizes of the tile-list hierarchy, tilelists.cu): M = tile
+    // intersections, S = tile-row hits, E1 = row-group hits, E3 = (row, column-group) hits
     const uint32_t *order = vB;
     const int per = (n + G - 1) / G;
     const int begin = min(n, b * per), end = min(n, begin + per);
-    {
-        int sum = 0;
-        long long m = 0;
-        for (int i = begin + tid; i < end; i += DS_THREADS) {
-            const int g = (int)order[i];
-            m += tiles_per_gauss[g];
-            const int ry = rects[g].y;
-            sum += max(0, ((ry >> 16) & 0xffff) - (ry & 0xffff));
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
-        if (lane == 0 && m) atomicAdd(reinterpret_cast<unsigned long long *>(totals_out), (unsigned long long)m);
-        int tot;
-        ds_block_excl_scan(sum, &tot, s_w);
-        if (tid == 0) blk_sums[b] = tot;
+    long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+    for (int i = begin + tid; i < end; i += DS_THREADS) {
+        const int g = (int)order[i];
+        const int2 rc = rects[g];
+        const int x0 = rc.x & 0xffff, x1 = (rc.x >> 16) & 0xffff, y0 = rc.y & 0xffff, y1 = (rc.y >> 16) & 0xffff;
+        const int h = max(0, y1 - y0), w = max(0, x1 - x0);
+        const int rgc = h > 0 ? ((y1 - 1) >> rg_shift) - (y0 >> rg_shift) + 1 : 0;
+        const int cgc = w > 0 ? ((x1 - 1) >> cg_shift) - (x0 >> cg_shift) + 1 : 0;
+        t0 += tiles_per_gauss[g];
+        t1 += h;
+        t2 += rgc;
+        t3 += (long long)h * cgc;
     }
-    grid.sync();
-    long long base = 0, all = 0;
-    {
-        long long mine = 0, tot_all = 0;
-        for (int x = tid; x < G; x += DS_THREADS) {
-            const int v = blk_sums[x];
-            tot_all += v;
-            if (x < b) mine += v;
-        }
-        // block reduce of two 64-bit sums through shared memory
-        long long *s_ll = reinterpret_cast<long long *>(s_cnt);
-        s_ll[tid] = mine;
-        s_ll[DS_THREADS + tid] = tot_all;
-        __syncthreads();
-        for (int o = DS_THREADS / 2; o > 0; o >>= 1) {
-            if (tid < o) {
-                s_ll[tid] += s_ll[tid + o];
-                s_ll[DS_THREADS + tid] += s_ll[DS_THREADS + tid + o];
-            }
-            __syncthreads();
-        }
-        base = s_ll[0];
-        all = s_ll[DS_THREADS];
-        __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+        t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+        t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+        t3 += __shfl_xor_sync(0xffffffffu, t3, o);
     }
-    if (b == 0 && tid == 0) totals_out[1] = all;
-    int running = (int)base;
-    for (int sub = begin; sub < end; sub += DS_THREADS * 8) {
-        const int i0 = sub + tid * 8;  // thread-contiguous so the serial part is in memory order
-        int v[8], sum = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            v[k] = 0;
-            if (i0 + k < end) {
-                const int ry = rects[order[i0 + k]].y;
-                v[k] = max(0, ((ry >> 16) & 0xffff) - (ry & 0xffff));
-            }
-            sum += v[k];
-        }
-        int tot;
-        int ex = ds_block_excl_scan(sum, &tot, s_w) + running;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (i0 + k < end) cum_rows[i0 + k] = ex;
-            ex += v[k];
-        }
-        running += tot;
+    if (lane == 0 && t1 > 0) {
+        unsigned long long *t = reinterpret_cast<unsigned long long *>(totals_out);
+        atomicAdd(t + 0, (unsigned long long)t0);
+        atomicAdd(t + 1, (unsigned long long)t1);
+        atomicAdd(t + 2, (unsigned long long)t2);
+        atomicAdd(t + 3, (unsigned long long)t3);
     }
 }
 
@@ -279,19 +245,20 @@ static int ds_max_grid(int device) {
 
 extern "C" size_t b2s_bin_depth_workspace_bytes(int N) {
     size_t n = (size_t)(N > 0 ? N : 1);
-    // kA, vA, kB + table [BINS][G<=2048] + digit totals + block sums
-    return 3 * ds_align256(n * 4) + ds_align256((size_t)DS_BINS * 2048 * 4) + ds_align256(DS_BINS * 4) +
-           ds_align256(2048 * 4) + 1024;
+    // kA, vA, kB + table [BINS][G<=2048] + digit totals
+    return 3 * ds_align256(n * 4) + ds_align256((size_t)DS_BINS * 2048 * 4) + ds_align256(DS_BINS * 4) + 1024;
 }
 
 extern "C" int b2s_bin_sort_depth(const uint32_t *sort_keys, const int32_t *tiles_per_gauss, const int32_t *tile_rects,
-                                  int N, int32_t *order, int32_t *cum_rows, int64_t *totals, int32_t *n_vis,
+                                  int N, int tile_w, int tile_h, int32_t *order, int64_t *totals, int32_t *n_vis,
                                   void *workspace, size_t workspace_bytes, b2s_stream_t stream) {
     if (N < 0) return B2S_ERR_ARG;
+    int rg_shift = 0, cg_shift = 0;
+    if (b2s_tl_shifts(tile_w, tile_h, &rg_shift, &cg_shift) != B2S_OK) return B2S_ERR_UNSUPPORTED;
     if (workspace_bytes < b2s_bin_depth_workspace_bytes(N)) return B2S_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     if (N == 0) {
-        cudaMemsetAsync(totals, 0, 2 * sizeof(int64_t), st);
+        cudaMemsetAsync(totals, 0, 5 * sizeof(int64_t), st);
         cudaMemsetAsync(n_vis, 0, sizeof(int32_t), st);
         return B2S_OK;
     }
@@ -307,13 +274,12 @@ extern "C" int b2s_bin_sort_depth(const uint32_t *sort_keys, const int32_t *tile
     uint32_t *vA = (uint32_t *)w; w += n4;
     uint32_t *kB = (uint32_t *)w; w += n4;
     int32_t *table = (int32_t *)w; w += ds_align256((size_t)DS_BINS * 2048 * 4);
-    int32_t *digit_tot = (int32_t *)w; w += ds_align256(DS_BINS * 4);
-    int32_t *blk_sums = (int32_t *)w;
+    int32_t *digit_tot = (int32_t *)w;
     uint32_t *vB = (uint32_t *)order;
     const int2 *rects = (const int2 *)tile_rects;
-    void *args[] = {(void *)&sort_keys, (void *)&tiles_per_gauss, (void *)&N,         (void *)&kA,
-                    (void *)&vA,        (void *)&kB,              (void *)&vB,        (void *)&table,
-                    (void *)&digit_tot, (void *)&blk_sums,        (void *)&rects,     (void *)&cum_rows,
+    void *args[] = {(void *)&sort_keys, (void *)&tiles_per_gauss, (void *)&N,        (void *)&kA,
+                    (void *)&vA,        (void *)&kB,              (void *)&vB,       (void *)&table,
+                    (void *)&digit_tot, (void *)&rects,           (void *)&rg_shift, (void *)&cg_shift,
                     (void *)&totals,    (void *)&n_vis};
     cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_depth_sort_coop, dim3(G), dim3(DS_THREADS), args,
                                                 DS_SMEM, st);

@@ -6,28 +6,58 @@
 // Input: the Gaussians in stable depth order (order[], from b2s_bin_sort_depth) and each Gaussian's tile
 // rectangle (tile_rects, from the projection kernel).  The (Gaussian x tile) incidence is a sparse matrix given
 // row by row (row = rectangle of one Gaussian); upstream's sorted list is its column-major transpose with the
-// rows kept in order.  It is built by two order-preserving "interval multisplits", each perfectly load balanced:
-//   stage 1 (rows):  the depth-ordered stream is cut into chunks of equal WORK (TL_C1 appended hits; one warp
-//                    each); every Gaussian is appended to the list of each tile ROW its rectangle covers, as an
-//                    8-byte hit (gaussian id, x0 | x1 << 16).  S = sum of rectangle heights hits in total.
-//   stage 2 (tiles): every row list is cut into chunks of equal work (~TL_C2 appended entries; one warp each);
-//                    every hit is appended to the list of each TILE of that row in [x0, x1) -> flatten_ids.
-// Both stages are count (difference array in shared memory: 2 atomics per item, independent of its extent) ->
-// exclusive prefix over the chunks -> fill.  The fill never ranks or sorts: a warp takes 32 items, every lane ORs
-// its lane bit into the shared-memory word of each bin its interval covers (transposing the 32 x bins incidence),
-// then lane l OWNS bins l, l+32, ... with their list cursors in registers and appends the items of its words in
-// bit order.  Items are visited in stream order, so every list is in depth order (ties: ascending id): bit-identical
-// to the stable global sort, with M x 4 B written exactly once and no atomics on global memory.
-// Chunks are cut by appended entries, not by items or image area, so neither tile rows near the horizon (several
-// times the mean load) nor screen-filling Gaussians close to the camera (hundreds of tiles each, all at the front
-// of every list) unbalance the warps.  Integer work; no tensor cores.
+// rows kept in order.  It is built by a hierarchy of ORDER-PRESERVING FILTERS, each splitting every list of the
+// previous level into <= 16 (32 for very large images) child lists:
+//     level 1  depth-ordered Gaussians        -> row groups  (8 or 16 tile rows)
+//     level 2  row-group lists                -> tile rows
+//     level 3  tile-row lists                 -> column groups (16 tile columns)
+//     level 4  (row, column-group) lists      -> tiles  = flatten_ids, isect_offsets
+// A level is three launches: count (per 1024/2048-item chunk and child), prefix (over the chunks of a list; the last
+// CTA turns the child lengths into child offsets and into the chunk table of the next level) and fill.  Count and
+// fill walk a chunk 32 items at a time; for every child b the warp ballots "item covers b" and the covering lanes
+// write their payload at cursor_b + (rank among the set lanes): stream order is preserved (depth order, ties by
+// ascending id: bit-identical to the stable global sort), every store instruction writes one contiguous run, and
+// the work per chunk does not depend on how large the Gaussians are -- a 4-byte scatter of the M entries by
+// "tile-owner lanes" (the previous design) spent its time in the SM's store-address path (lg/mio-throttle stalls,
+// ~2.5 cycles per entry).  Cost ~ sum over levels of items x children / 32 ballots instead of M scattered stores.
+// Integer work; no tensor cores.
 #include <cstdlib>
 
 #include "common.cuh"
 
-constexpr int TL_C1 = 1024;     // tile-row hits appended per stage-1 chunk (one warp)
-constexpr int TL_C2 = 2048;     // tile-list entries appended per stage-2 chunk (one warp)
-constexpr int TL_WARPS = 2;     // warps (= chunks) per CTA: small CTAs so that every chunk is resident at once
+constexpr int TL_WARPS = 8;   // warps per CTA; a CTA owns one chunk, warp w the w-th slice of it
+// items per chunk at level K = TL_WARPS slices of 128 (levels 1-2) or 256 (levels 3-4) items: short slices = many
+// warps in flight (a warp is a serial chain of dependent loads and the early levels have few items), CTA-sized
+// chunks = short per-list chunk tables (the prefix over a list's chunks is a serial dependency)
+template <int K> struct TlCh {
+    static constexpr int slice = K <= 2 ? 128 : 256;
+    static constexpr int v = slice * TL_WARPS;
+};
+static inline int tl_ch(int k) { return (k <= 2 ? 128 : 256) * TL_WARPS; }
+
+struct TlGeom {
+    int tile_w, tile_h;
+    int rg_shift, cg_shift;  // tile rows per row group = 1 << rg_shift, tile columns per column group = 1 << cg_shift
+    int nrg, ncg;            // number of row groups / column groups (<= 32)
+};
+
+// smallest shift >= lo with ceil(n / 2^shift) <= 16 (<= 32 at the largest shift); -1 if the grid is too large
+static inline int tl_shift(int n, int lo) {
+    for (int s = lo; s <= 5; ++s)
+        if (((n + (1 << s) - 1) >> s) <= 16) return s;
+    return ((n + 31) >> 5) <= 32 ? 5 : -1;
+}
+static inline bool tl_geom(int tile_w, int tile_h, TlGeom &g) {
+    if (tile_w <= 0 || tile_h <= 0) return false;
+    g.tile_w = tile_w;
+    g.tile_h = tile_h;
+    g.rg_shift = tl_shift(tile_h, 3);
+    g.cg_shift = tl_shift(tile_w, 4);
+    if (g.rg_shift < 0 || g.cg_shift < 0) return false;
+    g.nrg = (tile_h + (1 << g.rg_shift) - 1) >> g.rg_shift;
+    g.ncg = (tile_w + (1 << g.cg_shift) - 1) >> g.cg_shift;
+    return true;
+}
 
 __device__ __forceinline__ int tl_warp_incl_scan(int v, int lane) {
 #pragma unroll
@@ -38,388 +68,282 @@ __device__ __forceinline__ int tl_warp_incl_scan(int v, int lane) {
     return v;
 }
 
-// ---- interval counting: one warp, items [begin, end), interval of item i over bins = iv(i) -> (lo, hi).
-// s_d: nbins + 1 ints of this warp's shared memory.  Afterwards lane-strided s_d[b] = number of items covering bin b.
-template <class IV>
-__device__ __forceinline__ void tl_warp_count(int *s_d, int nbins, int begin, int end, int lane, IV iv) {
-    for (int b = lane; b <= nbins; b += 32) s_d[b] = 0;
-    __syncwarp();
-    for (int i = begin + lane; i < end; i += 32) {
-        int lo, hi;
-        iv(i, lo, hi);
-        if (hi > lo) {
-            atomicAdd(&s_d[lo], 1);
-            atomicAdd(&s_d[hi], -1);
-        }
-    }
-    __syncwarp();
-    int carry = 0;
-    for (int b0 = 0; b0 < nbins; b0 += 32) {
-        const int v = (b0 + lane < nbins) ? s_d[b0 + lane] : 0;
-        const int incl = tl_warp_incl_scan(v, lane) + carry;
-        if (b0 + lane < nbins) s_d[b0 + lane] = incl;
-        carry = __shfl_sync(0xffffffffu, incl, 31);
-    }
-    __syncwarp();
+// children per list and geometry of level K
+template <int K>
+__device__ __forceinline__ int tl_nb(const TlGeom &g) {
+    return K == 1 ? g.nrg : K == 2 ? (1 << g.rg_shift) : K == 3 ? g.ncg : (1 << g.cg_shift);
 }
-
-// ---- ordered fill: one warp, items [begin, end) in stream order.  fetch(i) loads the raw item i and
-// decode(item, lo, hi, payload) turns it into its bin interval and payload; cursor0(bin) is the output index of
-// the first item this chunk appends to `bin`; out receives the payloads.
-// s_words: 32 * NG ints, s_pay: 32 payloads (this warp's shared memory).  NG = bins owned per lane (32 * NG bins
-// per pass over the chunk; more bins: more passes).  The next batch's raw items are fetched while the current one
-// is expanded (decoded only when needed, so the load latency is hidden), and the expansion is a warp-convergent,
-// branch-free loop in which a lane pops one bit from each of its NG words per round (NG independent
-// shared-load -> predicated-store chains).
-template <class PAY, int NG, class ITEM, class FETCH, class DECODE, class CUR>
-__device__ __forceinline__ void tl_warp_fill(unsigned *s_words, PAY *s_pay, int nbins, int begin, int end, int lane,
-                                             FETCH fetch, DECODE decode, CUR cursor0, PAY *__restrict__ out) {
-    constexpr int BAND = 32 * NG;
-    for (int band = 0; band < nbins; band += BAND) {  // one pass unless there are more than 32 * NG bins
-        PAY *cur[NG];
-#pragma unroll
-        for (int k = 0; k < NG; ++k) {
-            const int b = band + lane + 32 * k;
-            cur[k] = out + (b < nbins ? cursor0(b) : 0);
-        }
-        ITEM nxt = ITEM();
-        bool nvalid = begin + lane < end;
-        if (nvalid) nxt = fetch(begin + lane);
-        for (int i0 = begin; i0 < end; i0 += 32) {
-            int lo = 0, hi = 0;
-            PAY pay = PAY();
-            if (nvalid) decode(nxt, lo, hi, pay);
-            lo = max(lo - band, 0);
-            hi = min(hi - band, BAND);
-            s_pay[lane] = pay;
-#pragma unroll
-            for (int k = 0; k < NG; ++k) s_words[lane + 32 * k] = 0u;
-            nvalid = i0 + 32 + lane < end;
-            if (nvalid) nxt = fetch(i0 + 32 + lane);  // prefetch the next batch (raw; decoded next round)
-            __syncwarp();
-            for (int b = lo; b < hi; ++b) atomicOr(&s_words[b], 1u << lane);
-            __syncwarp();
-            unsigned w[NG];
-            unsigned any = 0u;
-#pragma unroll
-            for (int k = 0; k < NG; ++k) {
-                w[k] = s_words[lane + 32 * k];
-                any |= w[k];
-            }
-            while (__any_sync(0xffffffffu, any != 0u)) {
-                PAY v[NG];
-#pragma unroll
-                for (int k = 0; k < NG; ++k) v[k] = s_pay[(__ffs(w[k]) - 1) & 31];
-                any = 0u;
-#pragma unroll
-                for (int k = 0; k < NG; ++k) {
-                    if (w[k]) *cur[k] = v[k];
-                    cur[k] += w[k] ? 1 : 0;
-                    w[k] &= w[k] - 1;  // 0 stays 0
-                    any |= w[k];
-                }
-            }
-            __syncwarp();
-        }
+// children [lo, hi) of list L covered by an item whose packed range (lo | hi << 16 along the level's axis) is r
+template <int K>
+__device__ __forceinline__ void tl_bins(int r, int L, const TlGeom &g, int &lo, int &hi) {
+    const int a = r & 0xffff, b = (r >> 16) & 0xffff;
+    if (K == 1) {
+        lo = a >> g.rg_shift;
+        hi = b > a ? ((b - 1) >> g.rg_shift) + 1 : lo;
+    } else if (K == 2) {
+        const int base = L << g.rg_shift;
+        lo = max(a - base, 0);
+        hi = min(b - base, 1 << g.rg_shift);
+    } else if (K == 3) {
+        lo = a >> g.cg_shift;
+        hi = b > a ? ((b - 1) >> g.cg_shift) + 1 : lo;
+    } else {
+        const int base = (L % g.ncg) << g.cg_shift;
+        lo = max(a - base, 0);
+        hi = min(b - base, 1 << g.cg_shift);
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// stage 1: rows.  Chunk c = the Gaussians whose exclusive row-hit prefix cum_rows[i] lies in
-// [c * TL_C1, (c + 1) * TL_C1): equal WORK (appends) per warp, whatever the sizes of the Gaussians.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_bounds1(const int32_t *__restrict__ cum_rows, const int32_t *__restrict__ n_vis, int nc1,
-          int32_t *__restrict__ bounds1 /* [nc1 + 1] */) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c > nc1) return;
-    const int nv = *n_vis;
-    int lo = 0, hi = nv;  // first i with cum_rows[i] >= c * TL_C1
-    if (c == nc1) lo = nv;
-    const long long target = (long long)c * TL_C1;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (cum_rows[mid] < target) lo = mid + 1;
-        else hi = mid;
+// chunk c of level K -> list L and item range [begin, end)
+template <int K>
+__device__ __forceinline__ bool tl_chunk(int c, int nlists, const int32_t *__restrict__ list_off,
+                                         const int32_t *__restrict__ chunk_off, const int32_t *__restrict__ n_vis,
+                                         int &L, int &begin, int &end) {
+    if (K == 1) {  // one list: the depth-ordered stream
+        const int nv = *n_vis;
+        L = 0;
+        begin = c * TlCh<K>::v;
+        end = min(nv, begin + TlCh<K>::v);
+        return begin < nv;
     }
-    bounds1[c] = lo;
-}
-
-// count1[y * nc1s + c] = Gaussians of chunk c covering tile row y; count1w[..] = tiles of row y they cover
-__global__ void __launch_bounds__(32 * TL_WARPS)
-k_rows_count(const int2 *__restrict__ rects, const int32_t *__restrict__ order, const int32_t *__restrict__ bounds1,
-             int nc1, int tile_w, int tile_h, int nc1s, int32_t *__restrict__ count1, int32_t *__restrict__ count1w) {
-    extern __shared__ int s_dyn[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = blockIdx.x * TL_WARPS + warp;
-    if (c >= nc1) return;
-    const int begin = bounds1[c], end = bounds1[c + 1];
-    int *s_d = s_dyn + warp * 2 * (tile_h + 1);
-    int *s_w = s_d + tile_h + 1;
-    for (int b = lane; b <= tile_h; b += 32) s_d[b] = s_w[b] = 0;
-    __syncwarp();
-    for (int i = begin + lane; i < end; i += 32) {
-        const int2 rc = rects[order[i]];
-        const int lo = rc.y & 0xffff, hi = min((rc.y >> 16) & 0xffff, tile_h);
-        const int wd = max(0, min((rc.x >> 16) & 0xffff, tile_w) - (rc.x & 0xffff));
-        if (hi > lo) {
-            atomicAdd(&s_d[lo], 1);
-            atomicAdd(&s_d[hi], -1);
-            atomicAdd(&s_w[lo], wd);
-            atomicAdd(&s_w[hi], -wd);
-        }
-    }
-    __syncwarp();
-    int carry = 0, carry_w = 0;
-    for (int b0 = 0; b0 < tile_h; b0 += 32) {
-        const int y = b0 + lane;
-        const int v = y < tile_h ? s_d[y] : 0, vw = y < tile_h ? s_w[y] : 0;
-        const int incl = tl_warp_incl_scan(v, lane) + carry, incl_w = tl_warp_incl_scan(vw, lane) + carry_w;
-        if (y < tile_h) {
-            count1[(size_t)y * nc1s + c] = incl;
-            count1w[(size_t)y * nc1s + c] = incl_w;
-        }
-        carry = __shfl_sync(0xffffffffu, incl, 31);
-        carry_w = __shfl_sync(0xffffffffu, incl_w, 31);
-    }
-}
-
-// CTA (y, which): in-place exclusive scan over the chunks of count1[y][.] (which = 0; total -> row_len[y]) or
-// count1w[y][.] (which = 1; total -> row_app[y])
-__global__ void __launch_bounds__(256)
-k_rows_prefix(int32_t *__restrict__ count1, int32_t *__restrict__ count1w, int nc1, int nc1s,
-              int32_t *__restrict__ row_len, int32_t *__restrict__ row_app) {
-    __shared__ int s_w[9];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int32_t *r = (blockIdx.y ? count1w : count1) + (size_t)blockIdx.x * nc1s;
-    const int per = (nc1 + 255) / 256;
-    const int b = min(nc1, tid * per), e = min(nc1, b + per);
-    int sum = 0;
-    for (int i = b; i < e; ++i) sum += r[i];
-    const int incl = tl_warp_incl_scan(sum, lane);
-    if (lane == 31) s_w[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        const int w = lane < 8 ? s_w[lane] : 0;
-        const int wi = tl_warp_incl_scan(w, lane);
-        if (lane < 8) s_w[lane] = wi - w;
-        if (lane == 7) s_w[8] = wi;
-    }
-    __syncthreads();
-    int run = s_w[warp] + incl - sum;
-    for (int i = b; i < e; ++i) {
-        const int v = r[i];
-        r[i] = run;
-        run += v;
-    }
-    if (tid == 0) (blockIdx.y ? row_app : row_len)[blockIdx.x] = s_w[8];
-}
-
-// one warp: row_off = exclusive scan of row_len, chunk_off = exclusive scan of ceil(row_app / TL_C2); entry
-// [tile_h] holds the totals (S and the number of stage-2 chunks).
-__global__ void __launch_bounds__(32)
-k_rows_offsets(const int32_t *__restrict__ row_len, const int32_t *__restrict__ row_app, int tile_h,
-               int32_t *__restrict__ row_off, int32_t *__restrict__ chunk_off) {
-    const int lane = threadIdx.x;
-    int carry_r = 0, carry_c = 0;
-    for (int y0 = 0; y0 < tile_h; y0 += 32) {
-        const int y = y0 + lane;
-        const int len = y < tile_h ? row_len[y] : 0;
-        const int nch = y < tile_h ? (row_app[y] + TL_C2 - 1) / TL_C2 : 0;
-        const int ir = tl_warp_incl_scan(len, lane), ic = tl_warp_incl_scan(nch, lane);
-        if (y < tile_h) {
-            row_off[y] = carry_r + ir - len;
-            chunk_off[y] = carry_c + ic - nch;
-        }
-        carry_r += __shfl_sync(0xffffffffu, ir, 31);
-        carry_c += __shfl_sync(0xffffffffu, ic, 31);
-    }
-    if (lane == 0) {
-        row_off[tile_h] = carry_r;
-        chunk_off[tile_h] = carry_c;
-    }
-}
-
-// row_list[row_off[y] ..) = the Gaussians covering tile row y, in depth order, as (id, x0 | x1 << 16)
-template <int NG>
-__global__ void __launch_bounds__(32 * TL_WARPS)
-k_rows_fill(const int2 *__restrict__ rects, const int32_t *__restrict__ order, const int32_t *__restrict__ bounds1,
-            int nc1, int tile_h, int nc1s, const int32_t *__restrict__ count1,
-            const int32_t *__restrict__ row_off, int2 *__restrict__ row_list) {
-    __shared__ unsigned s_words[TL_WARPS][32 * NG];
-    __shared__ int2 s_pay[TL_WARPS][32];
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = blockIdx.x * TL_WARPS + warp;
-    if (c >= nc1) return;
-    const int begin = bounds1[c], end = bounds1[c + 1];
-    tl_warp_fill<int2, NG, int4>(
-        s_words[warp], s_pay[warp], tile_h, begin, end, lane,
-        [&](int i) {
-            const int g = order[i];
-            const int2 rc = rects[g];
-            return make_int4(g, rc.x, rc.y, 0);
-        },
-        [&](const int4 &it, int &lo, int &hi, int2 &pay) {
-            lo = it.z & 0xffff;
-            hi = min((it.z >> 16) & 0xffff, tile_h);
-            pay = make_int2(it.x, it.y);
-        },
-        [&](int y) { return row_off[y] + count1[(size_t)y * nc1s + c]; }, row_list);
-}
-
-// ------------------------------------------------------------------------------------------------
-// stage 2: tiles.  The list of row y is cut at stage-1 cell boundaries (cell = hits of one stage-1 chunk in
-// row y, a handful of hits) into chunks of ~TL_C2 appends: chunk k of row y = the cells whose exclusive append
-// prefix count1w[y][c] lies in [k * TL_C2, (k + 1) * TL_C2).  bounds2[c2] = (first hit, row) of chunk c2.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_bounds2(const int32_t *__restrict__ count1, const int32_t *__restrict__ count1w, int nc1, int nc1s, int tile_h,
-          const int32_t *__restrict__ row_off, const int32_t *__restrict__ chunk_off, int2 *__restrict__ bounds2) {
-    const int c2 = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c2 >= chunk_off[tile_h]) return;
-    int lo = 0, hi = tile_h;  // last y with chunk_off[y] <= c2
+    if (c >= chunk_off[nlists]) return false;
+    int lo = 0, hi = nlists;  // last L with chunk_off[L] <= c
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
-        if (chunk_off[mid] <= c2) lo = mid;
+        if (chunk_off[mid] <= c) lo = mid;
         else hi = mid;
     }
-    const int y = lo;
-    const long long target = (long long)(c2 - chunk_off[y]) * TL_C2;
-    const int32_t *rw = count1w + (size_t)y * nc1s;
-    int a = 0, b = nc1;  // first cell with append prefix >= target
-    while (a < b) {
-        const int mid = (a + b) >> 1;
-        if (rw[mid] < target) a = mid + 1;
-        else b = mid;
-    }
-    const int first = a < nc1 ? row_off[y] + count1[(size_t)y * nc1s + a] : row_off[y + 1];
-    bounds2[c2] = make_int2(first, y);
-}
-
-__device__ __forceinline__ bool tl_chunk2(int c2, int tile_h, const int32_t *__restrict__ row_off,
-                                          const int32_t *__restrict__ chunk_off, const int2 *__restrict__ bounds2,
-                                          int &y, int &begin, int &end) {
-    if (c2 >= chunk_off[tile_h]) return false;
-    const int2 b = bounds2[c2];
-    y = b.y;
-    begin = b.x;
-    end = (c2 + 1 < chunk_off[y + 1]) ? bounds2[c2 + 1].x : row_off[y + 1];
+    L = lo;
+    begin = list_off[L] + (c - chunk_off[L]) * TlCh<K>::v;
+    end = min(list_off[L + 1], begin + TlCh<K>::v);
     return true;
 }
 
-// table2[c2 * tile_w + x] = number of hits of chunk c2 covering tile x of its row
-__global__ void __launch_bounds__(32 * TL_WARPS)
-k_tiles_count(const int2 *__restrict__ row_list, const int32_t *__restrict__ row_off,
-              const int32_t *__restrict__ chunk_off, const int2 *__restrict__ bounds2, int tile_w, int tile_h,
-              int32_t *__restrict__ table2) {
-    extern __shared__ int s_dyn[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c2 = blockIdx.x * TL_WARPS + warp;
-    int y, begin, end;
-    if (!tl_chunk2(c2, tile_h, row_off, chunk_off, bounds2, y, begin, end)) return;
-    int *s_d = s_dyn + warp * (tile_w + 1);
-    tl_warp_count(s_d, tile_w, begin, end, lane, [&](int i, int &lo, int &hi) {
-        const int rx = row_list[i].y;
-        lo = rx & 0xffff;
-        hi = min((rx >> 16) & 0xffff, tile_w);
-    });
-    for (int x = lane; x < tile_w; x += 32) table2[(size_t)c2 * tile_w + x] = s_d[x];
+// item i of level K as (gaussian id, packed range along the level's axis)
+template <int K>
+__device__ __forceinline__ int2 tl_item(int i, const int2 *__restrict__ in, const int32_t *__restrict__ order,
+                                        const int2 *__restrict__ rects) {
+    if (K == 1) {
+        const int g = order[i];
+        return make_int2(g, rects[g].y);
+    }
+    return in[i];
 }
 
-// CTA = (tile row y, 32 consecutive tiles of it); 8 warps split the row's chunks.  In-place exclusive prefix of
-// table2[.][x] over the chunks of row y, and the tile's total.
-__global__ void __launch_bounds__(256)
-k_tiles_prefix(int32_t *__restrict__ table2, const int32_t *__restrict__ chunk_off, int tile_w,
-               int32_t *__restrict__ tile_total) {
-    __shared__ int s_part[8][32];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int y = blockIdx.y;
-    const int x = blockIdx.x * 32 + lane;
-    const int c0 = chunk_off[y], nc = chunk_off[y + 1] - c0;
-    const int r0 = c0 + (int)((long long)w * nc / 8), r1 = c0 + (int)((long long)(w + 1) * nc / 8);
-    int sum = 0;
-    if (x < tile_w) {
-#pragma unroll 4
-        for (int r = r0; r < r1; ++r) sum += table2[(size_t)r * tile_w + x];
+// children-per-slice counting shared by count and fill: lane b of warp w ends with the number of items of slice w
+// of the chunk [begin, end) that cover child b
+template <int K>
+__device__ __forceinline__ int tl_slice_count(const TlGeom &g, int NB, int L, int sb, int se, int lane,
+                                              const int2 *__restrict__ in, const int32_t *__restrict__ order,
+                                              const int2 *__restrict__ rects) {
+    int cnt = 0;
+    int2 nxt = make_int2(0, 0);
+    if (sb + lane < se) nxt = tl_item<K>(sb + lane, in, order, rects);
+    for (int i0 = sb; i0 < se; i0 += 32) {
+        int lo = 0, hi = 0;
+        if (i0 + lane < se) tl_bins<K>(nxt.y, L, g, lo, hi);
+        if (i0 + 32 + lane < se) nxt = tl_item<K>(i0 + 32 + lane, in, order, rects);  // prefetch
+        for (int b = 0; b < NB; ++b) {
+            const unsigned bal = __ballot_sync(0xffffffffu, lo <= b && b < hi);
+            if (lane == b) cnt += __popc(bal);
+        }
     }
-    s_part[w][lane] = sum;
+    return cnt;
+}
+
+// ---- count: table[b * nch + c] = items of chunk c covering child b
+template <int K>
+__global__ void __launch_bounds__(32 * TL_WARPS)
+k_level_count(const TlGeom g, const int2 *__restrict__ in, const int32_t *__restrict__ order,
+              const int2 *__restrict__ rects, const int32_t *__restrict__ n_vis, int nlists,
+              const int32_t *__restrict__ list_off, const int32_t *__restrict__ chunk_off, int nch,
+              int32_t *__restrict__ table, int32_t *__restrict__ slice_cnt /* [nch][TL_WARPS][32] */,
+              unsigned *__restrict__ ticket) {
+    __shared__ int s_cnt[TL_WARPS][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *ticket = 0u;  // armed for this level's prefix kernel
+    const int c = blockIdx.x;
+    int L, begin, end;
+    if (!tl_chunk<K>(c, nlists, list_off, chunk_off, n_vis, L, begin, end)) return;  // CTA-uniform
+    const int NB = tl_nb<K>(g);
+    const int sb = min(end, begin + warp * TlCh<K>::slice), se = min(end, sb + TlCh<K>::slice);
+    const int mine = tl_slice_count<K>(g, NB, L, sb, se, lane, in, order, rects);
+    s_cnt[warp][lane] = mine;
     __syncthreads();
-    int run = 0, tot = 0;
+    // exclusive prefix over the slices (read back by the fill kernel) and the chunk's total
+    int pre = 0, tot = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int v = s_part[k][lane];
-        run += (k < w) ? v : 0;
+    for (int w = 0; w < TL_WARPS; ++w) {
+        const int v = s_cnt[w][lane];
+        pre += (w < warp) ? v : 0;
         tot += v;
     }
-    if (x < tile_w) {
-        if (w == 0) tile_total[y * tile_w + x] = tot;
-        for (int r = r0; r < r1; ++r) {
-            const size_t a = (size_t)r * tile_w + x;
-            const int v = table2[a];
-            table2[a] = run;
-            run += v;
-        }
-    }
+    slice_cnt[((size_t)c * TL_WARPS + warp) * 32 + lane] = pre;
+    if (warp == 0 && lane < NB) table[(size_t)lane * nch + c] = tot;
 }
 
-// single CTA: isect_offsets = exclusive scan of tile_total (T = 8160 at 1080p, 32400 at 4K)
-__global__ void __launch_bounds__(1024)
-k_tiles_offsets(const int32_t *__restrict__ tile_total, int T, int32_t *__restrict__ offsets) {
-    __shared__ int s_w[33];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int carry = 0;
-    for (int base = 0; base < T; base += 1024 * 8) {
-        const int i0 = base + tid * 8;
-        int v[8], sum = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            v[k] = (i0 + k < T) ? tile_total[i0 + k] : 0;
-            sum += v[k];
-        }
-        const int incl = tl_warp_incl_scan(sum, lane);
-        if (lane == 31) s_w[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            const int wv = s_w[lane];
-            const int wi = tl_warp_incl_scan(wv, lane);
-            s_w[lane] = wi - wv;
-            if (lane == 31) s_w[32] = wi;
-        }
-        __syncthreads();
-        int ex = carry + s_w[warp] + incl - sum;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (i0 + k < T) offsets[i0 + k] = ex;
-            ex += v[k];
-        }
-        carry += s_w[32];
-        __syncthreads();
-    }
-}
+// ---- prefix: one CTA per child list (L, b): in-place exclusive scan of table[., b] over the chunks of L and the
+// child's length; the last CTA to finish then builds the child offsets and (levels 1-3) the next level's chunk
+// table, or (level 4) isect_offsets.
+constexpr int TL_PT = 128;  // threads of a prefix CTA
 
-// flatten_ids[isect_offsets[t] ..) = the Gaussians intersecting tile t, in depth order
-template <int NG>
-__global__ void __launch_bounds__(32 * TL_WARPS)
-k_tiles_fill(const int2 *__restrict__ row_list, const int32_t *__restrict__ row_off,
-             const int32_t *__restrict__ chunk_off, const int2 *__restrict__ bounds2, int tile_w, int tile_h,
-             const int32_t *__restrict__ table2, const int32_t *__restrict__ offsets,
-             int32_t *__restrict__ flatten_ids) {
-    __shared__ unsigned s_words[TL_WARPS][32 * NG];
-    __shared__ int s_pay[TL_WARPS][32];
-
+__device__ __forceinline__ int tl_block_excl_scan(int v, int &total, int *s_w /* TL_PT / 32 */) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c2 = blockIdx.x * TL_WARPS + warp;
-    int y, begin, end;
-    if (!tl_chunk2(c2, tile_h, row_off, chunk_off, bounds2, y, begin, end)) return;
-    tl_warp_fill<int, NG, int2>(
-        s_words[warp], s_pay[warp], tile_w, begin, end, lane, [&](int i) { return row_list[i]; },
-        [&](const int2 &h, int &lo, int &hi, int &pay) {
-            lo = h.y & 0xffff;
-            hi = min((h.y >> 16) & 0xffff, tile_w);
-            pay = h.x;
-        },
-        [&](int x) { return offsets[y * tile_w + x] + table2[(size_t)c2 * tile_w + x]; }, flatten_ids);
+    const int incl = tl_warp_incl_scan(v, lane);
+    __syncthreads();
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    int pre = 0;
+    total = 0;
+#pragma unroll
+    for (int w = 0; w < TL_PT / 32; ++w) {
+        const int x = s_w[w];
+        pre += (w < warp) ? x : 0;
+        total += x;
+    }
+    return pre + incl - v;
+}
+
+template <int K>
+__global__ void __launch_bounds__(TL_PT)
+k_level_prefix(const TlGeom g, const int32_t *__restrict__ n_vis, int nlists, const int32_t *__restrict__ chunk_off,
+               int nch, int32_t *__restrict__ table, int32_t *__restrict__ out_len, int32_t *__restrict__ out_off,
+               int32_t *__restrict__ out_chunk_off, int32_t *__restrict__ isect_offsets,
+               unsigned *__restrict__ ticket) {
+    __shared__ int s_w[TL_PT / 32];
+    __shared__ unsigned s_last;
+    const int tid = threadIdx.x;
+    const int NB = tl_nb<K>(g);
+    const int nout = nlists * NB;
+    if (K >= 3) {  // short chunk tables: one warp per child list
+        const int lane = tid & 31;
+        const int o = blockIdx.x * (TL_PT / 32) + (tid >> 5);
+        if (o < nout) {
+            const int L = o / NB, b = o - L * NB;
+            const int c0 = chunk_off[L], c1 = chunk_off[L + 1];
+            int32_t *row = table + (size_t)b * nch;
+            int carry = 0;
+            for (int c = c0; c < c1; c += 32) {
+                const bool ok = c + lane < c1;
+                const int v = ok ? row[c + lane] : 0;
+                const int incl = tl_warp_incl_scan(v, lane);
+                if (ok) row[c + lane] = carry + incl - v;
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) out_len[o] = carry;
+        }
+    } else {
+        const int o = blockIdx.x;  // child list index L * NB + b
+        const int L = o / NB, b = o - L * NB;
+        int c0, c1;
+        if (K == 1) {
+            c0 = 0;
+            c1 = (*n_vis + TlCh<K>::v - 1) / TlCh<K>::v;
+        } else {
+            c0 = chunk_off[L];
+            c1 = chunk_off[L + 1];
+        }
+        int32_t *row = table + (size_t)b * nch;  // this child's counts, contiguous over the chunks
+        int carry = 0;
+        for (int c = c0; c < c1; c += TL_PT) {
+            const bool ok = c + tid < c1;
+            const int v = ok ? row[c + tid] : 0;
+            int total;
+            const int ex = tl_block_excl_scan(v, total, s_w);
+            if (ok) row[c + tid] = carry + ex;
+            carry += total;
+        }
+        if (tid == 0) out_len[o] = carry;
+    }
+    // last CTA: exclusive scans over all child lists (16 consecutive entries per thread and round)
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    constexpr int IPT = 16;
+    constexpr int CHN = TlCh<(K < 4 ? K + 1 : 4)>::v;  // chunk size of the level that consumes the children
+    int carry_e = 0, carry_c = 0;
+    for (int base = 0; base < nout; base += TL_PT * IPT) {
+        const int i0 = base + tid * IPT;
+        int len[IPT], se = 0, sc = 0;
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+            len[k] = i0 + k < nout ? out_len[i0 + k] : 0;
+            se += len[k];
+            sc += (len[k] + CHN - 1) / CHN;
+        }
+        int te, tc;
+        int pe = carry_e + tl_block_excl_scan(se, te, s_w);
+        int pc = carry_c + tl_block_excl_scan(sc, tc, s_w);
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+            const int i = i0 + k;
+            if (i < nout) {
+                out_off[i] = pe;
+                if (K < 4) {
+                    out_chunk_off[i] = pc;
+                } else {  // child (L, b) of level 4 is tile (y, x)
+                    const int L = i / NB, b = i - L * NB;
+                    const int y = L / g.ncg, x = ((L % g.ncg) << g.cg_shift) + b;
+                    if (y < g.tile_h && x < g.tile_w) isect_offsets[y * g.tile_w + x] = pe;
+                }
+            }
+            pe += len[k];
+            pc += (len[k] + CHN - 1) / CHN;
+        }
+        carry_e += te;
+        carry_c += tc;
+    }
+    if (tid == 0) {
+        out_off[nout] = carry_e;
+        if (K < 4) out_chunk_off[nout] = carry_c;
+    }
+}
+
+// ---- fill: the items of chunk c are appended, in order, to every child list they cover
+template <int K>
+__global__ void __launch_bounds__(32 * TL_WARPS)
+k_level_fill(const TlGeom g, const int2 *__restrict__ in, const int32_t *__restrict__ order,
+             const int2 *__restrict__ rects, const int32_t *__restrict__ n_vis, int nlists,
+             const int32_t *__restrict__ list_off, const int32_t *__restrict__ chunk_off, int nch,
+             const int32_t *__restrict__ table, const int32_t *__restrict__ slice_cnt,
+             const int32_t *__restrict__ out_off, int2 *__restrict__ out2, int32_t *__restrict__ out1) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = lanemask_lt();
+    const int c = blockIdx.x;
+    int L, begin, end;
+    if (!tl_chunk<K>(c, nlists, list_off, chunk_off, n_vis, L, begin, end)) return;  // CTA-uniform
+    const int NB = tl_nb<K>(g);
+    const int sb = min(end, begin + warp * TlCh<K>::slice), se = min(end, sb + TlCh<K>::slice);
+    // the slices of the chunk are filled concurrently: slice w starts behind what slices 0..w-1 append
+    int cur = 0;  // lane b holds the cursor of child b
+    if (lane < NB)
+        cur = out_off[L * NB + lane] + table[(size_t)lane * nch + c] +
+              slice_cnt[((size_t)c * TL_WARPS + warp) * 32 + lane];
+    int2 nxt = make_int2(0, 0);
+    if (sb + lane < se) nxt = tl_item<K>(sb + lane, in, order, rects);
+    for (int i0 = sb; i0 < se; i0 += 32) {
+        const int2 it = nxt;
+        int lo = 0, hi = 0;
+        if (i0 + lane < se) tl_bins<K>(it.y, L, g, lo, hi);
+        if (i0 + 32 + lane < se) nxt = tl_item<K>(i0 + 32 + lane, in, order, rects);  // prefetch
+        int2 pay = it;
+        if (K == 2 && hi > lo) pay.y = rects[it.x].x;  // rows are resolved: carry the column range from here on
+        for (int b = 0; b < NB; ++b) {
+            const bool hit = lo <= b && b < hi;
+            const unsigned bal = __ballot_sync(0xffffffffu, hit);
+            if (bal == 0u) continue;
+            const int base = __shfl_sync(0xffffffffu, cur, b);
+            if (hit) {
+                const int pos = base + __popc(bal & lt);
+                if (K == 4) out1[pos] = pay.x;
+                else out2[pos] = pay;
+            }
+            if (lane == b) cur += __popc(bal);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -427,105 +351,108 @@ k_tiles_fill(const int2 *__restrict__ row_list, const int32_t *__restrict__ row_
 // ------------------------------------------------------------------------------------------------
 static inline size_t tl_align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-static inline bool tl_supported(int tile_w, int tile_h) {
-    return tile_w > 0 && tile_h > 0 && tile_w <= 32767 && tile_h <= 32767;
-}
-
 struct TlLayout {
-    int nc1;         // stage-1 chunks
-    long long nc2s;  // stage-2 chunks (upper bound from M)
-    size_t bounds1, count1, count1w, row_len, row_app, row_off, chunk_off, row_list, bounds2, table2, tile_total, total;
+    int nl[5];         // lists entering level k (k = 1..4)
+    int nb[5];         // children per list at level k
+    long long nch[5];  // chunks at level k (upper bound)
+    size_t table[5], slice[5], out_len[5], out_off[5], chunk_off[5], out[4], ticket, total;
 };
 
-static TlLayout tl_layout(long long M, long long S, int tile_w, int tile_h) {
-    TlLayout L;
-    L.nc1 = (int)(S / TL_C1) + 1;
-    L.nc2s = M / TL_C2 + tile_h;
+// totals = {M, S, E1, E3, n_vis} as written by b2s_bin_sort_depth
+static bool tl_layout(const long long *t, int tile_w, int tile_h, TlGeom &g, TlLayout &L) {
+    if (!tl_geom(tile_w, tile_h, g)) return false;
+    const long long M = t[0], S = t[1], E1 = t[2], E3 = t[3], nv = t[4];
+    const long long in_items[5] = {0, nv, E1, S, E3};
+    const long long out_items[5] = {0, E1, S, E3, M};
+    L.nb[1] = g.nrg; L.nb[2] = 1 << g.rg_shift; L.nb[3] = g.ncg; L.nb[4] = 1 << g.cg_shift;
+    L.nl[1] = 1;
+    for (int k = 2; k <= 4; ++k) L.nl[k] = L.nl[k - 1] * L.nb[k - 1];
     size_t o = 0;
-    L.bounds1 = o; o += tl_align256((size_t)(L.nc1 + 1) * 4);
-    L.count1 = o; o += tl_align256((size_t)tile_h * L.nc1 * 4);
-    L.count1w = o; o += tl_align256((size_t)tile_h * L.nc1 * 4);
-    L.row_len = o; o += tl_align256((size_t)tile_h * 4);
-    L.row_app = o; o += tl_align256((size_t)tile_h * 4);
-    L.row_off = o; o += tl_align256((size_t)(tile_h + 1) * 4);
-    L.chunk_off = o; o += tl_align256((size_t)(tile_h + 1) * 4);
-    L.row_list = o; o += tl_align256((size_t)(S > 0 ? S : 1) * 8);
-    L.bounds2 = o; o += tl_align256((size_t)(L.nc2s + 1) * 8);
-    L.table2 = o; o += tl_align256((size_t)L.nc2s * tile_w * 4);
-    L.tile_total = o; o += tl_align256((size_t)tile_w * tile_h * 4);
+    for (int k = 1; k <= 4; ++k) {
+        L.nch[k] = in_items[k] / tl_ch(k) + L.nl[k];
+        const size_t nout = (size_t)L.nl[k] * L.nb[k];
+        L.table[k] = o; o += tl_align256((size_t)L.nch[k] * L.nb[k] * 4);
+        L.slice[k] = o; o += tl_align256((size_t)L.nch[k] * TL_WARPS * 32 * 4);
+        L.out_len[k] = o; o += tl_align256(nout * 4);
+        L.out_off[k] = o; o += tl_align256((nout + 1) * 4);
+        L.chunk_off[k] = o; o += tl_align256((nout + 1) * 4);  // chunk table of level k + 1
+        if (k < 4) { L.out[k] = o; o += tl_align256((size_t)(out_items[k] > 0 ? out_items[k] : 1) * 8); }
+    }
+    L.ticket = o; o += 256;
     L.total = o + 1024;
-    return L;
+    return true;
 }
 
-extern "C" size_t b2s_bin_tiles_workspace_bytes(int N, long long M, long long S, int tile_w, int tile_h) {
-    (void)N;
-    if (!tl_supported(tile_w, tile_h) || S < 0 || M < 0) return 0;
-    return tl_layout(M, S, tile_w, tile_h).total;
+extern "C" size_t b2s_bin_tiles_workspace_bytes(const long long *totals_host, int tile_w, int tile_h) {
+    TlGeom g;
+    TlLayout L;
+    if (!totals_host || !tl_layout(totals_host, tile_w, tile_h, g, L)) return 0;
+    return L.total;
 }
 
-extern "C" int b2s_bin_tiles(const int32_t *tile_rects, const int32_t *order, const int32_t *cum_rows,
-                             const int32_t *n_vis, int N, long long M, long long S, int tile_size, int tile_w,
-                             int tile_h, int32_t *flatten_ids, int32_t *isect_offsets, void *workspace,
-                             size_t workspace_bytes, b2s_stream_t stream) {
-    if (N < 0 || M < 0 || S < 0 || S >= (1LL << 31) || M >= (1LL << 31) || tile_w <= 0 || tile_h <= 0) return B2S_ERR_ARG;
-    if (tile_size != 16 || !tl_supported(tile_w, tile_h)) return B2S_ERR_UNSUPPORTED;
-    if (workspace_bytes < b2s_bin_tiles_workspace_bytes(N, M, S, tile_w, tile_h)) return B2S_ERR_WORKSPACE;
+template <int K>
+static int tl_run_level(const TlGeom &g, const TlLayout &L, char *w, const int32_t *order, const int2 *rects,
+                        const int32_t *n_vis, int32_t *flatten_ids, int32_t *isect_offsets, cudaStream_t st) {
+    const int2 *in = K == 1 ? nullptr : (const int2 *)(w + L.out[K - 1]);
+    const int32_t *list_off = K == 1 ? nullptr : (const int32_t *)(w + L.out_off[K - 1]);
+    const int32_t *chunk_off = K == 1 ? nullptr : (const int32_t *)(w + L.chunk_off[K - 1]);
+    int32_t *table = (int32_t *)(w + L.table[K]);
+    int32_t *slice_cnt = (int32_t *)(w + L.slice[K]);
+    int32_t *out_len = (int32_t *)(w + L.out_len[K]);
+    int32_t *out_off = (int32_t *)(w + L.out_off[K]);
+    int32_t *out_chunk_off = (int32_t *)(w + L.chunk_off[K]);
+    unsigned *ticket = (unsigned *)(w + L.ticket);
+    int2 *out2 = K < 4 ? (int2 *)(w + L.out[K < 4 ? K : 1]) : nullptr;
+    const int nlists = L.nl[K];
+    const int nch = (int)L.nch[K];
+    k_level_count<K><<<nch, 32 * TL_WARPS, 0, st>>>(g, in, order, rects, n_vis, nlists, list_off, chunk_off, nch, table,
+                                                    slice_cnt, ticket);
+    B2S_LAUNCH_CHECK();
+    const int nout = nlists * L.nb[K];
+    k_level_prefix<K><<<K >= 3 ? b2s_div_up(nout, TL_PT / 32) : nout, TL_PT, 0, st>>>(g, n_vis, nlists, chunk_off, nch, table, out_len, out_off,
+                                                          out_chunk_off, isect_offsets, ticket);
+    B2S_LAUNCH_CHECK();
+    k_level_fill<K><<<nch, 32 * TL_WARPS, 0, st>>>(g, in, order, rects, n_vis, nlists, list_off, chunk_off, nch, table,
+                                                   slice_cnt, out_off, out2, flatten_ids);
+    B2S_LAUNCH_CHECK();
+    return B2S_OK;
+}
+
+extern "C" int b2s_bin_tiles(const int32_t *tile_rects, const int32_t *order, const int32_t *n_vis,
+                             const long long *totals_host, int N, int tile_size, int tile_w, int tile_h,
+                             int32_t *flatten_ids, int32_t *isect_offsets, void *workspace, size_t workspace_bytes,
+                             b2s_stream_t stream) {
+    if (N < 0 || !totals_host || tile_w <= 0 || tile_h <= 0) return B2S_ERR_ARG;
+    const long long M = totals_host[0];
+    for (int k = 0; k < 5; ++k)
+        if (totals_host[k] < 0 || totals_host[k] >= (1LL << 31)) return B2S_ERR_ARG;
+    if (tile_size != 16) return B2S_ERR_UNSUPPORTED;
+    TlGeom g;
+    TlLayout L;
+    if (!tl_layout(totals_host, tile_w, tile_h, g, L)) return B2S_ERR_UNSUPPORTED;
+    if (workspace_bytes < L.total) return B2S_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const int T = tile_w * tile_h;
     if (M == 0 || N == 0) {
         cudaMemsetAsync(isect_offsets, 0, sizeof(int32_t) * (size_t)T, st);
         return B2S_OK;
     }
-    const TlLayout L = tl_layout(M, S, tile_w, tile_h);
     char *w = (char *)workspace;
-    int32_t *bounds1 = (int32_t *)(w + L.bounds1);
-    int32_t *count1 = (int32_t *)(w + L.count1);
-    int32_t *count1w = (int32_t *)(w + L.count1w);
-    int32_t *row_len = (int32_t *)(w + L.row_len);
-    int32_t *row_app = (int32_t *)(w + L.row_app);
-    int32_t *row_off = (int32_t *)(w + L.row_off);
-    int32_t *chunk_off = (int32_t *)(w + L.chunk_off);
-    int2 *row_list = (int2 *)(w + L.row_list);
-    int2 *bounds2 = (int2 *)(w + L.bounds2);
-    int32_t *table2 = (int32_t *)(w + L.table2);
-    int32_t *tile_total = (int32_t *)(w + L.tile_total);
     const int2 *rects = (const int2 *)tile_rects;
+    int rc;
+    if ((rc = tl_run_level<1>(g, L, w, order, rects, n_vis, flatten_ids, isect_offsets, st)) != B2S_OK) return rc;
+    if ((rc = tl_run_level<2>(g, L, w, order, rects, n_vis, flatten_ids, isect_offsets, st)) != B2S_OK) return rc;
+    if ((rc = tl_run_level<3>(g, L, w, order, rects, n_vis, flatten_ids, isect_offsets, st)) != B2S_OK) return rc;
+    if ((rc = tl_run_level<4>(g, L, w, order, rects, n_vis, flatten_ids, isect_offsets, st)) != B2S_OK) return rc;
+    return B2S_OK;
+}
 
-    const int nc1 = L.nc1;
-    const int grid1 = b2s_div_up(nc1, TL_WARPS);
-    const int grid2 = b2s_div_up(L.nc2s, TL_WARPS);
-    const size_t smem1 = (size_t)TL_WARPS * 2 * (tile_h + 1) * sizeof(int);
-    const size_t smem2 = (size_t)TL_WARPS * (tile_w + 1) * sizeof(int);
-    if (smem1 > 48 * 1024 || smem2 > 48 * 1024) return B2S_ERR_UNSUPPORTED;
-    k_bounds1<<<b2s_div_up(nc1 + 1, 256), 256, 0, st>>>(cum_rows, n_vis, nc1, bounds1);
-    B2S_LAUNCH_CHECK();
-    k_rows_count<<<grid1, 32 * TL_WARPS, smem1, st>>>(rects, order, bounds1, nc1, tile_w, tile_h, nc1, count1, count1w);
-    B2S_LAUNCH_CHECK();
-    k_rows_prefix<<<dim3(tile_h, 2), 256, 0, st>>>(count1, count1w, nc1, nc1, row_len, row_app);
-    B2S_LAUNCH_CHECK();
-    k_rows_offsets<<<1, 32, 0, st>>>(row_len, row_app, tile_h, row_off, chunk_off);
-    B2S_LAUNCH_CHECK();
-    // bins owned per lane: 4 (<= 128 tile rows / columns, i.e. <= 2048 px) or 8; larger grids take several passes
-    if (tile_h <= 128)
-        k_rows_fill<4><<<grid1, 32 * TL_WARPS, 0, st>>>(rects, order, bounds1, nc1, tile_h, nc1, count1, row_off, row_list);
-    else
-        k_rows_fill<8><<<grid1, 32 * TL_WARPS, 0, st>>>(rects, order, bounds1, nc1, tile_h, nc1, count1, row_off, row_list);
-    B2S_LAUNCH_CHECK();
-    k_bounds2<<<b2s_div_up(L.nc2s, 256), 256, 0, st>>>(count1, count1w, nc1, nc1, tile_h, row_off, chunk_off, bounds2);
-    B2S_LAUNCH_CHECK();
-    k_tiles_count<<<grid2, 32 * TL_WARPS, smem2, st>>>(row_list, row_off, chunk_off, bounds2, tile_w, tile_h, table2);
-    B2S_LAUNCH_CHECK();
-    k_tiles_prefix<<<dim3(b2s_div_up(tile_w, 32), tile_h), 256, 0, st>>>(table2, chunk_off, tile_w, tile_total);
-    B2S_LAUNCH_CHECK();
-    k_tiles_offsets<<<1, 1024, 0, st>>>(tile_total, T, isect_offsets);
-    B2S_LAUNCH_CHECK();
-    if (tile_w <= 128)
-        k_tiles_fill<4><<<grid2, 32 * TL_WARPS, 0, st>>>(row_list, row_off, chunk_off, bounds2, tile_w, tile_h, table2,
-                                                         isect_offsets, flatten_ids);
-    else
-        k_tiles_fill<8><<<grid2, 32 * TL_WARPS, 0, st>>>(row_list, row_off, chunk_off, bounds2, tile_w, tile_h, table2,
-                                                         isect_offsets, flatten_ids);
-    B2S_LAUNCH_CHECK();
+// Row-group / column-group geometry used by b2s_bin_sort_depth for the E1 / E3 totals (same rule as tl_geom).
+int b2s_tl_shifts(int tile_w, int tile_h, int *rg_shift, int *cg_shift) {
+    TlGeom g;
+    if (!tl_geom(tile_w, tile_h, g)) return B2S_ERR_UNSUPPORTED;
+    *rg_shift = g.rg_shift;
+    *cg_shift = g.cg_shift;
     return B2S_OK;
 }
 

@@ -232,26 +232,26 @@ def _bin(rects: Tensor, tiles: Tensor, keys: Tensor, tile_w: int, tile_h: int) -
     dev = rects.device
     N = tiles.shape[0]
     order = torch.empty(N, dtype=torch.int32, device=dev)
-    cum_rows = torch.empty(N, dtype=torch.int32, device=dev)
-    totals = torch.empty(2, dtype=torch.int64, device=dev)
+    totals = torch.empty(5, dtype=torch.int64, device=dev)
     n_vis = torch.empty(1, dtype=torch.int32, device=dev)
     wsb = int(lib.b2s_bin_depth_workspace_bytes(N))
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     with _timed("bin_sort_depth"):
-        _lib.check(lib.b2s_bin_sort_depth(_ptr(keys), _ptr(tiles), _ptr(rects), N, _ptr(order), _ptr(cum_rows), _ptr(totals),
-                                          _ptr(n_vis), _ptr(ws), wsb, _stream()), "b2s_bin_sort_depth")
-    # the one unavoidable device->host read: M sizes flatten_ids, S (tile-row hits) the tile-list workspace
-    M, S = (int(v) for v in totals.tolist())
+        _lib.check(lib.b2s_bin_sort_depth(_ptr(keys), _ptr(tiles), _ptr(rects), N, tile_w, tile_h, _ptr(order),
+                                          _ptr(totals), _ptr(n_vis), _ptr(ws), wsb, _stream()), "b2s_bin_sort_depth")
+    # the one unavoidable device->host read: M sizes flatten_ids, the other totals the tile-list workspace
+    tot = (C.c_longlong * 5)(*[int(v) for v in totals.tolist()])
+    M = int(tot[0])
     if M >= 2 ** 31:
         raise RuntimeError(f"{M} tile intersections exceed the int32 offset range (same limit as upstream)")
     flatten_ids = torch.empty(M, dtype=torch.int32, device=dev)
     offsets = torch.empty(tile_h, tile_w, dtype=torch.int32, device=dev)
-    wsb2 = int(lib.b2s_bin_tiles_workspace_bytes(N, M, S, tile_w, tile_h))
+    wsb2 = int(lib.b2s_bin_tiles_workspace_bytes(tot, tile_w, tile_h))
     if wsb2 == 0:
         raise NotImplementedError(f"tile grid {tile_w}x{tile_h} not supported")
     ws2 = torch.empty(wsb2, dtype=torch.uint8, device=dev)
     with _timed("bin_tiles"):
-        _lib.check(lib.b2s_bin_tiles(_ptr(rects), _ptr(order), _ptr(cum_rows), _ptr(n_vis), N, M, S, 16, tile_w, tile_h,
+        _lib.check(lib.b2s_bin_tiles(_ptr(rects), _ptr(order), _ptr(n_vis), tot, N, 16, tile_w, tile_h,
                                      _ptr(flatten_ids), _ptr(offsets), _ptr(ws2), wsb2, _stream()),
                    "b2s_bin_tiles")
     return flatten_ids, offsets

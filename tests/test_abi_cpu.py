@@ -111,3 +111,27 @@ def test_scene_generators_are_deterministic():
     d = scenes.street(n=1000, seed=1, camera=1)
     np.testing.assert_array_equal(a["means"], d["means"])
     assert np.abs(a["viewmat"] - d["viewmat"]).max() > 1e-3
+
+
+def test_exchange_shard_layout():
+    """Row ownership of the multi-GPU gradient exchange (pure host arithmetic of the C ABI; no GPU needed):
+    shards are multiples of 256 rows (one projection-backward CTA never straddles two owners) and cover n_shared."""
+    from mtgs_b200 import _lib
+    lib = _lib.load()
+    for n, w in [(0, 1), (1, 1), (255, 2), (256, 2), (257, 2), (2_000_000, 8), (3_000_001, 7), (500_000, 4)]:
+        s = lib.b2s_exchange_shard_rows(n, w)
+        assert s > 0 and s % 256 == 0
+        assert s * w >= n
+        assert (s - 256) * w < max(n, 1) + 256 * w  # not more than one CTA of slack per rank
+    assert lib.b2s_exchange_shard_rows(10, 0) < 0 and lib.b2s_exchange_shard_rows(10, 9) < 0  # world in 1..8
+    assert lib.b2s_exchange_shard_rows(-1, 2) < 0
+
+
+def test_grad_exchange_needs_cuda_and_never_falls_back():
+    import torch
+    from mtgs_b200.parallel import GradExchange, current_exchange
+    assert current_exchange() is None
+    if not torch.cuda.is_available():
+        import pytest
+        with pytest.raises(Exception):
+            GradExchange(n_shared=1024, d_in=3)
