@@ -344,7 +344,7 @@ __device__ __forceinline__ void load_pixel_cotangent(size_t pid, const float *__
 // PX pixels per thread (same column, PX adjacent rows); 256 / PX threads per tile.  PX = 4 halves the number of
 // (warp, Gaussian) reductions and staged-record reads per pixel compared with PX = 2.
 template <int CDIM, int DOUT, bool ED, int PX>
-__global__ void __launch_bounds__(256 / PX)
+__global__ void __launch_bounds__(256 / PX, PX == 4 ? (CDIM == 4 ? 9 : 8) : 1)
 k_blend_bwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, const float4 *__restrict__ colpack,
             const int32_t *__restrict__ offsets, const int32_t *__restrict__ flatten_ids, long long M, int W, int H,
             int tile_w, int tile_h, const float *__restrict__ render, const float *__restrict__ alpha_in,
@@ -560,10 +560,15 @@ static int launch_bwd(const float *means2d, const float *geo, const float *colpa
     // pixels per thread in the backward (see k_blend_bwd); B2S_BWD_PX=2 selects the 128-thread variant (tuning knob)
     static const int px = [] {
         const char *e = getenv("B2S_BWD_PX");
-        return (e && atoi(e) == 2) ? 2 : 4;
+        const int v = e ? atoi(e) : 4;
+        return (v == 2 || v == 8) ? v : 4;
     }();
     if (px == 2)
         k_blend_bwd<CDIM, DOUT, ED, 2><<<tile_w * tile_h, 128, 0, st>>>(
+            (const float2 *)means2d, (const float4 *)geo, (const float4 *)colpack, offsets, flatten_ids, M, W, H, tile_w,
+            tile_h, render, alpha, last_ids, v_render, v_alpha, v_xyabs, v_geo, v_colpack);
+    else if (px == 8)
+        k_blend_bwd<CDIM, DOUT, ED, 8><<<tile_w * tile_h, 32, 0, st>>>(
             (const float2 *)means2d, (const float4 *)geo, (const float4 *)colpack, offsets, flatten_ids, M, W, H, tile_w,
             tile_h, render, alpha, last_ids, v_render, v_alpha, v_xyabs, v_geo, v_colpack);
     else

@@ -286,6 +286,7 @@ k_project_bwd(const float *__restrict__ means, const float *__restrict__ quats, 
             float comp = comps[g];
             float v_comp = v_op_eff * op;
             o_opac = v_op_eff * comp;
+            if (!EXCH) v_opacities[g] = o_opac;
             float det_conic = ia * ic - ib * ib;
             float v_sqr_comp = v_comp * 0.5f / (comp + 1e-6f);
             float one_minus = 1.0f - comp * comp;
@@ -295,6 +296,7 @@ k_project_bwd(const float *__restrict__ means, const float *__restrict__ quats, 
             G[3] += v_sqr_comp * (one_minus * ic - eps2d * det_conic);
         } else {
             o_opac = v_op_eff;
+            if (!EXCH) v_opacities[g] = o_opac;
         }
         float v_depth = with_depth ? v_colpack[(size_t)g * CDIM + d_in] : 0.f;
 
@@ -373,7 +375,10 @@ k_project_bwd(const float *__restrict__ means, const float *__restrict__ quats, 
             for (int j = 0; j < 3; ++j) vR[i * 3 + j] = vpc[i] * p[j];
         }
 #pragma unroll
-        for (int j = 0; j < 3; ++j) o_means[j] = R[0 * 3 + j] * vpc[0] + R[1 * 3 + j] * vpc[1] + R[2 * 3 + j] * vpc[2];
+        for (int j = 0; j < 3; ++j) {
+            o_means[j] = R[0 * 3 + j] * vpc[0] + R[1 * 3 + j] * vpc[1] + R[2 * 3 + j] * vpc[2];
+            if (!EXCH) v_means[3 * g + j] = o_means[j];
+        }
         // v_R += vSc (R Sigma^T) + vSc^T (R Sigma)
         float tmp[9];
         mat3_mul(vSc, RS, tmp);
@@ -400,8 +405,10 @@ k_project_bwd(const float *__restrict__ means, const float *__restrict__ quats, 
 #pragma unroll
             for (int j = 0; j < 3; ++j) Gq[i * 3 + j] = vM[i * 3 + j] * s[j];
 #pragma unroll
-        for (int j = 0; j < 3; ++j)
+        for (int j = 0; j < 3; ++j) {
             o_scales[j] = Rq[0 * 3 + j] * vM[0 * 3 + j] + Rq[1 * 3 + j] * vM[1 * 3 + j] + Rq[2 * 3 + j] * vM[2 * 3 + j];
+            if (!EXCH) v_scales[3 * g + j] = o_scales[j];
+        }
         float vqn[4];
         vqn[0] = 2.f * (qx * (Gq[7] - Gq[5]) + qy * (Gq[2] - Gq[6]) + qz * (Gq[3] - Gq[1]));
         vqn[1] = 2.f * (-2.f * qx * (Gq[4] + Gq[8]) + qy * (Gq[1] + Gq[3]) + qz * (Gq[2] + Gq[6]) + qw * (Gq[7] - Gq[5]));
@@ -412,11 +419,13 @@ k_project_bwd(const float *__restrict__ means, const float *__restrict__ quats, 
                              (vqn[2] - dotp * qy) * inv_norm, (vqn[3] - dotp * qz) * inv_norm);
     }
     if (!EXCH) {
-        if (g < N) {
-            v_means[3 * g] = o_means[0]; v_means[3 * g + 1] = o_means[1]; v_means[3 * g + 2] = o_means[2];
-            v_scales[3 * g] = o_scales[0]; v_scales[3 * g + 1] = o_scales[1]; v_scales[3 * g + 2] = o_scales[2];
+        if (live) {
             v_quats[g] = o_quat;
-            v_opacities[g] = o_opac;
+        } else if (g < N) {  // culled: define the row (zeros) so callers need no memset pass
+            v_means[3 * g] = v_means[3 * g + 1] = v_means[3 * g + 2] = 0.f;
+            v_scales[3 * g] = v_scales[3 * g + 1] = v_scales[3 * g + 2] = 0.f;
+            v_quats[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+            v_opacities[g] = 0.f;
         }
     } else {
         // ---- transpose the CTA's rows through shared memory, then 16-byte coalesced stores into the owner's slot
