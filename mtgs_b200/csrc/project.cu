@@ -88,7 +88,7 @@ __device__ __forceinline__ void covar_cam_rn(const float *R, const float *Rq, fl
 }
 
 template <int CDIM>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 k_project_fwd(const float *__restrict__ means, const float *__restrict__ quats, const float *__restrict__ scales,
               const float *__restrict__ opacities, const float *__restrict__ colors_in,
               const float *__restrict__ viewmat, const float *__restrict__ K, int N, int W, int H, int tile_w,
@@ -246,7 +246,7 @@ __device__ __forceinline__ void mat3_mul_at(const float *A, const float *B, floa
 // one-warp kernel then raises this rank's flag at every peer (exchange.cu, which also holds the reduce +
 // all-gather half).
 template <int CDIM, bool EXCH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_project_bwd(const float *__restrict__ means, const float *__restrict__ quats, const float *__restrict__ scales,
               const float *__restrict__ opacities, const float *__restrict__ viewmat, const float *__restrict__ K,
               int N, int W, int H, float eps2d, int calc_comp, int d_in, int with_depth,
