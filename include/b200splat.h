@@ -153,6 +153,25 @@ int b2s_sh_bwd(int degree, const float *dirs, const float *coeffs, const uint8_t
                int K, const float *v_colors, float *v_coeffs, float *v_dirs /* may be NULL */,
                b2s_stream_t stream);
 
+/* ---- masked SSIM (reference mtgs/utils/ssim.py:56-108, called at mtgs_scene_graph.py:822-840) ----
+ * X, Y: [N, C, H, W] contiguous fp32; win: the 1-D Gaussian window (device, win_size odd <= 15, H and W >= win_size);
+ * "valid" filtering as the reference: the SSIM map is [N, C, H - win_size + 1, W - win_size + 1].
+ * mask: uint8 over the FULL image (the kernel reads it at the window centres, i.e. cropped by win_size / 2 as the
+ *   reference does), addressed mask[n * mask_n_stride + c * mask_c_stride + y * W + x] (c stride 0 = shared by the
+ *   channels); NULL = no mask.
+ * fwd: acc[plane] = (sum of mask * ssim, sum of mask) as doubles, pre-zeroed by the caller, plane = n * C + c; map_a,
+ *   map_b, map_c (SSIM-map shaped) receive mask * dS/dmu_Y, mask * dS/dE[YY], mask * dS/dE[XY]; map_ax (may be NULL)
+ *   mask * dS/dmu_X, needed only for the gradient w.r.t. X.
+ * bwd: grad = plane_scale[plane] * (F^T map_a + 2 self F^T map_b + other F^T map_c) with F^T the adjoint of the
+ *   filter; gradient w.r.t. Y: (self, other, map_a) = (Y, X, map_a); w.r.t. X: (X, Y, map_ax). */
+int b2s_ssim_fwd(const float *X, const float *Y, const uint8_t *mask, long long mask_n_stride,
+                 long long mask_c_stride, int N, int C, int H, int W, const float *win, int win_size, float C1,
+                 float C2, float *map_a, float *map_b, float *map_c, float *map_ax, double *acc,
+                 b2s_stream_t stream);
+int b2s_ssim_bwd(const float *self, const float *other, const float *map_a, const float *map_b,
+                 const float *map_c, const float *plane_scale, int N, int C, int H, int W, const float *win,
+                 int win_size, float *grad, b2s_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,6 +36,8 @@ SIGNATURES = {
     "b2s_bin_isect_ids": (_i, [_vp, _i, _vp, _vp, _ll, _vp, _vp]),
     "b2s_blend_fwd": (_i, [_vp] * 5 + [_ll] + [_i] * 7 + [_vp] * 3 + [_vp]),
     "b2s_blend_bwd": (_i, [_vp] * 5 + [_ll] + [_i] * 7 + [_vp] * 8 + [_vp]),
+    "b2s_ssim_fwd": (_i, [_vp] * 3 + [_ll, _ll] + [_i] * 4 + [_vp, _i, _f, _f] + [_vp] * 5 + [_vp]),
+    "b2s_ssim_bwd": (_i, [_vp] * 6 + [_i] * 4 + [_vp, _i, _vp] + [_vp]),
     "b2s_sh_fwd": (_i, [_i] + [_vp] * 3 + [_i, _i] + [_vp, _vp]),
     "b2s_sh_bwd": (_i, [_i] + [_vp] * 3 + [_i, _i] + [_vp] * 3 + [_vp]),
 }
