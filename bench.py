@@ -451,6 +451,52 @@ def main():
     except Exception as e:  # pragma: no cover
         hbm_stages["sh_error"] = str(e)
 
+    # ---- row f3 (next-row widening): masked SSIM fwd+bwd at the bench resolution, ours vs a plain-torch restatement
+    # of the reference's op sequence (depthwise conv2d x 10 + elementwise + masked mean; mtgs/utils/ssim.py:56-108)
+    ssim_stats = None
+    try:
+        import torch.nn.functional as F
+        from mtgs_b200.ssim import _fspecial_gauss_1d, ssim as ssim_ours
+        gt = torch.rand(1, 3, H, W, device=dev)
+        pred = (gt * 0.8 + 0.1 * torch.rand(1, 3, H, W, device=dev)).requires_grad_(True)
+        cmask = torch.rand(H, W, 1, device=dev) < 0.9
+        win = _fspecial_gauss_1d(11, 1.5).repeat(3, 1, 1, 1).to(dev)
+
+        def ssim_torch(X, Y, mask):
+            def filt(t):
+                t = F.conv2d(t, win.transpose(2, -1), groups=3)
+                return F.conv2d(t, win, groups=3)
+            C1, C2 = 0.01 ** 2, 0.03 ** 2
+            mu1, mu2 = filt(X), filt(Y)
+            s1, s2, s12 = filt(X * X) - mu1 ** 2, filt(Y * Y) - mu2 ** 2, filt(X * Y) - mu1 * mu2
+            m = ((2 * mu1 * mu2 + C1) / (mu1 ** 2 + mu2 ** 2 + C1)) * ((2 * s12 + C2) / (s1 + s2 + C2))
+            mk = mask.permute(2, 0, 1)[None].expand_as(X)[..., 5:-5, 5:-5]
+            return torch.masked_select(m, mk).mean()
+
+        def timeit(fn):
+            for _ in range(3):
+                pred.grad = None
+                (1 - fn(gt, pred, cmask)).backward()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(10):
+                pred.grad = None
+                (1 - fn(gt, pred, cmask)).backward()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / 10
+
+        t_ours = timeit(lambda X, Y, m: ssim_ours(X, Y, data_range=1.0, mask=m))
+        g_ours = pred.grad.clone()
+        t_torch = timeit(ssim_torch)
+        ssim_stats = {"resolution": f"{W}x{H}x3", "ours_fwd_bwd_ms": t_ours, "torch_restatement_fwd_bwd_ms": t_torch,
+                      "max_abs_grad_diff": float((g_ours - pred.grad).abs().max()),
+                      # fwd: X, Y in + 3 maps out; bwd: X, Y, 3 maps in + grad out  (4 B each, per pixel and channel)
+                      "algorithmic_GBps": 11 * 4 * 3 * H * W / (t_ours * 1e-3) / 1e9}
+        del gt, pred, cmask
+    except Exception as e:  # pragma: no cover
+        ssim_stats = {"error": str(e)}
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "impl": "ours",
@@ -458,7 +504,7 @@ def main():
             "roofline_step": {"algorithmic_bytes": ab["total"], "frac_of_hbm_peak": step_frac,
                               "bytes_per_gaussian": ab["total"] / N},
             "cpu_baseline": cpu_baseline,
-            "stats": {"N_vis": N_vis, "M": M, "stage_ms": stage_ms, "phase_ms": phase_ms, "hbm_bound_stages": hbm_stages,
+            "stats": {"N_vis": N_vis, "M": M, "stage_ms": stage_ms, "phase_ms": phase_ms, "hbm_bound_stages": hbm_stages, "ssim_f3": ssim_stats,
                       "loss": float(loss.item()) if math.isfinite(float(loss.item())) else None}}
     print(json.dumps(line))
     if exch is not None:
