@@ -285,14 +285,21 @@ __device__ __forceinline__ void pair_grad(float2 (&v)[16], float2 &T, float2 (&b
     v[3] = add2(v[3], abs2(vy));
 }
 
-// Transposing butterfly: 16 values per lane -> value k summed over the warp lands in lane 2k (and 2k+1).
+// Transposing butterfly: NV (<= 16) values per lane -> value k summed over the warp lands in lane 2k (and 2k+1).
+// Values NV..15 do not exist (CDIM = 4 uses 12): their partners in the first exchange are reduced without the
+// lane-dependent selects.
+template <int NV>
 __device__ __forceinline__ float warp_reduce16_transposed(float (&v)[16], const int lane) {
     bool hi = lane & 16;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const float send = hi ? v[i] : v[i + 8];
-        const float keep = hi ? v[i + 8] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        if (i + 8 < NV) {
+            const float send = hi ? v[i] : v[i + 8];
+            const float keep = hi ? v[i + 8] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        } else {
+            v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);  // lanes 16..31 end up with a copy (slot 8 + i is unused)
+        }
     }
     hi = lane & 8;
 #pragma unroll
@@ -505,8 +512,8 @@ k_blend_bwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
                 pair_grad<CDIM>(v2, T[q], buf[q], vrc[q], Tfvra[q], col, ca, cb, cc, sc.y, dx, dy[q], al[q], g[q]);
             float v[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) v[k] = v2[k].x + v2[k].y;
-            const float r = warp_reduce16_transposed(v, lane);
+            for (int k = 0; k < 16; ++k) v[k] = k < 8 + CDIM ? v2[k].x + v2[k].y : 0.f;
+            const float r = warp_reduce16_transposed<8 + CDIM>(v, lane);
             if (!(lane & 1)) s_acc[warp][t][lane >> 1] = r;
         }
         __syncthreads();

@@ -185,7 +185,7 @@ k_level_count(const TlGeom g, const int2 *__restrict__ in, const int32_t *__rest
 // ---- prefix: one CTA per child list (L, b): in-place exclusive scan of table[., b] over the chunks of L and the
 // child's length; the last CTA to finish then builds the child offsets and (levels 1-3) the next level's chunk
 // table, or (level 4) isect_offsets.
-constexpr int TL_PT = 128;  // threads of a prefix CTA
+constexpr int TL_PT = 512;  // threads of a prefix CTA (levels 3-4: 16 child lists per CTA, so few CTAs contend for the ticket)
 
 __device__ __forceinline__ int tl_block_excl_scan(int v, int &total, int *s_w /* TL_PT / 32 */) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
