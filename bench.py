@@ -237,7 +237,23 @@ def main():
     w_a = torch.randn(1, H, W, 1, device=dev, generator=gen)
     fused = world > 1 and args.exchange == "fused"
     arena = SharedGradArena([params[k] for k in names], average=True) if (world > 1 and not fused) else None
-    exch = GradExchange(n_shared=N, d_in=vcfg["d_in"], rows_cap=N, average=True) if fused else None
+    exch = None
+    if fused:
+        # set-up needs CUDA IPC between the ranks; if the box does not allow it, measure the NCCL baseline instead and
+        # say so in the JSON line (all ranks must take the same branch)
+        err = None
+        try:
+            exch = GradExchange(n_shared=N, d_in=vcfg["d_in"], rows_cap=N, average=True)
+        except Exception as e:  # pragma: no cover
+            err = f"{type(e).__name__}: {e}"
+        flag = torch.tensor([1 if err else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if int(flag.item()):
+            if exch is not None:
+                exch.close()
+            exch, fused = None, False
+            config["parallelism"] += f" -- FUSED EXCHANGE UNAVAILABLE ({err or 'failed on another rank'}); NCCL all-reduce used"
+            arena = SharedGradArena([params[k] for k in names], average=True)
 
     def step(p):
         with rendering._timed("phase_forward"):
@@ -245,7 +261,9 @@ def main():
                                        W, H, packed=False, render_mode=vcfg["render_mode"],
                                        rasterize_mode=vcfg["rasterize_mode"], absgrad=vcfg["absgrad"])
         with rendering._timed("phase_loss"):
-            loss = (r * w_c).sum() + (a * w_a).sum()
+            # loss = sum(render * w_c) + sum(alpha * w_a), written as two dot products: same value and
+            # cotangents, no image-sized temporaries
+            loss = torch.dot(r.reshape(-1), w_c.reshape(-1)) + torch.dot(a.reshape(-1), w_a.reshape(-1))
         if arena is not None:
             arena.zero_()
         else:
@@ -338,7 +356,7 @@ def main():
         r, a, m = rasterization(p["means"], p["quats"], p["scales"], p["opacities"], p["colors"], viewmat, Ks, W, H,
                                 packed=False, render_mode=vcfg["render_mode"], rasterize_mode=vcfg["rasterize_mode"],
                                 absgrad=vcfg["absgrad"])
-        l = (r * w_c).sum() + (a * w_a).sum()
+        l = torch.dot(r.reshape(-1), w_c.reshape(-1)) + torch.dot(a.reshape(-1), w_a.reshape(-1))
         l.backward()
         flat = torch.cat([p[k].grad.reshape(-1) for k in names])
         dist.all_reduce(flat)

@@ -214,18 +214,25 @@ class GradExchange:
                 mine.append(bytes(buf.raw))
         gathered = [None] * self.world
         dist.all_gather_object(gathered, mine, group=self.group)
+        failure = None
         with torch.cuda.device(self.device):
             for r, handles in enumerate(gathered):
-                if r == self.rank:
+                if r == self.rank or failure is not None:
                     continue
                 ptrs = []
-                for h in handles:
-                    q = C.c_void_p()
-                    self._check(self._lib.b2s_ipc_import(C.create_string_buffer(h, 64), C.byref(q)), "b2s_ipc_import")
-                    ptrs.append(int(q.value))
-                    self._imported.append(int(q.value))
-                self.stage_ptrs[r], self.arena_ptrs[r], self.flag_ptrs[r] = ptrs
+                try:
+                    for h in handles:
+                        q = C.c_void_p()
+                        self._check(self._lib.b2s_ipc_import(C.create_string_buffer(h, 64), C.byref(q)),
+                                    "b2s_ipc_import")
+                        ptrs.append(int(q.value))
+                        self._imported.append(int(q.value))
+                    self.stage_ptrs[r], self.arena_ptrs[r], self.flag_ptrs[r] = ptrs
+                except RuntimeError as e:  # keep the collectives below matched on every rank, then report
+                    failure = e
         dist.barrier(group=self.group)
+        if failure is not None:
+            raise failure
 
     @staticmethod
     def local_ranks(world: int, n_shared: int, d_in: int, rows_cap: Optional[int] = None, average: bool = True,
