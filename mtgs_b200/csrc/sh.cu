@@ -131,6 +131,42 @@ __device__ __forceinline__ void stage_rows(const float *__restrict__ src, float 
     }
 }
 
+// ---- TMA (bulk asynchronous copy) helpers: cp.async.bulk moves a contiguous, 16-byte aligned run between global and
+// shared memory without occupying the threads; completion of loads is signalled on an mbarrier (transaction bytes),
+// completion of stores through the bulk async-group.
+__device__ __forceinline__ unsigned sh_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sh_mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sh_smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void sh_mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sh_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sh_mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SH_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra SH_DONE;\n"
+        "bra SH_WAIT;\n"
+        "SH_DONE:\n"
+        "}\n" ::"r"(sh_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void sh_bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     sh_smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(sh_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void sh_bulk_s2g(void *dst_gmem, const void *src_smem, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(sh_smem_u32(src_smem)),
+                 "r"(bytes)
+                 : "memory");
+}
+
 static inline int sh_row_stride(int K) {
     int f = K * 3;
     int units = (f + 3) / 4;      // 16-byte units
@@ -143,22 +179,37 @@ __global__ void __launch_bounds__(SH_THREADS)
 k_sh_fwd(const float *__restrict__ dirs, const float *__restrict__ coeffs, const uint8_t *__restrict__ masks, int N,
          int K, int stride, float *__restrict__ colors) {
     extern __shared__ __align__(16) float s_rows[];
+    __shared__ __align__(8) unsigned long long s_bar;
     constexpr int NB = (DEG + 1) * (DEG + 1);
     const int g0 = blockIdx.x * SH_THREADS;
     const int rows = min(SH_THREADS, N - g0);
     const int rf = K * 3;
-    stage_rows(coeffs + (size_t)g0 * rf, s_rows, rows, rf, stride, (rf & 3) == 0);
-    __syncthreads();
-    const int g = g0 + threadIdx.x;
-    if (g >= N) return;
-    if (masks && !masks[g]) return;
-    float x = dirs[3 * g], y = dirs[3 * g + 1], z = dirs[3 * g + 2];
-    if (DEG >= 1) {
-        const float inorm = rsqrtf(x * x + y * y + z * z);
-        x *= inorm; y *= inorm; z *= inorm;
+    // rows of 16-byte multiples (K = 16: 192 B) are fetched by the TMA engine, one bulk copy per row into the padded
+    // shared-memory row, while the threads load their directions and evaluate the basis; other K: cooperative loads
+    const bool tma = (rf & 3) == 0 && ((size_t)coeffs & 15) == 0;
+    if (tma) {
+        if (threadIdx.x == 0) sh_mbar_init(&s_bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) sh_mbar_expect_tx(&s_bar, (unsigned)(rows * rf * 4));
+        if ((int)threadIdx.x < rows)
+            sh_bulk_g2s(s_rows + threadIdx.x * stride, coeffs + (size_t)(g0 + threadIdx.x) * rf, (unsigned)(rf * 4), &s_bar);
+    } else {
+        stage_rows(coeffs + (size_t)g0 * rf, s_rows, rows, rf, stride, (rf & 3) == 0);
+        __syncthreads();
     }
+    const int g = g0 + threadIdx.x;
+    const bool live = g < N && !(masks && !masks[g]);
     float B[SH_MAXK];
-    sh_basis<DEG>(x, y, z, B);
+    if (live) {
+        float x = dirs[3 * g], y = dirs[3 * g + 1], z = dirs[3 * g + 2];
+        if (DEG >= 1) {
+            const float inorm = rsqrtf(x * x + y * y + z * z);
+            x *= inorm; y *= inorm; z *= inorm;
+        }
+        sh_basis<DEG>(x, y, z, B);
+    }
+    if (tma) sh_mbar_wait(&s_bar, 0);  // every thread observes the completed transaction before reading the rows
+    if (!live) return;
     const float *row = s_rows + threadIdx.x * stride;
     float r0 = 0.f, r1 = 0.f, r2 = 0.f;
 #pragma unroll
@@ -237,8 +288,18 @@ k_sh_bwd(const float *__restrict__ dirs, const float *__restrict__ coeffs, const
             }
         }
     }
-    __syncthreads();
     float *dst = v_coeffs + (size_t)g0 * rf;
+    if ((rf & 3) == 0 && ((size_t)v_coeffs & 15) == 0) {
+        // each thread hands its finished 16-byte-multiple row to the TMA engine (shared -> global bulk store)
+        if (g < N) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my generic-proxy writes -> async proxy
+            sh_bulk_s2g(dst + (size_t)threadIdx.x * rf, s_rows + threadIdx.x * stride, (unsigned)(rf * 4));
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the read
+        }
+        return;
+    }
+    __syncthreads();
     if ((rf & 3) == 0) {
         const int q_per_row = rf / 4;
         const int total = rows * q_per_row;
