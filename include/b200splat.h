@@ -104,7 +104,7 @@ int b2s_project_bwd_exchange(const float *means, const float *quats, const float
                              long long rows_cap, float scale, unsigned epoch, int phases,
                              const unsigned long long *stage_ptrs_host,
                              const unsigned long long *arena_ptrs_host,
-                             const unsigned long long *flag_ptrs_host, unsigned *ticket, unsigned *status,
+                             const unsigned long long *flag_ptrs_host, unsigned *status,
                              b2s_stream_t stream);
 
 /* ---- tile binning + depth sort (upstream isect_tiles + radix sort + isect_offset_encode; A.2) ----

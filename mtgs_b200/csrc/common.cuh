@@ -67,14 +67,7 @@ struct B2sExchange {
     float *stage[B2S_MAX_WORLD];     // stage[r]: rank r's staging buffer [world][slot_floats] (peer-mapped)
     float *arena[B2S_MAX_WORLD];     // arena[r]: rank r's reduced-gradient arena (peer-mapped)
     unsigned *flags[B2S_MAX_WORLD];  // flags[r]: rank r's flag words [2 phases][B2S_MAX_WORLD] (peer-mapped)
-    unsigned *ticket;                // local CTA ticket counter (zero between launches)
 };
 
 // tile rows per row group / tile columns per column group of the tile-list hierarchy (tilelists.cu)
 int b2s_tl_shifts(int tile_w, int tile_h, int *rg_shift, int *cg_shift);
-
-// device-wide exclusive scan of int32 (binning.cu); `in` may alias `out`; gather may be null.
-// ws must hold b2s_scan_ws_ints(n) ints.  Grand total (int64) is written to *total_out when non-null.
-size_t b2s_scan_ws_ints(int n);
-int b2s_device_excl_scan(const int32_t *in, const int32_t *gather, int n, int32_t *out, int64_t *total_out,
-                         int32_t *ws, cudaStream_t st);

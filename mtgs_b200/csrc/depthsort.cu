@@ -1,9 +1,12 @@
 // Depth order of the visible Gaussians in ONE cooperative kernel (sm_100a).
 //
-// First half of the two-level replacement of upstream gsplat v1.4.0's 64-bit radix sort of all tile
-// intersections (reached from mtgs_scene_graph.py:641-662): a stable sort by (tile, depth
-// bits) equals a stable sort of the GAUSSIANS by depth bits followed by an order-preserving bucketing of their
-// intersections by tile (tilelists.cu).  This file produces
+// First half of the two-level replacement of upstream gsplat v1.4.0's isect_tiles pass 2 + 64-bit radix sort of
+// all tile intersections + isect_offset_encode (reached from mtgs_scene_graph.py:641-662).
+// The upstream order is "stable sort of all M intersections by (tile, depth bits)", ties in emission order
+// (= ascending Gaussian id).  A stable sort by a composite key equals a stable sort by the minor key followed by a
+// stable sort by the major key, and all intersections of one Gaussian share its depth, so a stable sort of the
+// GAUSSIANS by depth bits followed by an order-preserving bucketing of their intersections by tile (tilelists.cu)
+// gives bit-identical flatten_ids / isect_offsets without ever sorting M 64-bit keys.  This file produces
 //     order[0 .. n_vis)  Gaussian ids in stable depth order (ties: ascending id), culled Gaussians dropped
 //     totals[5]          M = tile intersections, S = tile-row hits, E1 / E3 = row-group and (row, column-group) hits
 //                        (the list sizes of the tile-list hierarchy, tilelists.cu), n_vis

@@ -161,15 +161,15 @@ extern "C" int b2s_project_bwd_exchange(
     const int32_t *radii, const float *geo, const float *comps, const float *v_means2d, int v_means2d_stride,
     const float *v_geo, const float *v_colpack, float *v_viewmat, int n_shared, int world, int rank, long long rows_cap,
     float scale, unsigned epoch, int phases, const unsigned long long *stage_ptrs_host,
-    const unsigned long long *arena_ptrs_host, const unsigned long long *flag_ptrs_host, unsigned *ticket,
-    unsigned *status, b2s_stream_t stream) {
+    const unsigned long long *arena_ptrs_host, const unsigned long long *flag_ptrs_host, unsigned *status,
+    b2s_stream_t stream) {
     if (N < 0 || n_shared < 0 || n_shared > N || world < 1 || world > B2S_MAX_WORLD || rank < 0 || rank >= world)
         return B2S_ERR_ARG;
     if (rows_cap < N || (rows_cap & 3) || d_in < 0 || d_in > 8) return B2S_ERR_ARG;
     if (cdim != 4 && cdim != 8) return B2S_ERR_UNSUPPORTED;
     if (calc_comp && comps == nullptr) return B2S_ERR_ARG;
     if (v_means2d_stride < 2 || (v_means2d_stride & 1)) return B2S_ERR_ARG;
-    if (!stage_ptrs_host || !arena_ptrs_host || !flag_ptrs_host || !ticket || !status) return B2S_ERR_ARG;
+    if (!stage_ptrs_host || !arena_ptrs_host || !flag_ptrs_host || !status) return B2S_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     B2sExchange ex = {};
     ex.world = world;
@@ -183,7 +183,6 @@ extern "C" int b2s_project_bwd_exchange(
         ex.flags[r] = (unsigned *)(uintptr_t)flag_ptrs_host[r];
         if (!ex.stage[r] || !ex.arena[r] || !ex.flags[r]) return B2S_ERR_ARG;
     }
-    ex.ticket = ticket;
     float *arena = ex.arena[rank];
     int rc;
     if (n_shared > 0 && (phases & 1)) {

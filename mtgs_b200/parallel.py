@@ -196,7 +196,6 @@ class GradExchange:
         self.stage_ptrs[self.rank], self.arena_ptrs[self.rank], self.flag_ptrs[self.rank] = self._own
         self._imported = []
         self.arena = torch.as_tensor(_DevMem(self._own[1], self.F * self.rows_cap), device=self.device)
-        self.ticket = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.epoch = 0
         if _local is None and self.world > 1:
@@ -300,7 +299,7 @@ class GradExchange:
         self._check(self._lib.b2s_project_bwd_exchange(
             *args, self.n_shared, self.world, self.rank, self.rows_cap, self.scale, self.epoch, phases,
             self._ptr_array(self.stage_ptrs), self._ptr_array(self.arena_ptrs), self._ptr_array(self.flag_ptrs),
-            C.c_void_p(self.ticket.data_ptr()), C.c_void_p(self.status.data_ptr()), stream),
+            C.c_void_p(self.status.data_ptr()), stream),
             "b2s_project_bwd_exchange")
 
     @staticmethod
