@@ -398,11 +398,13 @@ def main():
                    "project_bwd_exchange": ab["project_bwd"] + N * (44 + 4 * vcfg["d_in"]) * 2}
     phase_ms = {k: stage_ms.pop(k) for k in list(stage_ms) if k.startswith("phase_") or k.startswith("exch_")}
     dom = max(stage_ms, key=stage_ms.get) if stage_ms else None
-    traffic = None
+    traffic = ipc = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if dom and os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(dom)
+            tj = json.load(open(tpath))
+            traffic = tj.get(dom)
+            ipc = tj.get("ipc", {}).get(dom)
         except Exception:
             traffic = None
     roofline = None
@@ -411,6 +413,9 @@ def main():
         roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": stage_bytes[dom],
                     "kernel_ms": stage_ms[dom],
+                    # secondary roofline of an instruction-issue-bound kernel: issued warp-instructions per cycle
+                    # over the SM's 4 issue slots (ncu capture summarised in profiles/, not measured live)
+                    "issue_slot_utilisation": (ipc / 4.0) if ipc else None,
                     "note": "blend kernels are FP32-ALU/MUFU/shuffle bound (SURVEY 8d): HBM fraction is small by "
                             "construction; whole-step HBM fraction in roofline_step"}
     step_frac = ab["total"] / (ms_per_step * 1e-3) / 1e9 / peak
