@@ -130,25 +130,29 @@ __device__ __forceinline__ int2 tl_item(int i, const int2 *__restrict__ in, cons
     return in[i];
 }
 
-// children-per-slice counting shared by count and fill: lane b of warp w ends with the number of items of slice w
-// of the chunk [begin, end) that cover child b
+// children-per-slice counting: lane b of the warp ends with the number of items of the slice [sb, se) that cover
+// child b.  Counting needs no ordering, so it uses a difference array (+1 at the first covered child, -1 behind the
+// last: two shared-memory atomics per item, whatever its extent) and one warp scan, instead of one ballot per child.
 template <int K>
-__device__ __forceinline__ int tl_slice_count(const TlGeom &g, int NB, int L, int sb, int se, int lane,
+__device__ __forceinline__ int tl_slice_count(const TlGeom &g, int NB, int L, int sb, int se, int lane, int *s_d /* 33 */,
                                               const int2 *__restrict__ in, const int32_t *__restrict__ order,
                                               const int2 *__restrict__ rects) {
-    int cnt = 0;
+    s_d[lane] = 0;
+    if (lane == 0) s_d[32] = 0;
+    __syncwarp();
     int2 nxt = make_int2(0, 0);
     if (sb + lane < se) nxt = tl_item<K>(sb + lane, in, order, rects);
     for (int i0 = sb; i0 < se; i0 += 32) {
         int lo = 0, hi = 0;
         if (i0 + lane < se) tl_bins<K>(nxt.y, L, g, lo, hi);
         if (i0 + 32 + lane < se) nxt = tl_item<K>(i0 + 32 + lane, in, order, rects);  // prefetch
-        for (int b = 0; b < NB; ++b) {
-            const unsigned bal = __ballot_sync(0xffffffffu, lo <= b && b < hi);
-            if (lane == b) cnt += __popc(bal);
+        if (hi > lo) {
+            atomicAdd(&s_d[lo], 1);
+            atomicAdd(&s_d[hi], -1);  // hi <= NB <= 32
         }
     }
-    return cnt;
+    __syncwarp();
+    return tl_warp_incl_scan(s_d[lane], lane);  // lanes >= NB hold garbage-free zeros or are ignored by the callers
 }
 
 // ---- count: table[b * nch + c] = items of chunk c covering child b
@@ -160,6 +164,7 @@ k_level_count(const TlGeom g, const int2 *__restrict__ in, const int32_t *__rest
               int32_t *__restrict__ table, int32_t *__restrict__ slice_cnt /* [nch][TL_WARPS][32] */,
               unsigned *__restrict__ ticket) {
     __shared__ int s_cnt[TL_WARPS][32];
+    __shared__ int s_diff[TL_WARPS][33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (blockIdx.x == 0 && threadIdx.x == 0) *ticket = 0u;  // armed for this level's prefix kernel
     const int c = blockIdx.x;
@@ -167,8 +172,8 @@ k_level_count(const TlGeom g, const int2 *__restrict__ in, const int32_t *__rest
     if (!tl_chunk<K>(c, nlists, list_off, chunk_off, n_vis, L, begin, end)) return;  // CTA-uniform
     const int NB = tl_nb<K>(g);
     const int sb = min(end, begin + warp * TlCh<K>::slice), se = min(end, sb + TlCh<K>::slice);
-    const int mine = tl_slice_count<K>(g, NB, L, sb, se, lane, in, order, rects);
-    s_cnt[warp][lane] = mine;
+    const int mine = tl_slice_count<K>(g, NB, L, sb, se, lane, s_diff[warp], in, order, rects);
+    s_cnt[warp][lane] = lane < NB ? mine : 0;
     __syncthreads();
     // exclusive prefix over the slices (read back by the fill kernel) and the chunk's total
     int pre = 0, tot = 0;
