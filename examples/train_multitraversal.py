@@ -11,8 +11,10 @@ a perturbed copy is then optimised against them through the SAME public API MTGS
 
 Single GPU:   python examples/train_multitraversal.py --iters 300
 Multi GPU :   torchrun --nproc-per-node 4 --master-addr 127.0.0.1 examples/train_multitraversal.py --traversals 4
-              (rank r owns traversal r; shared-node gradients are all-reduced through SharedGradArena, the
-               per-traversal adapters stay rank-local -- SURVEY.md 8e)
+              (rank r owns traversal r; the gradients of the shared geometry are exchanged INSIDE the projection
+               backward (GradExchange, exchange_colors=False because the SH colours are view dependent), the SH
+               coefficient gradients are all-reduced at their leaves (SharedGradArena), the per-traversal
+               adapters stay rank-local -- SURVEY.md 8e)
 """
 from __future__ import annotations
 
@@ -30,7 +32,7 @@ if ROOT not in sys.path:
 
 from mtgs_b200 import scenes  # noqa: E402
 from mtgs_b200.cuda._wrapper import spherical_harmonics  # noqa: E402
-from mtgs_b200.parallel import SharedGradArena, traversal_of_rank  # noqa: E402
+from mtgs_b200.parallel import GradExchange, SharedGradArena, traversal_of_rank  # noqa: E402
 from mtgs_b200.rendering import rasterization  # noqa: E402
 
 C0 = 0.28209479177387814
@@ -76,7 +78,7 @@ def psnr(a, b):
 
 def main(argv=None):
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=100_000)
+    ap.add_argument("--n-gauss", dest="n", type=int, default=100_000)
     ap.add_argument("--traversals", type=int, default=3)
     ap.add_argument("--width", type=int, default=960)
     ap.add_argument("--height", type=int, default=540)
@@ -110,8 +112,11 @@ def main(argv=None):
         noise = {"means": 0.02, "scales": 0.15, "quats": 0.05, "opacities": 0.5, "features_dc": 0.5,
                  "features_rest": 0.05, "features_adapters": 0.3}[k]
         model[k] = (v + noise * torch.randn(v.shape, generator=g).to(dev)).requires_grad_(True)
-    shared = [model[k] for k in ("means", "scales", "quats", "opacities", "features_dc", "features_rest")]
-    arena = SharedGradArena(shared, average=True) if world > 1 else None
+    # multi-GPU: geometry gradients (means / scales / quats / opacities: replicated elementwise activations) are
+    # averaged inside the projection backward; the colour path goes through per-camera SH, so its shared leaves
+    # (features_dc, features_rest) are all-reduced where they live
+    arena = SharedGradArena([model[k] for k in ("features_dc", "features_rest")], average=True) if world > 1 else None
+    exch = GradExchange(n_shared=args.n, d_in=3, rows_cap=args.n, average=True, exchange_colors=False) if world > 1 else None
     lrs = {"means": 1.6e-4, "scales": 5e-3, "quats": 1e-3, "opacities": 5e-2, "features_dc": 2.5e-3,
            "features_rest": 1.25e-4, "features_adapters": 2.5e-3}
     opt = torch.optim.Adam([{"params": [model[k]], "lr": lrs[k], "eps": 1e-15} for k in model])
@@ -129,12 +134,14 @@ def main(argv=None):
         first.setdefault(t, psnr(rgb.detach(), tgt_rgb))
         if arena is not None:
             arena.zero_()
-            model["features_adapters"].grad = None
+            for k in ("means", "scales", "quats", "opacities", "features_adapters"):
+                model[k].grad = None
+            with exch.active():
+                loss.backward()
+            arena.all_reduce()
         else:
             opt.zero_grad(set_to_none=True)
-        loss.backward()
-        if arena is not None:
-            arena.all_reduce()
+            loss.backward()
         with torch.no_grad():  # densification statistics exactly as mtgs_scene_graph.py:1171-1178
             grads = info["means2d"].absgrad[0]
             vis = info["radii"][0] > 0
@@ -150,6 +157,9 @@ def main(argv=None):
         print("final PSNR per traversal:", {k: round(v, 2) for k, v in final.items()})
     if world > 1:
         import torch.distributed as dist
+        exch.check()
+        dist.barrier()
+        exch.close()
         dist.destroy_process_group()
     return first, final
 

@@ -74,11 +74,14 @@ int b2s_project_bwd(const float *means, const float *quats, const float *scales,
 /* ---- multi-GPU: projection backward fused with the exchange of the shared-node gradients ----
  * One traversal camera per GPU over replicated shared Gaussians (mtgs_scene_graph.py:548 renders one camera per
  * call); rows [0, n_shared) of the rasterizer inputs are the replicated ones, rows [n_shared, N) are rank-local.
- * Each rank owns shard = b2s_exchange_shard_rows(n_shared, world) consecutive rows.  Buffers (peer-mapped through
- * CUDA IPC, allocated with b2s_peer_alloc so that they are exportable):
- *   stage  [world][(11 + d_in) * shard] floats  partial gradient rows of MY shard, one slot per source rank
- *   arena  [(11 + d_in) * rows_cap]     floats  reduced gradient, SoA blocks: means at 0, quats at 3 rows_cap,
- *                                               scales at 7 rows_cap, opacities at 10 rows_cap, colours at 11 rows_cap
+ * Each rank owns shard = b2s_exchange_shard_rows(n_shared, world) consecutive rows.  d_col = d_in when
+ * exchange_colors != 0 (the colours are replicated view-independent inputs), else 0: colour gradients stay in
+ * v_colpack on the GPU (view-dependent colours, e.g. SH evaluated per camera, must be reduced at their own leaves
+ * because their Jacobian differs from rank to rank).  Buffers (peer-mapped through CUDA IPC, allocated with
+ * b2s_peer_alloc so that they are exportable):
+ *   stage  [world][(11 + d_col) * shard] floats  partial gradient rows of MY shard, one slot per source rank
+ *   arena  [(11 + d_col) * rows_cap]     floats  reduced gradient, SoA blocks: means at 0, quats at 3 rows_cap,
+ *                                                scales at 7 rows_cap, opacities at 10 rows_cap, colours at 11 rows_cap
  *   flags  [2][8] uint32 (zero-initialised)     phase-0 / phase-1 arrival flags, written by the peers
  * The call enqueues: projection backward storing its rows straight into the owners' stage slots (peer stores), the
  * plain projection backward for the rank-local rows, the reduce of my shard + store of the result into every rank's
@@ -100,8 +103,8 @@ int b2s_project_bwd_exchange(const float *means, const float *quats, const float
                              int H, float eps2d, int calc_comp, int d_in, int with_depth, int cdim,
                              const int32_t *radii, const float *geo, const float *comps,
                              const float *v_means2d, int v_means2d_stride, const float *v_geo,
-                             const float *v_colpack, float *v_viewmat, int n_shared, int world, int rank,
-                             long long rows_cap, float scale, unsigned epoch, int phases,
+                             const float *v_colpack, float *v_viewmat, int n_shared, int exchange_colors,
+                             int world, int rank, long long rows_cap, float scale, unsigned epoch, int phases,
                              const unsigned long long *stage_ptrs_host,
                              const unsigned long long *arena_ptrs_host,
                              const unsigned long long *flag_ptrs_host, unsigned *status,

@@ -62,7 +62,8 @@ __device__ __forceinline__ float4 ldg_stream4(const float4 *p) {
 struct B2sExchange {
     int world, rank;
     int shard;              // Gaussians (rows) owned per rank; multiple of 256
-    long long slot_floats;  // floats per (owner, source) staging slot = (11 + d_in) * shard
+    int d_col;              // colour floats per row that take part in the exchange (d_in, or 0: colours stay local)
+    long long slot_floats;  // floats per (owner, source) staging slot = (11 + d_col) * shard
     unsigned epoch;         // step counter written into the flags
     float *stage[B2S_MAX_WORLD];     // stage[r]: rank r's staging buffer [world][slot_floats] (peer-mapped)
     float *arena[B2S_MAX_WORLD];     // arena[r]: rank r's reduced-gradient arena (peer-mapped)

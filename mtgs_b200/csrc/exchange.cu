@@ -46,7 +46,7 @@ __device__ __forceinline__ bool ex_wait_flag(const volatile unsigned *flag, unsi
 }
 
 __global__ void __launch_bounds__(256)
-k_grad_reduce_bcast(const B2sExchange ex, int n_shared, int d_in, long long rows_cap, float scale,
+k_grad_reduce_bcast(const B2sExchange ex, int n_shared, long long rows_cap, float scale,
                     unsigned *__restrict__ status) {
     __shared__ unsigned s_ok;
     if (threadIdx.x == 0) s_ok = 1u;
@@ -69,7 +69,7 @@ k_grad_reduce_bcast(const B2sExchange ex, int n_shared, int d_in, long long rows
             // block p of the slot (means | quats | scales | opacity | colours) and the float index inside it
             int a_p = 0, wp = 3;
             long long b0 = 0;
-            if (e >= b4) { a_p = 11; wp = d_in; b0 = b4; }
+            if (e >= b4) { a_p = 11; wp = ex.d_col; b0 = b4; }
             else if (e >= b3) { a_p = 10; wp = 1; b0 = b3; }
             else if (e >= b2) { a_p = 7; wp = 3; b0 = b2; }
             else if (e >= b1) { a_p = 3; wp = 4; b0 = b1; }
@@ -159,8 +159,8 @@ extern "C" int b2s_project_bwd_exchange(
     const float *means, const float *quats, const float *scales, const float *opacities, const float *viewmat,
     const float *K, int N, int W, int H, float eps2d, int calc_comp, int d_in, int with_depth, int cdim,
     const int32_t *radii, const float *geo, const float *comps, const float *v_means2d, int v_means2d_stride,
-    const float *v_geo, const float *v_colpack, float *v_viewmat, int n_shared, int world, int rank, long long rows_cap,
-    float scale, unsigned epoch, int phases, const unsigned long long *stage_ptrs_host,
+    const float *v_geo, const float *v_colpack, float *v_viewmat, int n_shared, int exchange_colors, int world, int rank,
+    long long rows_cap, float scale, unsigned epoch, int phases, const unsigned long long *stage_ptrs_host,
     const unsigned long long *arena_ptrs_host, const unsigned long long *flag_ptrs_host, unsigned *status,
     b2s_stream_t stream) {
     if (N < 0 || n_shared < 0 || n_shared > N || world < 1 || world > B2S_MAX_WORLD || rank < 0 || rank >= world)
@@ -175,7 +175,8 @@ extern "C" int b2s_project_bwd_exchange(
     ex.world = world;
     ex.rank = rank;
     ex.shard = b2s_exchange_shard_rows(n_shared, world);
-    ex.slot_floats = (long long)(11 + d_in) * ex.shard;
+    ex.d_col = exchange_colors ? d_in : 0;
+    ex.slot_floats = (long long)(11 + ex.d_col) * ex.shard;
     ex.epoch = epoch;
     for (int r = 0; r < world; ++r) {
         ex.stage[r] = (float *)(uintptr_t)stage_ptrs_host[r];
@@ -208,7 +209,7 @@ extern "C" int b2s_project_bwd_exchange(
         int device = 0, sms = 148;
         cudaGetDevice(&device);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-        k_grad_reduce_bcast<<<sms * 4, 256, 0, st>>>(ex, n_shared, d_in, rows_cap, scale, status);
+        k_grad_reduce_bcast<<<sms * 4, 256, 0, st>>>(ex, n_shared, rows_cap, scale, status);
         B2S_LAUNCH_CHECK();
     }
     if (n_shared > 0 && (phases & 4)) {

@@ -429,19 +429,20 @@ k_project_bwd(const float *__restrict__ means, const float *__restrict__ quats, 
         }
     } else {
         // ---- transpose the CTA's rows through shared memory, then 16-byte coalesced stores into the owner's slot
-        extern __shared__ __align__(16) float s_ex[];  // [768 means | 1024 quats | 768 scales | 256 opac | d_in * 256 colours]
+        extern __shared__ __align__(16) float s_ex[];  // [768 means | 1024 quats | 768 scales | 256 opac | d_col * 256 colours]
+        const int d_col = ex.d_col;
         const int t = threadIdx.x;
         s_ex[3 * t] = o_means[0]; s_ex[3 * t + 1] = o_means[1]; s_ex[3 * t + 2] = o_means[2];
         reinterpret_cast<float4 *>(s_ex + 768)[t] = o_quat;
         s_ex[1792 + 3 * t] = o_scales[0]; s_ex[1792 + 3 * t + 1] = o_scales[1]; s_ex[1792 + 3 * t + 2] = o_scales[2];
         s_ex[2560 + t] = o_opac;
-        for (int k = 0; k < d_in; ++k) s_ex[2816 + d_in * t + k] = live ? v_colpack[(size_t)g * CDIM + k] : 0.f;
+        for (int k = 0; k < d_col; ++k) s_ex[2816 + d_col * t + k] = live ? v_colpack[(size_t)g * CDIM + k] : 0.f;
         __syncthreads();
         const int g0 = blockIdx.x * 256;
         const int owner = g0 / ex.shard, l0 = g0 - owner * ex.shard;
         const int rows = min(256, N - g0);
         float *slot = ex.stage[owner] + (size_t)ex.rank * ex.slot_floats;
-        const int widths[5] = {3, 4, 3, 1, d_in};
+        const int widths[5] = {3, 4, 3, 1, d_col};
         int s_off = 0, a_p = 0;
 #pragma unroll
         for (int p = 0; p < 5; ++p) {
@@ -554,7 +555,7 @@ int b2s_launch_project_bwd_exchange(const float *means, const float *quats, cons
                                     const float *v_geo, const float *v_colpack, float *v_viewmat, const B2sExchange &ex,
                                     cudaStream_t st) {
     dim3 grid(b2s_div_up(n_rows, 256)), block(256);
-    const size_t smem = (size_t)(11 + d_in) * 256 * sizeof(float);
+    const size_t smem = (size_t)(11 + ex.d_col) * 256 * sizeof(float);
 #define LAUNCH(CD)                                                                                               \
     k_project_bwd<CD, true><<<grid, block, smem, st>>>(means, quats, scales, opacities, viewmat, K, n_rows, W, H, \
                                                        eps2d, calc_comp, d_in, with_depth, radii,                \

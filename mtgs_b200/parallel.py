@@ -145,10 +145,14 @@ class GradExchange:
 
     Rows ``[0, n_shared)`` of means / quats / scales / opacities / colors are the replicated shared-node Gaussians
     (identical values on every rank); rows beyond are rank-local (the vehicles of the rank's own traversal,
-    reference rigid_node.py:87, 259-261) and stay on the GPU.  Because the activations MTGS applies before the
-    rasterizer (vanilla_gaussian_splatting.py:299-307) are elementwise functions of replicated parameters, reducing
-    at the rasterizer inputs and then back-propagating the reduced gradient locally gives the same leaf gradients
-    as reducing at the leaves.
+    reference rigid_node.py:87, 259-261) and stay on the GPU.  Because the activations MTGS applies to means,
+    scales, quats and opacities before the rasterizer (vanilla_gaussian_splatting.py:299-307) are elementwise
+    functions of replicated parameters, reducing at the rasterizer inputs and then back-propagating the reduced
+    gradient locally gives the same leaf gradients as reducing at the leaves.  That argument does NOT hold for
+    colours evaluated from spherical harmonics per camera (vanilla_gaussian_splatting.py:309-318): their Jacobian
+    (the SH basis of the rank's own view directions) differs from rank to rank.  Pass ``exchange_colors=False``
+    then: colour gradients stay local and the SH coefficient gradients are reduced at their leaves
+    (``SharedGradArena``); ``exchange_colors=True`` is for replicated, view-independent colour inputs.
 
     Usage (one process per GPU, ``torch.distributed`` initialised with NCCL)::
 
@@ -156,12 +160,15 @@ class GradExchange:
         render, alpha, info = rasterization(...)
         with ex.active():
             loss.backward()          # .grad of the inputs already holds the mean over all ranks
+
+    The gradient tensors handed to autograd alias the exchange arena: they are valid until the next exchange
+    (consume them -- optimizer step, or clone -- before the next ``backward`` under ``active()``).
     """
 
     MAX_WORLD = 8
 
     def __init__(self, n_shared: int, d_in: int, rows_cap: Optional[int] = None, group=None, average: bool = True,
-                 device: Optional[torch.device] = None, _local: Optional[tuple] = None):
+                 device: Optional[torch.device] = None, exchange_colors: bool = True, _local: Optional[tuple] = None):
         from . import _lib
         import ctypes as C
         self._lib = lib = _lib.load()
@@ -176,13 +183,14 @@ class GradExchange:
             raise NotImplementedError(f"GradExchange supports up to {self.MAX_WORLD} ranks (one NVSwitch domain)")
         self.group = group
         self.n_shared, self.d_in = int(n_shared), int(d_in)
+        self.exchange_colors = bool(exchange_colors)
         self.rows_cap = (int(rows_cap if rows_cap is not None else n_shared) + 3) // 4 * 4
         if self.rows_cap < self.n_shared:
             raise ValueError("rows_cap < n_shared")
         self.scale = 1.0 / self.world if average else 1.0
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.shard = int(lib.b2s_exchange_shard_rows(self.n_shared, self.world))
-        self.F = 11 + self.d_in
+        self.F = 11 + (self.d_in if self.exchange_colors else 0)
         self._sizes = (self.world * self.F * self.shard * 4, self.F * self.rows_cap * 4, 256)
         self._own = []
         with torch.cuda.device(self.device):
@@ -235,10 +243,11 @@ class GradExchange:
 
     @staticmethod
     def local_ranks(world: int, n_shared: int, d_in: int, rows_cap: Optional[int] = None, average: bool = True,
-                    device: Optional[torch.device] = None) -> List["GradExchange"]:
+                    device: Optional[torch.device] = None, exchange_colors: bool = True) -> List["GradExchange"]:
         """``world`` exchanges living in ONE process on ONE GPU, wired to each other's buffers (tests only:
         every rank's backward runs phase 1, then ``finish_all`` plays the remaining phases, all on one stream)."""
-        exs = [GradExchange(n_shared, d_in, rows_cap, average=average, device=device, _local=(world, r))
+        exs = [GradExchange(n_shared, d_in, rows_cap, average=average, device=device, exchange_colors=exchange_colors,
+                            _local=(world, r))
                for r in range(world)]
         for a in exs:
             for b in exs:
@@ -279,9 +288,11 @@ class GradExchange:
     def grad_views(self, N: int) -> Dict[str, Tensor]:
         """Views of the arena holding the gradients of an N-row call (rows < n_shared: reduced over ranks)."""
         c, a = self.rows_cap, self.arena
-        return {"means": a[0:3 * N].view(N, 3), "quats": a[3 * c:3 * c + 4 * N].view(N, 4),
-                "scales": a[7 * c:7 * c + 3 * N].view(N, 3), "opacities": a[10 * c:10 * c + N],
-                "colors": a[11 * c:11 * c + self.d_in * N].view(N, self.d_in)}
+        out = {"means": a[0:3 * N].view(N, 3), "quats": a[3 * c:3 * c + 4 * N].view(N, 4),
+               "scales": a[7 * c:7 * c + 3 * N].view(N, 3), "opacities": a[10 * c:10 * c + N]}
+        if self.exchange_colors:
+            out["colors"] = a[11 * c:11 * c + self.d_in * N].view(N, self.d_in)
+        return out
 
     def _ptr_array(self, ptrs):
         import ctypes as C
@@ -297,7 +308,8 @@ class GradExchange:
         self._last_args = args
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         self._check(self._lib.b2s_project_bwd_exchange(
-            *args, self.n_shared, self.world, self.rank, self.rows_cap, self.scale, self.epoch, phases,
+            *args, self.n_shared, int(self.exchange_colors), self.world, self.rank, self.rows_cap, self.scale,
+            self.epoch, phases,
             self._ptr_array(self.stage_ptrs), self._ptr_array(self.arena_ptrs), self._ptr_array(self.flag_ptrs),
             C.c_void_p(self.status.data_ptr()), stream),
             "b2s_project_bwd_exchange")

@@ -161,9 +161,13 @@ class _Project(torch.autograd.Function):
             else:
                 ex.launch(ex._phases, args)
             gv = ex.grad_views(N)
-            if N > ex.n_shared:
-                gv["colors"][ex.n_shared:] = v_colpack[ex.n_shared:, :d_in]
-            return (gv["means"], gv["quats"], gv["scales"], gv["opacities"], gv["colors"], v_view) + (None,) * 12
+            if not ex.exchange_colors:
+                v_colors = v_colpack[:, :d_in]  # view-dependent colours: reduced at their own leaves by the caller
+            else:
+                v_colors = gv["colors"]
+                if N > ex.n_shared:
+                    v_colors[ex.n_shared:] = v_colpack[ex.n_shared:, :d_in]
+            return (gv["means"], gv["quats"], gv["scales"], gv["opacities"], v_colors, v_view) + (None,) * 12
         v_means = torch.empty_like(means)
         v_quats = torch.empty_like(quats)
         v_scales = torch.empty_like(scales)

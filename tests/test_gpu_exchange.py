@@ -31,10 +31,11 @@ def _loss(t, cam, W, H, w_c, w_a):
     return (r * w_c).sum() + (a * w_a).sum()
 
 
-@pytest.mark.parametrize("world,n,n_tail,d_in,average", [(1, 1000, 0, 3, True), (2, 3001, 0, 3, True),
-                                                         (4, 5000, 37, 3, False), (3, 2049, 5, 6, True),
-                                                         (8, 20000, 0, 3, True)])
-def test_exchange_matches_sum_of_plain_backwards(cuda_device, world, n, n_tail, d_in, average):
+@pytest.mark.parametrize("world,n,n_tail,d_in,average,xcol", [(1, 1000, 0, 3, True, True), (2, 3001, 0, 3, True, True),
+                                                              (4, 5000, 37, 3, False, True), (3, 2049, 5, 6, True, True),
+                                                              (8, 20000, 0, 3, True, True), (2, 3001, 0, 3, True, False),
+                                                              (3, 2049, 5, 6, False, False)])
+def test_exchange_matches_sum_of_plain_backwards(cuda_device, world, n, n_tail, d_in, average, xcol):
     from mtgs_b200.parallel import GradExchange
     dev = cuda_device
     W, H = 320, 192
@@ -51,18 +52,26 @@ def test_exchange_matches_sum_of_plain_backwards(cuda_device, world, n, n_tail, 
         plain.append({k: t[k].grad.detach().clone() for k in NAMES})
     scale = 1.0 / world if average else 1.0
     # exchange path: phase 1 of every rank, then the reduce / broadcast / wait phases
-    exs = GradExchange.local_ranks(world, n_shared, d_in, rows_cap=n, average=average, device=dev)
+    exs = GradExchange.local_ranks(world, n_shared, d_in, rows_cap=n, average=average, device=dev, exchange_colors=xcol)
     try:
+        local_colors = []
         for r in range(world):
             t = _inputs(cams[0], dev)
             with exs[r].active():
                 _loss(t, cams[r], W, H, w_c, w_a).backward()
+            local_colors.append(t["colors"].grad.detach().clone())
         GradExchange.finish_all(exs)
         torch.cuda.synchronize()
         for r in range(world):
             exs[r].check()
             got = exs[r].grad_views(n)
+            if not xcol:  # view-dependent colours: the gradient stays local and unscaled
+                assert "colors" not in got
+                tol = 2e-4 * float(plain[r]["colors"].abs().max()) + 1e-9
+                assert float((local_colors[r] - plain[r]["colors"]).abs().max()) <= tol
             for k in NAMES:
+                if k == "colors" and not xcol:
+                    continue
                 want = sum(p[k][:n_shared] for p in plain) * scale
                 g = got[k][:n_shared]
                 tol = 2e-4 * float(want.abs().max()) + 1e-9

@@ -13,7 +13,7 @@ def test_multitraversal_training_improves_psnr(cuda_device):
     spec = importlib.util.spec_from_file_location("train_mt", os.path.join(ROOT, "examples", "train_multitraversal.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    first, final = mod.main(["--n", "20000", "--traversals", "2", "--width", "320", "--height", "192", "--iters", "80",
+    first, final = mod.main(["--n-gauss", "20000", "--traversals", "2", "--width", "320", "--height", "192", "--iters", "80",
                              "--log-every", "40"])
     assert set(first) == set(final) == {0, 1}
     for t in first:
