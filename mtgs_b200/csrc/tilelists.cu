@@ -391,7 +391,10 @@ static bool tl_layout(const long long *t, int tile_w, int tile_h, TlGeom &g, TlL
 extern "C" size_t b2s_bin_tiles_workspace_bytes(const long long *totals_host, int tile_w, int tile_h) {
     TlGeom g;
     TlLayout L;
-    if (!totals_host || !tl_layout(totals_host, tile_w, tile_h, g, L)) return 0;
+    if (!totals_host) return 0;
+    for (int k = 0; k < 5; ++k)
+        if (totals_host[k] < 0 || totals_host[k] >= (1LL << 31)) return 0;
+    if (!tl_layout(totals_host, tile_w, tile_h, g, L)) return 0;
     return L.total;
 }
 

@@ -135,3 +135,45 @@ def test_grad_exchange_needs_cuda_and_never_falls_back():
         import pytest
         with pytest.raises(Exception):
             GradExchange(n_shared=1024, d_in=3)
+
+
+def test_tile_list_workspace_sizing_is_host_only_and_monotone():
+    """b2s_bin_tiles_workspace_bytes is pure host arithmetic over the five list-size totals (M, S, E1, E3, n_vis):
+    callable without a GPU, monotone in every total, 0 for unsupported tile grids (more than 512 tiles per axis
+    would need more than 32 children per list)."""
+    import ctypes as C
+    from mtgs_b200 import _lib
+    lib = _lib.load()
+
+    def ws(tot, tw, th):
+        return int(lib.b2s_bin_tiles_workspace_bytes((C.c_longlong * 5)(*tot), tw, th))
+
+    base = [19_184_915, 3_727_319, 1_500_000, 4_700_000, 1_206_176]  # the bench workload's totals (1080p)
+    w0 = ws(base, 120, 68)
+    assert 0 < w0 < 1 << 31
+    for k in range(5):
+        bigger = list(base)
+        bigger[k] *= 2
+        assert ws(bigger, 120, 68) >= w0
+    assert ws(base, 240, 135) > 0          # 4K: 16-row groups, 15 column groups
+    assert ws(base, 275, 19) > 0 and ws(base, 19, 275) > 0   # > 256 tiles along one axis
+    assert ws([0, 0, 0, 0, 0], 4, 3) > 0   # empty scene still has offset tables
+    assert ws(base, 2000, 68) == 0 and ws(base, 120, 2000) == 0 and ws(base, 0, 68) == 0
+    assert ws([-1, 0, 0, 0, 0], 120, 68) == 0
+    assert int(lib.b2s_bin_depth_workspace_bytes(0)) > 0
+    assert int(lib.b2s_bin_depth_workspace_bytes(3_000_000)) > int(lib.b2s_bin_depth_workspace_bytes(1_000_000))
+
+
+def test_padded_channels_and_lazy_meta():
+    import pytest
+    from mtgs_b200.rendering import Meta, padded_channels
+    assert [padded_channels(c) for c in range(1, 9)] == [4, 4, 4, 4, 8, 8, 8, 8]  # MTGS uses 3, 4, 6, 7 (Appendix B)
+    with pytest.raises(NotImplementedError):
+        padded_channels(9)
+    m = Meta(a=1)
+    calls = []
+    m._lazy = lambda: calls.append(1) or "ids"
+    assert m.get("isect_ids") == "ids" and m["isect_ids"] == "ids" and len(calls) == 1  # built once, on first access
+    assert m.get("missing", 7) == 7
+    with pytest.raises(KeyError):
+        m["missing"]
