@@ -21,12 +21,11 @@ from . import _lib
 
 
 def _fspecial_gauss_1d(size: int, sigma: float) -> Tensor:
-    """1-D Gaussian window, shape (1, 1, size) (reference ssim.py:11-25)."""
-    coords = torch.arange(size, dtype=torch.float)
-    coords -= size // 2
-    g = torch.exp(-(coords ** 2) / (2 * sigma ** 2))
-    g /= g.sum()
-    return g.unsqueeze(0).unsqueeze(0)
+    """Normalised 1-D Gaussian window of ``size`` taps, shape (1, 1, size) -- same values as the reference helper of
+    this name (ssim.py:11-25)."""
+    offsets = torch.arange(size, dtype=torch.float32) - float(size // 2)
+    weights = torch.exp(offsets.square().neg() / (2 * sigma ** 2))
+    return (weights / weights.sum()).view(1, 1, size)
 
 
 def _ptr(t: Optional[Tensor]):

@@ -39,6 +39,11 @@ def test_window_matches_reference_constants():
     w = ssim_ref.gauss_window(11, 1.5)
     assert abs(float(w.sum()) - 1.0) < 1e-6 and np.allclose(w, w[::-1]) and w.argmax() == 5
     np.testing.assert_allclose(w[5], 0.26601171, rtol=1e-5)  # centre tap of the 11 / 1.5 window
+    from mtgs_b200.ssim import _fspecial_gauss_1d
+    for size, sigma in ((11, 1.5), (7, 1.0), (15, 2.5)):
+        ours = _fspecial_gauss_1d(size, sigma)
+        assert tuple(ours.shape) == (1, 1, size)
+        np.testing.assert_allclose(ours.reshape(-1).numpy(), ssim_ref.gauss_window(size, sigma), rtol=1e-6)  # 1 ulp (exp)
 
 
 def test_host_mirror_signature_and_errors():
