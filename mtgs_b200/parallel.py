@@ -1,4 +1,9 @@
-"""Multi-GPU sharding of the hot path: one traversal camera per rank, all-reduce of shared-node gradients.
+"""Multi-GPU sharding of the hot path: one traversal camera per rank, exchange of the shared-node gradients.
+
+Two mechanisms: ``GradExchange`` (bottom of this file) fuses the exchange INTO the projection backward over NVLink
+peer memory and is what ``bench.py --gpus N`` measures; ``SharedGradArena`` is the library all-reduce after the
+backward that it replaces for the geometry gradients -- still the right tool for leaves whose Jacobian differs per
+rank (SH coefficients) and the baseline of ``bench.py --exchange nccl``.
 
 The reference has no working multi-GPU data path (DDP wiring at mtgs/scene_model/custom_pipeline.py:86-89 is
 unused).  The scheme here is the one BASELINE.json's north_star names:
