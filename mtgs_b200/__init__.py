@@ -39,3 +39,15 @@ def install_as_gsplat(force: bool = False) -> None:
     sys.modules["gsplat.rendering"] = rendering
     sys.modules["gsplat.cuda"] = _cuda
     sys.modules["gsplat.cuda._wrapper"] = _wrapper
+
+
+def install_as_mtgs_ssim(force: bool = False) -> None:
+    """Make ``from mtgs.utils.ssim import MaskedSSIM`` (mtgs/scene_model/mtgs_scene_graph.py:36) resolve to
+    ``mtgs_b200.ssim`` without touching the reference tree: the import system consults ``sys.modules`` for the
+    fully qualified submodule name before it looks inside the ``mtgs.utils`` package."""
+    name = "mtgs.utils.ssim"
+    if name in sys.modules and not force and not getattr(sys.modules[name], "__b200__", False):
+        raise RuntimeError(f"`{name}` is already imported; pass force=True to shadow it")
+    from . import ssim
+    ssim.__b200__ = True
+    sys.modules[name] = ssim

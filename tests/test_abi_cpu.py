@@ -177,3 +177,13 @@ def test_padded_channels_and_lazy_meta():
     assert m.get("missing", 7) == 7
     with pytest.raises(KeyError):
         m["missing"]
+
+
+def test_ssim_alias_resolves_the_mtgs_import():
+    import importlib
+    import sys
+    import mtgs_b200
+    mtgs_b200.install_as_mtgs_ssim()
+    mod = importlib.import_module("mtgs.utils.ssim") if "mtgs" in sys.modules else sys.modules["mtgs.utils.ssim"]
+    assert mod.MaskedSSIM.__module__ == "mtgs_b200.ssim" and mod.ssim.__module__ == "mtgs_b200.ssim"
+    mtgs_b200.install_as_mtgs_ssim()  # idempotent
