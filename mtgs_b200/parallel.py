@@ -332,3 +332,48 @@ class GradExchange:
         code = int(self.status.item())
         if code:
             raise RuntimeError(f"gradient exchange timed out waiting for a peer (phase code {code})")
+
+
+# ------------------------------------------------------------------------------------------------
+# Camera sampling per rank (SURVEY 8e "Partitioning")
+# ------------------------------------------------------------------------------------------------
+class RankTraversalSampler:
+    """Balanced multi-traversal camera sampler restricted to the traversals owned by one rank.
+
+    Reference: ``MultiTraversalBalancedSampler`` (mtgs/dataset/utils/sampler.py:27-58) first draws a not-yet-seen
+    traversal, then a not-yet-seen image of that traversal, refilling either pool when it runs empty.  With one
+    traversal camera per GPU every rank runs the same two-level draw over ITS traversals
+    (``traversal_of_rank``), so the union over ranks still visits every traversal equally often and every image
+    of a traversal once per pass.  With ``world_size == 1`` the draw order is the reference's, call for call, under
+    the same ``random`` seed (tests/test_parallel_cpu.py checks that against indices the reference produced).
+
+    ``travel_ids[i]`` is the traversal of image ``i`` (``dataparser_outputs.travel_ids`` in the reference)."""
+
+    def __init__(self, travel_ids: Sequence[int], rank: int = 0, world_size: int = 1, rng=None):
+        import random as _random
+        self._rng = rng if rng is not None else _random
+        ids = [int(t) for t in travel_ids]
+        all_traversals = set(ids)
+        ordered = list(all_traversals)  # same construction as the reference (set -> list)
+        mine = set(traversal_of_rank(rank, world_size, len(ordered)))
+        self.traversals = [t for k, t in enumerate(ordered) if k in mine]
+        if not self.traversals:
+            raise ValueError(f"rank {rank} of {world_size} owns no traversal ({len(ordered)} traversals in the data)")
+        self.traversal_indices = {t: [i for i, x in enumerate(ids) if x == t] for t in self.traversals}
+        self.traversal_counts = {t: len(v) for t, v in self.traversal_indices.items()}
+        self.unseen_traversals = list(self.traversals)
+        self.unseen_per_traversal_images = {t: list(v) for t, v in self.traversal_indices.items()}
+
+    def get_next_traversal(self) -> int:
+        t = self.unseen_traversals.pop(self._rng.randint(0, len(self.unseen_traversals) - 1))
+        if not self.unseen_traversals:
+            self.unseen_traversals = list(self.traversals)
+        return t
+
+    def get_next_image_idx(self) -> int:
+        t = self.get_next_traversal()
+        pool = self.unseen_per_traversal_images[t]
+        idx = pool.pop(self._rng.randint(0, len(pool) - 1))
+        if not pool:
+            self.unseen_per_traversal_images[t] = list(self.traversal_indices[t])
+        return idx

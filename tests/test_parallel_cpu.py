@@ -90,3 +90,41 @@ def test_arena_validation_and_single_process():
     assert traversal_of_rank(1, 4, 8) == [1, 5]
     with pytest.raises(ValueError):
         traversal_of_rank(4, 4, 8)
+
+
+def test_rank_sampler_reproduces_the_reference_draw_order_at_world_1():
+    """Pinned against sequences produced by the reference's own MultiTraversalBalancedSampler
+    (tests/golden/make_sampler_golden.py)."""
+    import json
+    import os
+    import random
+    from mtgs_b200.parallel import RankTraversalSampler
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sampler_reference_golden.json")))
+    for name, case in gold.items():
+        random.seed(case["seed"])
+        s = RankTraversalSampler(case["travel_ids"])
+        got = [s.get_next_image_idx() for _ in range(len(case["sequence"]))]
+        assert got == case["sequence"], name
+
+
+def test_rank_sampler_partitions_traversals_and_stays_balanced():
+    import random
+    from collections import Counter
+    from mtgs_b200.parallel import RankTraversalSampler
+    travel_ids = [0] * 5 + [1] * 3 + [2] * 8 + [3] * 4
+    seen_traversals = []
+    for rank in range(2):
+        s = RankTraversalSampler(travel_ids, rank=rank, world_size=2, rng=random.Random(rank))
+        seen_traversals.append(set(s.traversals))
+        draws = [s.get_next_image_idx() for _ in range(2 * 40)]
+        per_trav = Counter(travel_ids[i] for i in draws)
+        assert set(per_trav) == set(s.traversals)
+        assert len(set(per_trav.values())) == 1                      # every owned traversal drawn equally often
+        for t in s.traversals:                                       # one pass over a traversal visits each image once
+            n = s.traversal_counts[t]
+            first_pass = [i for i in draws if travel_ids[i] == t][:n]
+            assert sorted(first_pass) == s.traversal_indices[t]
+    assert seen_traversals[0].isdisjoint(seen_traversals[1]) and set.union(*seen_traversals) == {0, 1, 2, 3}
+    import pytest
+    with pytest.raises(ValueError):
+        RankTraversalSampler([0, 0, 1], rank=3, world_size=4)
