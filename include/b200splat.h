@@ -19,7 +19,8 @@
  *     scratch workspace are caller-owned; work is enqueued on `stream`;
  *   - return value: 0 on success, B2S_ERR_* (< 0) on argument errors,
  *     -(int)cudaError_t - 1000 on a CUDA launch error; b2s_error_string() names it;
- *   - thread-compatible: no mutable globals; one in-flight call per stream.
+ *   - thread-compatible: the only mutable global is the atomic diagnostic counter behind b2s_launch_count();
+ *     one in-flight call per stream.
  */
 #ifndef B200SPLAT_H
 #define B200SPLAT_H
@@ -87,8 +88,10 @@ int b2s_project_bwd(const float *means, const float *quats, const float *scales,
  * plain projection backward for the rank-local rows, the reduce of my shard + store of the result into every rank's
  * arena, and a stream-ordered wait.  When it has run, arena holds scale * sum over ranks for the shared rows and the
  * local gradient for the others.  *_ptrs_host are HOST arrays of `world` device pointers (this rank's own buffers at
- * index `rank`); epoch must increase by one per call on every rank; *status (device word) becomes non-zero if a
- * wait timed out (~2 s) instead of hanging the GPU.  Colour gradients of the rank-local rows are left in v_colpack.
+ * index `rank`); epoch must increase by one per call on every rank.  The waits block like a library collective (ranks
+ * must stay in lock-step) and give up after timeout_s seconds (<= 0: 120 s): then *status (a word the device can write;
+ * pinned host memory lets the host poll it without synchronising) becomes non-zero AND the shared rows of the arena are
+ * filled with NaN -- never stale or partial gradients.  Colour gradients of the rank-local rows are left in v_colpack.
  * phases: bit 0 = projection backward + peer stores + "partials delivered" flags, bit 1 = reduce + broadcast,
  * bit 2 = "result delivered" flags, bit 3 = final wait (15 = all; the split exists so that a test can play several
  * ranks on one GPU from one stream). */
@@ -105,7 +108,7 @@ int b2s_project_bwd_exchange(const float *means, const float *quats, const float
                              const float *v_means2d, int v_means2d_stride, const float *v_geo,
                              const float *v_colpack, float *v_viewmat, int n_shared, int exchange_colors,
                              int world, int rank, long long rows_cap, float scale, unsigned epoch, int phases,
-                             const unsigned long long *stage_ptrs_host,
+                             float timeout_s, const unsigned long long *stage_ptrs_host,
                              const unsigned long long *arena_ptrs_host,
                              const unsigned long long *flag_ptrs_host, unsigned *status,
                              b2s_stream_t stream);

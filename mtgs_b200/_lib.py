@@ -28,7 +28,7 @@ SIGNATURES = {
     "b2s_ipc_import": (_i, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "b2s_ipc_close": (_i, [_vp]),
     "b2s_project_bwd_exchange": (_i, [_vp] * 6 + [_i] * 3 + [_f] + [_i] * 4 + [_vp] * 4 + [_i] + [_vp] * 3 +
-                                 [_i, _i, _i, _i, _ll, _f, C.c_uint, _i] + [_vp] * 4 + [_vp]),
+                                 [_i, _i, _i, _i, _ll, _f, C.c_uint, _i, _f] + [_vp] * 4 + [_vp]),
     "b2s_bin_depth_workspace_bytes": (_sz, [_i]),
     "b2s_bin_sort_depth": (_i, [_vp] * 3 + [_i, _i, _i] + [_vp] * 4 + [_sz, _vp]),
     "b2s_bin_tiles_workspace_bytes": (_sz, [C.POINTER(_ll), _i, _i]),
@@ -66,7 +66,10 @@ def load() -> C.CDLL:
 def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = load().b2s_error_string(rc)
-        raise RuntimeError(f"{what} failed: {msg.decode() if msg else rc} (code {rc})")
+        text = f"{what} failed: {msg.decode() if msg else rc} (code {rc})"
+        if rc == -2:  # B2S_ERR_UNSUPPORTED: a configuration this build does not instantiate
+            raise NotImplementedError(text)
+        raise RuntimeError(text)
 
 
 def launch_count() -> int:

@@ -1,11 +1,15 @@
 // Library-level entry points of libb200splat.so (version, error strings, launch counter).
+#include <atomic>
+
 #include "common.cuh"
 
-long long g_b2s_launches = 0;
+static std::atomic<long long> g_b2s_launches{0};
 
-extern "C" int b2s_version(void) { return 100; }
+void b2s_count_launch(int n) { g_b2s_launches.fetch_add(n, std::memory_order_relaxed); }
 
-extern "C" long long b2s_launch_count(void) { return g_b2s_launches; }
+extern "C" int b2s_version(void) { return 200; }
+
+extern "C" long long b2s_launch_count(void) { return g_b2s_launches.load(std::memory_order_relaxed); }
 
 extern "C" const char *b2s_error_string(int code) {
     switch (code) {

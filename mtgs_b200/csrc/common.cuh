@@ -11,11 +11,12 @@
 #define B2S_LOG2E 1.4426950408889634f
 #define B2S_LN2 0.6931471805599453f
 
-extern long long g_b2s_launches;  // defined in api.cu
+// Diagnostic launch counter (api.cu): the library's only mutable global; atomic, never read by a kernel launch path.
+void b2s_count_launch(int n);
 
 static inline int b2s_check_launch() {
     cudaError_t e = cudaGetLastError();
-    ++g_b2s_launches;
+    b2s_count_launch(1);
     return e == cudaSuccess ? B2S_OK : -(int)e - 1000;
 }
 
@@ -65,6 +66,7 @@ struct B2sExchange {
     int d_col;              // colour floats per row that take part in the exchange (d_in, or 0: colours stay local)
     long long slot_floats;  // floats per (owner, source) staging slot = (11 + d_col) * shard
     unsigned epoch;         // step counter written into the flags
+    long long timeout_cycles;  // spin-loop budget of the flag waits (SM clock cycles)
     float *stage[B2S_MAX_WORLD];     // stage[r]: rank r's staging buffer [world][slot_floats] (peer-mapped)
     float *arena[B2S_MAX_WORLD];     // arena[r]: rank r's reduced-gradient arena (peer-mapped)
     unsigned *flags[B2S_MAX_WORLD];  // flags[r]: rank r's flag words [2 phases][B2S_MAX_WORLD] (peer-mapped)

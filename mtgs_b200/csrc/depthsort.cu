@@ -286,9 +286,10 @@ extern "C" int b2s_bin_sort_depth(const uint32_t *sort_keys, const int32_t *tile
                     (void *)&totals,    (void *)&n_vis};
     cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_depth_sort_coop, dim3(G), dim3(DS_THREADS), args,
                                                 DS_SMEM, st);
-    ++g_b2s_launches;
-    if (e != cudaSuccess) return -(int)e - 1000;
+    if (e != cudaSuccess) {
+        b2s_count_launch(1);
+        return -(int)e - 1000;
+    }
     B2S_LAUNCH_CHECK();
-    --g_b2s_launches;  // counted once
     return B2S_OK;
 }

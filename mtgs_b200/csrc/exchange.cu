@@ -20,8 +20,11 @@
 //
 // Rows at or beyond n_shared (rank-local nodes, e.g. the vehicles of this rank's traversal; reference
 // rigid_node.py:87, 259-261) are written to the local arena by the plain kernel and never leave the GPU.
-// Flags carry a monotonically increasing epoch, so nothing is reset between steps; every spin loop gives up after
-// ~2 s and reports through a status word instead of hanging the GPU.
+// Flags carry a monotonically increasing epoch, so nothing is reset between steps.  The spin loops block like a library
+// collective would (ranks must stay in lock-step); they give up only after the caller's timeout (default 120 s) so that a
+// dead peer cannot hang the GPU for ever.  A timeout is LOUD: the status word (which may live in pinned host memory, so
+// the host reads it without synchronising) becomes non-zero and the reduced rows of this rank's arena are filled with
+// NaN, so an optimizer can never silently step on stale or partial gradients.
 #include <cstring>
 
 #include "common.cuh"
@@ -33,16 +36,28 @@ int b2s_launch_project_bwd_exchange(const float *means, const float *quats, cons
                                     const float *v_geo, const float *v_colpack, float *v_viewmat, const B2sExchange &ex,
                                     cudaStream_t st);
 
-constexpr long long EX_TIMEOUT_CYCLES = 4000000000LL;  // ~2 s at 1.9 GHz
-
 // spin until *flag == epoch; false on timeout
-__device__ __forceinline__ bool ex_wait_flag(const volatile unsigned *flag, unsigned epoch) {
+__device__ __forceinline__ bool ex_wait_flag(const volatile unsigned *flag, unsigned epoch, long long timeout_cycles) {
     const long long t0 = clock64();
     while (*flag != epoch) {
-        if (clock64() - t0 > EX_TIMEOUT_CYCLES) return false;
+        if (clock64() - t0 > timeout_cycles) return false;
         __nanosleep(200);
     }
     return true;
+}
+
+// NaN-fill of the shared rows of this rank's arena (timeout path only)
+__device__ void ex_poison_arena(const B2sExchange &ex, int n_shared, long long rows_cap) {
+    const float nan = __int_as_float(0x7fc00000);
+    float *a = ex.arena[ex.rank];
+    const int widths[5] = {3, 4, 3, 1, ex.d_col};
+    long long blk = 0;
+    for (int p = 0; p < 5; ++p) {
+        const long long n = (long long)widths[p] * n_shared;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+            a[blk * rows_cap + i] = nan;
+        blk += widths[p];
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -52,14 +67,17 @@ k_grad_reduce_bcast(const B2sExchange ex, int n_shared, long long rows_cap, floa
     if (threadIdx.x == 0) s_ok = 1u;
     __syncthreads();
     if (threadIdx.x < ex.world) {
-        if (!ex_wait_flag(ex.flags[ex.rank] + threadIdx.x, ex.epoch)) {
+        if (!ex_wait_flag(ex.flags[ex.rank] + threadIdx.x, ex.epoch, ex.timeout_cycles)) {
             s_ok = 0u;
-            atomicExch(status, 1u);
+            *(volatile unsigned *)status = 1u;
+            __threadfence_system();
         }
     }
     __syncthreads();
     __threadfence();
-    if (s_ok) {
+    if (!s_ok) {
+        ex_poison_arena(ex, n_shared, rows_cap);
+    } else {
         const long long n4 = ex.slot_floats >> 2;
         const float *mine = ex.stage[ex.rank];
         const long long b1 = 3LL * ex.shard, b2 = 7LL * ex.shard, b3 = 10LL * ex.shard, b4 = 11LL * ex.shard;
@@ -105,12 +123,20 @@ k_exchange_signal(const B2sExchange ex, int phase) {
 }
 
 // One warp: wait until every rank has published "my reduced rows are in every arena" (phase 1).
-__global__ void __launch_bounds__(32)
-k_exchange_wait(const B2sExchange ex, unsigned *__restrict__ status) {
+__global__ void __launch_bounds__(256)
+k_exchange_wait(const B2sExchange ex, int n_shared, long long rows_cap, unsigned *__restrict__ status) {
+    __shared__ unsigned s_ok;
+    if (threadIdx.x == 0) s_ok = 1u;
+    __syncthreads();
     if (threadIdx.x < ex.world) {
-        if (!ex_wait_flag(ex.flags[ex.rank] + B2S_MAX_WORLD + threadIdx.x, ex.epoch)) atomicExch(status, 2u);
+        if (!ex_wait_flag(ex.flags[ex.rank] + B2S_MAX_WORLD + threadIdx.x, ex.epoch, ex.timeout_cycles)) {
+            s_ok = 0u;
+            *(volatile unsigned *)status = 2u;
+        }
     }
     __threadfence_system();
+    __syncthreads();
+    if (!s_ok) ex_poison_arena(ex, n_shared, rows_cap);  // a peer's rows never arrived: nothing in the arena is trustworthy
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -160,9 +186,9 @@ extern "C" int b2s_project_bwd_exchange(
     const float *K, int N, int W, int H, float eps2d, int calc_comp, int d_in, int with_depth, int cdim,
     const int32_t *radii, const float *geo, const float *comps, const float *v_means2d, int v_means2d_stride,
     const float *v_geo, const float *v_colpack, float *v_viewmat, int n_shared, int exchange_colors, int world, int rank,
-    long long rows_cap, float scale, unsigned epoch, int phases, const unsigned long long *stage_ptrs_host,
-    const unsigned long long *arena_ptrs_host, const unsigned long long *flag_ptrs_host, unsigned *status,
-    b2s_stream_t stream) {
+    long long rows_cap, float scale, unsigned epoch, int phases, float timeout_s,
+    const unsigned long long *stage_ptrs_host, const unsigned long long *arena_ptrs_host,
+    const unsigned long long *flag_ptrs_host, unsigned *status, b2s_stream_t stream) {
     if (N < 0 || n_shared < 0 || n_shared > N || world < 1 || world > B2S_MAX_WORLD || rank < 0 || rank >= world)
         return B2S_ERR_ARG;
     if (rows_cap < N || (rows_cap & 3) || d_in < 0 || d_in > 8) return B2S_ERR_ARG;
@@ -178,6 +204,7 @@ extern "C" int b2s_project_bwd_exchange(
     ex.d_col = exchange_colors ? d_in : 0;
     ex.slot_floats = (long long)(11 + ex.d_col) * ex.shard;
     ex.epoch = epoch;
+    ex.timeout_cycles = (long long)((timeout_s > 0.f ? (double)timeout_s : 120.0) * 1.9e9);
     for (int r = 0; r < world; ++r) {
         ex.stage[r] = (float *)(uintptr_t)stage_ptrs_host[r];
         ex.arena[r] = (float *)(uintptr_t)arena_ptrs_host[r];
@@ -217,7 +244,7 @@ extern "C" int b2s_project_bwd_exchange(
         B2S_LAUNCH_CHECK();
     }
     if (n_shared > 0 && (phases & 8)) {
-        k_exchange_wait<<<1, 32, 0, st>>>(ex, status);
+        k_exchange_wait<<<1, 256, 0, st>>>(ex, n_shared, rows_cap, status);
         B2S_LAUNCH_CHECK();
     }
     return B2S_OK;

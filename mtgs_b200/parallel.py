@@ -166,14 +166,24 @@ class GradExchange:
         with ex.active():
             loss.backward()          # .grad of the inputs already holds the mean over all ranks
 
-    The gradient tensors handed to autograd alias the exchange arena: they are valid until the next exchange
-    (consume them -- optimizer step, or clone -- before the next ``backward`` under ``active()``).
+    Contract (the same as for a library collective): every rank must call the exchange once per step, in lock-step.
+    The waits block (up to ``timeout_s``, default 120 s); a timeout is loud -- the shared rows come back as NaN, the
+    next ``launch`` / ``check()`` raises.  ``n_shared`` may change between steps (densification / pruning of the
+    shared nodes, reference vanilla_gaussian_splatting.py:476-577): call ``set_n_shared`` on every rank after
+    ``refinement_after``; it validates that all ranks agree.  One exchange per ``active()`` context: a second
+    ``rasterization`` backward under the same context raises instead of overwriting the first one's gradients.
+
+    By default the gradients handed to autograd are CLONES of the arena slices.  ``zero_copy=True`` hands out views of
+    the arena instead (saves one 56 B / Gaussian copy): they are valid until the next exchange only, so the caller
+    must consume them (optimizer step) before the next ``backward`` and must not keep ``.grad`` alive across steps
+    (``zero_grad(set_to_none=True)``).
     """
 
     MAX_WORLD = 8
 
     def __init__(self, n_shared: int, d_in: int, rows_cap: Optional[int] = None, group=None, average: bool = True,
-                 device: Optional[torch.device] = None, exchange_colors: bool = True, _local: Optional[tuple] = None):
+                 device: Optional[torch.device] = None, exchange_colors: bool = True, zero_copy: bool = False,
+                 timeout_s: float = 120.0, _local: Optional[tuple] = None):
         from . import _lib
         import ctypes as C
         self._lib = lib = _lib.load()
@@ -193,10 +203,14 @@ class GradExchange:
         if self.rows_cap < self.n_shared:
             raise ValueError("rows_cap < n_shared")
         self.scale = 1.0 / self.world if average else 1.0
+        self.zero_copy = bool(zero_copy)
+        self.timeout_s = float(timeout_s)
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.shard = int(lib.b2s_exchange_shard_rows(self.n_shared, self.world))
+        # the staging buffer is sized for the largest shard n_shared can grow to (rows_cap)
+        self.shard_cap = int(lib.b2s_exchange_shard_rows(self.rows_cap, self.world))
         self.F = 11 + (self.d_in if self.exchange_colors else 0)
-        self._sizes = (self.world * self.F * self.shard * 4, self.F * self.rows_cap * 4, 256)
+        self._sizes = (self.world * self.F * self.shard_cap * 4, self.F * self.rows_cap * 4, 256)
         self._own = []
         with torch.cuda.device(self.device):
             for nbytes in self._sizes:
@@ -209,8 +223,11 @@ class GradExchange:
         self.stage_ptrs[self.rank], self.arena_ptrs[self.rank], self.flag_ptrs[self.rank] = self._own
         self._imported = []
         self.arena = torch.as_tensor(_DevMem(self._own[1], self.F * self.rows_cap), device=self.device)
-        self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # status word in pinned host memory: the kernels write it through the unified address space, the host reads
+        # it without synchronising (checked at the start of every launch)
+        self.status = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.epoch = 0
+        self._launches_in_ctx = 0
         if _local is None and self.world > 1:
             self._rendezvous()
 
@@ -264,6 +281,8 @@ class GradExchange:
     _phases = 15
 
     def close(self) -> None:
+        if not getattr(self, "_own", None) and not getattr(self, "_imported", None):
+            return
         with torch.cuda.device(self.device):
             torch.cuda.synchronize()
             for p in self._imported:
@@ -271,6 +290,34 @@ class GradExchange:
             for p in self._own:
                 self._lib.b2s_peer_free(p)
         self._imported, self._own = [], []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown
+            pass
+
+    def set_n_shared(self, n_shared: int) -> None:
+        """Number of replicated rows from now on (after densification / pruning of the shared nodes).  Collective:
+        every rank must call it with the same value (validated here)."""
+        n_shared = int(n_shared)
+        if n_shared < 0 or n_shared > self.rows_cap:
+            raise ValueError(f"n_shared={n_shared} outside [0, rows_cap={self.rows_cap}]; build a larger GradExchange")
+        if self.world > 1 and dist.is_available() and dist.is_initialized() and self._phases == 15:
+            t = torch.tensor([n_shared, -n_shared], device=self.device, dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            if int(t[0]) != n_shared or int(-t[1]) != n_shared:
+                raise RuntimeError(f"ranks disagree on n_shared (this rank {n_shared}, range "
+                                   f"[{int(-t[1])}, {int(t[0])}])")
+        self.n_shared = n_shared
+        self.shard = int(self._lib.b2s_exchange_shard_rows(self.n_shared, self.world))
 
     # -- per step -------------------------------------------------------------------------------
     def active(self):
@@ -281,6 +328,7 @@ class GradExchange:
                 global _ACTIVE_EXCHANGE
                 self_inner.prev = _ACTIVE_EXCHANGE
                 _ACTIVE_EXCHANGE = ex
+                ex._launches_in_ctx = 0
                 return ex
 
             def __exit__(self_inner, *exc):
@@ -306,7 +354,14 @@ class GradExchange:
     def launch(self, phases: int, args: Optional[tuple] = None) -> None:
         """Enqueue the selected phases on the current stream (``args`` = the projection-backward operands)."""
         import ctypes as C
+        if int(self.status[0]) != 0:  # pinned host word: no synchronisation
+            raise RuntimeError(f"gradient exchange timed out waiting for a peer in an earlier step (phase code "
+                               f"{int(self.status[0])}); its shared gradients were NaN-filled")
         if phases & 1:
+            if self._phases == 15 and self._launches_in_ctx > 0:
+                raise RuntimeError("a second rasterization backward ran under the same GradExchange.active() context: "
+                                   "its gradients would overwrite the first one's (one exchange per step)")
+            self._launches_in_ctx += 1
             self.epoch += 1
         if args is None:
             args = self._last_args
@@ -314,7 +369,7 @@ class GradExchange:
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         self._check(self._lib.b2s_project_bwd_exchange(
             *args, self.n_shared, int(self.exchange_colors), self.world, self.rank, self.rows_cap, self.scale,
-            self.epoch, phases,
+            self.epoch, phases, self.timeout_s,
             self._ptr_array(self.stage_ptrs), self._ptr_array(self.arena_ptrs), self._ptr_array(self.flag_ptrs),
             C.c_void_p(self.status.data_ptr()), stream),
             "b2s_project_bwd_exchange")
@@ -329,7 +384,8 @@ class GradExchange:
 
     def check(self) -> None:
         """Synchronise and raise if a peer never arrived (a spin loop timed out)."""
-        code = int(self.status.item())
+        torch.cuda.synchronize(self.device)
+        code = int(self.status[0])
         if code:
             raise RuntimeError(f"gradient exchange timed out waiting for a peer (phase code {code})")
 

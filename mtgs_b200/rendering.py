@@ -161,6 +161,8 @@ class _Project(torch.autograd.Function):
             else:
                 ex.launch(ex._phases, args)
             gv = ex.grad_views(N)
+            if not ex.zero_copy:
+                gv = {k: v.clone() for k, v in gv.items()}
             if not ex.exchange_colors:
                 v_colors = v_colpack[:, :d_in]  # view-dependent colours: reduced at their own leaves by the caller
             else:
@@ -201,10 +203,11 @@ class _Blend(torch.autograd.Function):
                                          _ptr(last_ids), _stream()), "b2s_blend_fwd")
         ctx.save_for_backward(means2d, geo, colpack, offsets, flatten_ids, render, alpha, last_ids)
         ctx.cfg = (W, H, tile_w, tile_h, cdim, d_out, ed, absgrad)
-        return render, alpha
+        ctx.mark_non_differentiable(last_ids)
+        return render, alpha, last_ids
 
     @staticmethod
-    def backward(ctx, v_render, v_alpha):
+    def backward(ctx, v_render, v_alpha, _v_last=None):
         lib = _lib.load()
         means2d, geo, colpack, offsets, flatten_ids, render, alpha, last_ids = ctx.saved_tensors
         W, H, tile_w, tile_h, cdim, d_out, ed, absgrad = ctx.cfg
@@ -287,11 +290,13 @@ def _rasterize_one(means, quats, scales, opacities, colors, viewmat, K, width, h
         means, quats, scales, opacities, cols, viewmat, K, width, height, tile_w, tile_h, float(eps2d),
         float(near_plane), float(far_plane), float(radius_clip), calc_comp, with_depth, cdim)
     flatten_ids, offsets = _bin(rects, tiles, keys, tile_w, tile_h)
-    render, alpha = _Blend.apply(means2d, geo, colpack, offsets, flatten_ids, width, height, tile_w, tile_h, cdim,
-                                 d_out, ed, bool(absgrad))
+    render, alpha, last_ids = _Blend.apply(means2d, geo, colpack, offsets, flatten_ids, width, height, tile_w, tile_h,
+                                           cdim, d_out, ed, bool(absgrad))
+    # keys with a leading underscore are not part of upstream's info dict (bench.py reads them for K_pairs)
     meta = dict(radii=radii.unsqueeze(0), means2d=means2d, depths=depths.unsqueeze(0),
                 conics=geo.detach()[:, :3].unsqueeze(0), opacities=geo.detach()[:, 3].unsqueeze(0),
-                tiles_per_gauss=tiles.unsqueeze(0), flatten_ids=flatten_ids, isect_offsets=offsets.unsqueeze(0))
+                tiles_per_gauss=tiles.unsqueeze(0), flatten_ids=flatten_ids, isect_offsets=offsets.unsqueeze(0),
+                _last_ids=last_ids, _walk_ids=flatten_ids, _walk_offsets=offsets)
     return render, alpha, meta
 
 
@@ -324,6 +329,10 @@ def rasterization(
 ) -> Tuple[Tensor, Tensor, Dict]:
     """Rasterize 3D Gaussians to ``(render_colors [C,H,W,D(+1)], render_alphas [C,H,W,1], meta)``.
 
+    ``info["depths"]`` is not differentiable here (gradient reaches the depths through the blended depth channel of
+    ``RGB+D`` / ``RGB+ED`` only, which is the only way MTGS uses them).  With ``C > 1`` cameras ``info["means2d"]``
+    is a concatenation of the per-camera tensors and carries no ``.grad``.
+
     Same contract as upstream for the argument combinations MTGS uses:
     ``packed=False, tile_size=16, sparse_grad=False``, ``render_mode`` in RGB / RGB+D / RGB+ED / D / ED,
     ``rasterize_mode`` classic / antialiased, optional ``absgrad`` and ``backgrounds``.  Other combinations
@@ -345,6 +354,14 @@ def rasterization(
         raise NotImplementedError("only tile_size=16 is built (MTGS: BLOCK_WIDTH = 16, mtgs_scene_graph.py:640)")
     if sparse_grad or distributed or covars is not None or camera_model != "pinhole":
         raise NotImplementedError("sparse_grad / distributed / covars / non-pinhole cameras are not built")
+    if near_plane < 0:
+        # the depth sort key is the fp32 bit pattern of z, which orders correctly for z >= 0 only (upstream compares
+        # the bits as a signed integer); MTGS passes near_plane = 0.01 (mtgs_scene_graph.py:653)
+        raise NotImplementedError("near_plane < 0 is not built")
+    if C_ > 1 and absgrad:
+        # upstream attaches .absgrad to ONE [C, N, 2] means2d tensor; here cameras are rendered one by one and
+        # info["means2d"] is a concatenation outside the graph.  MTGS renders one camera per call (:548).
+        raise NotImplementedError("absgrad with more than one camera is not built (MTGS uses C = 1)")
     _need_cuda(means, quats, scales, opacities, colors, viewmats, Ks)
     if sh_degree is None:
         assert (colors.dim() == 2 and colors.shape[0] == N) or (colors.dim() == 3 and colors.shape[:2] == (C_, N)), \

@@ -203,6 +203,7 @@ static inline void tile_rect(float mx, float my, int32_t radius, int tile_size, 
 int64_t orc_isect_count(const float *means2d, const int32_t *radii, int N, int tile_size,
                         int tile_w, int tile_h, int32_t *tiles_per_gauss) {
     int64_t total = 0;
+#pragma omp parallel for schedule(static) reduction(+ : total)
     for (int g = 0; g < N; ++g) {
         if (radii[g] <= 0) { tiles_per_gauss[g] = 0; continue; }
         int x0, y0, x1, y1;
@@ -227,7 +228,20 @@ void orc_isect_emit(const float *means2d, const int32_t *radii, const float *dep
                     int32_t *flatten_ids) {
     int tile_n_bits = orc_tile_bits(tile_w * tile_h);
     (void)tile_n_bits; /* camera id is 0 for C = 1, so its field is all zeros */
-    int64_t cur = 0;
+    /* start of every Gaussian's run = exclusive scan of its rectangle area (emission order = Gaussian order) */
+    int64_t *first = (int64_t *)malloc(sizeof(int64_t) * ((size_t)N + 1));
+    first[0] = 0;
+    for (int g = 0; g < N; ++g) {
+        int64_t n = 0;
+        if (radii[g] > 0) {
+            int x0, y0, x1, y1;
+            tile_rect(means2d[2 * g], means2d[2 * g + 1], radii[g], tile_size, tile_w, tile_h, &x0,
+                      &y0, &x1, &y1);
+            n = (int64_t)(y1 - y0) * (x1 - x0);
+        }
+        first[g + 1] = first[g] + n;
+    }
+#pragma omp parallel for schedule(dynamic, 1024)
     for (int g = 0; g < N; ++g) {
         if (radii[g] <= 0) continue;
         int x0, y0, x1, y1;
@@ -236,6 +250,7 @@ void orc_isect_emit(const float *means2d, const int32_t *radii, const float *dep
         int32_t dbits;
         memcpy(&dbits, depths + g, 4);
         int64_t depth_enc = (int64_t)dbits; /* upstream sign-extends an int32 view */
+        int64_t cur = first[g];
         for (int i = y0; i < y1; ++i)
             for (int j = x0; j < x1; ++j) {
                 int64_t tile_id = (int64_t)i * tile_w + j;
@@ -244,6 +259,7 @@ void orc_isect_emit(const float *means2d, const int32_t *radii, const float *dep
                 ++cur;
             }
     }
+    free(first);
 }
 
 /* stable LSD radix sort of (int64 key, int32 value) on bits [0, end_bit).
@@ -254,22 +270,45 @@ void orc_sort_pairs(int64_t M, int end_bit, int64_t *keys, int32_t *vals) {
     int32_t *v2 = (int32_t *)malloc(sizeof(int32_t) * (size_t)M);
     int64_t *ka = keys, *kb = k2;
     int32_t *va = vals, *vb = v2;
+    int nt = orc_num_threads();
+    if (nt < 1) nt = 1;
+    if ((int64_t)nt > M) nt = (int)M;
+    const int NB = 1 << 11;
+    int64_t *cnt = (int64_t *)malloc(sizeof(int64_t) * (size_t)nt * NB);
     for (int shift = 0; shift < end_bit; shift += 11) {
         int bits = end_bit - shift < 11 ? end_bit - shift : 11;
         int nb = 1 << bits;
-        int64_t *cnt = (int64_t *)calloc((size_t)nb + 1, sizeof(int64_t));
         uint64_t mask = (uint64_t)nb - 1;
-        for (int64_t i = 0; i < M; ++i) cnt[(((uint64_t)ka[i]) >> shift & mask) + 1]++;
-        for (int d = 0; d < nb; ++d) cnt[d + 1] += cnt[d];
-        for (int64_t i = 0; i < M; ++i) {
-            int64_t pos = cnt[((uint64_t)ka[i]) >> shift & mask]++;
-            kb[pos] = ka[i];
-            vb[pos] = va[i];
+        /* slice t = [M t / nt, M (t+1) / nt): per-slice digit counts, then offsets in (digit, slice) order keep
+         * the sort stable whatever the thread count */
+#pragma omp parallel for schedule(static, 1) num_threads(nt)
+        for (int t = 0; t < nt; ++t) {
+            int64_t *c = cnt + (size_t)t * NB;
+            memset(c, 0, sizeof(int64_t) * (size_t)nb);
+            int64_t lo = M * t / nt, hi = M * (t + 1) / nt;
+            for (int64_t i = lo; i < hi; ++i) c[((uint64_t)ka[i]) >> shift & mask]++;
         }
-        free(cnt);
+        int64_t run = 0;
+        for (int d = 0; d < nb; ++d)
+            for (int t = 0; t < nt; ++t) {
+                int64_t n = cnt[(size_t)t * NB + d];
+                cnt[(size_t)t * NB + d] = run;
+                run += n;
+            }
+#pragma omp parallel for schedule(static, 1) num_threads(nt)
+        for (int t = 0; t < nt; ++t) {
+            int64_t *c = cnt + (size_t)t * NB;
+            int64_t lo = M * t / nt, hi = M * (t + 1) / nt;
+            for (int64_t i = lo; i < hi; ++i) {
+                int64_t pos = c[((uint64_t)ka[i]) >> shift & mask]++;
+                kb[pos] = ka[i];
+                vb[pos] = va[i];
+            }
+        }
         int64_t *tk = ka; ka = kb; kb = tk;
         int32_t *tv = va; va = vb; vb = tv;
     }
+    free(cnt);
     if (ka != keys) {
         memcpy(keys, ka, sizeof(int64_t) * (size_t)M);
         memcpy(vals, va, sizeof(int32_t) * (size_t)M);
@@ -415,24 +454,31 @@ void orc_blend_bwd(const float *means2d, const float *conics, const float *color
                     for (int k = 0; k < CD; ++k) buffer[k] += cp[k] * fac;
                 }
             }
-#pragma omp critical
-        {
-            for (int64_t e = 0; e < L; ++e) {
-                int g = flatten_ids[start + e];
-                const double *A = acc + (size_t)e * stride;
-                v_means2d[2 * g] += A[0];
-                v_means2d[2 * g + 1] += A[1];
-                if (v_means2d_abs) {
-                    v_means2d_abs[2 * g] += A[2];
-                    v_means2d_abs[2 * g + 1] += A[3];
-                }
-                v_conics[3 * g] += A[4];
-                v_conics[3 * g + 1] += A[5];
-                v_conics[3 * g + 2] += A[6];
-                v_opacities[g] += A[7];
-                for (int k = 0; k < CD; ++k) v_colors[(size_t)g * CD + k] += A[8 + k];
+        /* merge into the per-Gaussian sums (double atomics: tiles run in parallel) */
+#define ORC_ADD(dst, val)            \
+    do {                             \
+        double v_ = (val);           \
+        if (v_ != 0.0) {             \
+            _Pragma("omp atomic")    \
+            (dst) += v_;             \
+        }                            \
+    } while (0)
+        for (int64_t e = 0; e < L; ++e) {
+            int g = flatten_ids[start + e];
+            const double *A = acc + (size_t)e * stride;
+            ORC_ADD(v_means2d[2 * g], A[0]);
+            ORC_ADD(v_means2d[2 * g + 1], A[1]);
+            if (v_means2d_abs) {
+                ORC_ADD(v_means2d_abs[2 * g], A[2]);
+                ORC_ADD(v_means2d_abs[2 * g + 1], A[3]);
             }
+            ORC_ADD(v_conics[3 * g], A[4]);
+            ORC_ADD(v_conics[3 * g + 1], A[5]);
+            ORC_ADD(v_conics[3 * g + 2], A[6]);
+            ORC_ADD(v_opacities[g], A[7]);
+            for (int k = 0; k < CD; ++k) ORC_ADD(v_colors[(size_t)g * CD + k], A[8 + k]);
         }
+#undef ORC_ADD
         free(acc);
     }
 }
@@ -452,6 +498,7 @@ void orc_project_bwd(const float *means, const float *quats, const float *scales
     float t[3] = {viewmat[3], viewmat[7], viewmat[11]};
     Pinhole cam = make_pinhole(K, W, H);
     double vR_acc[9] = {0}, vt_acc[3] = {0};
+#pragma omp parallel for schedule(static) reduction(+ : vR_acc[:9], vt_acc[:3])
     for (int g = 0; g < N; ++g) {
         for (int k = 0; k < 3; ++k) { v_means[3 * g + k] = 0.f; v_scales[3 * g + k] = 0.f; }
         for (int k = 0; k < 4; ++k) v_quats[4 * g + k] = 0.f;

@@ -14,7 +14,7 @@ import pytest
 import torch
 
 from mtgs_b200 import scenes
-from tests.util import assert_grad_close, assert_image_close, psnr
+from tests.util import assert_grad_close, assert_image_close, masked_psnr, psnr
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -269,6 +269,46 @@ def test_error_behaviour(cuda_device):
     r, a, m = rasterization(far, t["quats"], t["scales"], t["opacities"], t["colors"], t["viewmat"][None],
                             t["K"][None], 64, 48, packed=False)
     assert m["flatten_ids"].numel() == 0 and float(a.abs().max()) == 0.0 and int(m["radii"].max()) == 0
+
+
+@pytest.mark.parametrize("n,d_in", [(500_000, 3), (500_000, 6), (2_000_000, 3), (2_000_000, 6)])
+def test_full_size_oracle_parity(oracle, cuda_device, n, d_in):
+    """BASELINE config 2 itself (500 k @1920x1080) and the bench workload (2 M), CDIM 4 (RGB+ED) and CDIM 8
+    (RGB+normals+ED, mtgs/config/MTGS.py:101-111), against the oracle: bit-exact bins, forward images, every
+    gradient.  These are the deep-tile sizes (2 M: ~2350 entries per tile) where the transmittance reconstruction
+    by division and the per-tile cull are exercised hardest."""
+    s = scenes.street(n=n, seed=1, width=1920, height=1080, d_in=d_in)
+    rng = np.random.default_rng(11)
+    t = _to_dev(s, cuda_device, grad=True)
+    kw = dict(render_mode="RGB+ED", rasterize_mode="antialiased")
+    r, a, meta = _gpu_raster(t, s, absgrad=True, **kw)
+    meta["means2d"].retain_grad()
+    v_r = rng.standard_normal(tuple(r.shape[1:])).astype(np.float32)
+    v_a = rng.standard_normal(tuple(a.shape[1:])).astype(np.float32)
+    loss = (r[0] * torch.tensor(v_r, device=cuda_device)).sum() + (a[0] * torch.tensor(v_a, device=cuda_device)).sum()
+    loss.backward()
+    rc, ra, ref, ctx = _cpu_raster(oracle, s, **kw)
+    # bins: bit-exact
+    np.testing.assert_array_equal(meta["radii"][0].cpu().numpy(), ref["radii"], err_msg="radii")
+    np.testing.assert_array_equal(meta["tiles_per_gauss"][0].cpu().numpy(), ref["tiles_per_gauss"])
+    np.testing.assert_array_equal(meta["flatten_ids"].cpu().numpy(), ref["flatten_ids"], err_msg="flatten_ids")
+    np.testing.assert_array_equal(meta["isect_offsets"][0].cpu().numpy(), ref["isect_offsets"])
+    np.testing.assert_array_equal(meta["isect_ids"].cpu().numpy(), ref["isect_ids"], err_msg="isect_ids")
+    # images
+    rg, ag = r[0].detach().cpu().numpy(), a[0].detach().cpu().numpy()
+    _check_images(rg, ag, rc, ra, "RGB+ED")
+    assert masked_psnr(rg[..., :3], rc[..., :3]) > 60.0
+    # gradients
+    ctx["meta_offs"], ctx["meta_flat"] = ref["isect_offsets"], ref["flatten_ids"]
+    g = oracle.rasterization_bwd(ctx, v_r, v_a, absgrad=True)
+    assert_grad_close(meta["means2d"].grad[0].cpu().numpy(), g["v_means2d"], "means2d.grad")
+    assert_grad_close(meta["means2d"].absgrad[0].cpu().numpy(), g["v_means2d_abs"], "means2d.absgrad")
+    assert_grad_close(t["colors"].grad.cpu().numpy(), g["v_colors"], "v_colors")
+    assert_grad_close(t["opacities"].grad.cpu().numpy(), g["v_opacities"], "v_opacities")
+    assert_grad_close(t["means"].grad.cpu().numpy(), g["v_means"], "v_means")
+    assert_grad_close(t["quats"].grad.cpu().numpy(), g["v_quats"], "v_quats")
+    assert_grad_close(t["scales"].grad.cpu().numpy(), g["v_scales"], "v_scales")
+    assert_grad_close(t["viewmat"].grad.cpu().numpy(), g["v_viewmat"], "v_viewmat", rtol=5e-3, scale_atol=1e-3)
 
 
 def test_full_size_properties(cuda_device):
