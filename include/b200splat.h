@@ -45,10 +45,19 @@ const char *b2s_error_string(int code);
 long long b2s_launch_count(void);
 
 /* ---- projection + EWA covariance (upstream fully_fused_projection fwd; SURVEY A.1, A.2 pass 1) ----
- * Also emits, per Gaussian: the tile count of upstream isect_tiles pass 1, its tile rectangle, the depth
- * sort key (float bits of depth, 0xFFFFFFFF when culled), the packed blend record
+ * Also emits, per Gaussian: the tile count of upstream isect_tiles pass 1 and its tile rectangle (tile_rects), the
+ * depth sort key (float bits of depth, 0xFFFFFFFF when culled), the packed blend record
  *   geo[g]     = (conic a, conic b, conic c, opacity * compensation)
  *   colpack[g] = (colors_in[0..d_in), depth if with_depth, zero pad) , cdim floats
+ * and tight_rects: tile_rects intersected with the tiles whose pixel centres the footprint {alpha >= 1/255} of the
+ * Gaussian can reach -- the rectangles the blend's own tile lists are built from (not an upstream output).
+ * totals (int64[9], zero-filled by the caller) receives the list sizes of both tile-list builds:
+ *   [0..3] = M, S, E1, E3 over tile_rects   (M = upstream's number of intersections = sum of tiles_per_gauss)
+ *   [4..7] = the same over tight_rects      (upper bounds of the blend's own lists)
+ *   [8]    = number of visible Gaussians (radii > 0)
+ * The caller reads them back ONCE (the one device->host read of the path, overlapped with the depth sort) to size
+ * the lists and the workspace of b2s_bin_tiles.  bwd_arena (may be NULL) = the N * (8 + cdim) floats of the blend
+ * backward's accumulation buffers (v_xyabs | v_geo | v_colpack), zero-filled here so that no memset pass is needed.
  * comps may be NULL when calc_comp == 0.  colors_in is [N, d_in]. */
 int b2s_project_fwd(const float *means, const float *quats, const float *scales,
                     const float *opacities, const float *colors_in, const float *viewmat,
@@ -57,7 +66,9 @@ int b2s_project_fwd(const float *means, const float *quats, const float *scales,
                     int calc_comp, int d_in, int with_depth, int cdim, int32_t *radii,
                     float *means2d, float *depths, float *geo, float *comps, float *colpack,
                     int32_t *tiles_per_gauss, uint32_t *sort_keys,
-                    int32_t *tile_rects /* [N,2]: x0 | x1 << 16, y0 | y1 << 16 */, b2s_stream_t stream);
+                    int32_t *tile_rects /* [N,2]: x0 | x1 << 16, y0 | y1 << 16 */,
+                    int32_t *tight_rects /* [N,2], same packing */, int64_t *totals /* [9] */,
+                    float *bwd_arena, b2s_stream_t stream);
 
 /* upstream fully_fused_projection bwd fused with the opacity*compensation and
  * colour/depth un-packing VJPs.  v_means2d[g * v_means2d_stride + {0,1}] (stride 2, or 4 when it aliases
@@ -116,22 +127,25 @@ int b2s_project_bwd_exchange(const float *means, const float *quats, const float
 /* ---- tile binning + depth sort (upstream isect_tiles + radix sort + isect_offset_encode; A.2) ----
  * Two-level formulation with identical results to the stable 64-bit sort:
  *   (1) b2s_bin_sort_depth : stable sort of the visible Gaussians by depth key (one cooperative kernel) ->
- *       order[0..n_vis), *n_vis (device int32) and totals (device int64[5]) = {M tile intersections, S tile-row
- *       hits, E1 row-group hits, E3 (row, column-group) hits, n_vis}: the list sizes of every level of (2).  The
- *       caller reads totals back once (the one device->host read of the path; it sizes flatten_ids and the
- *       workspace of (2)).  Entries of order beyond n_vis are undefined.
+ *       order[0..n_vis), *n_vis (device int32).  Entries of order beyond n_vis are undefined.
  *   (2) b2s_bin_tiles      : hierarchy of order-preserving filters (Gaussians -> row groups -> tile rows ->
- *       column groups -> tiles) walking the Gaussians in depth order -> flatten_ids[M],
- *       isect_offsets[tile_h*tile_w] (no sort of the M intersections).  totals_host = the five values of (1).
+ *       column groups -> tiles) walking the Gaussians in depth order -> flatten_ids, isect_offsets (no sort of the
+ *       intersections).  totals_host = {list length, S, E1, E3, n_vis} for the rectangles passed in (b2s_project_fwd
+ *       totals [0..3] + [8] for tile_rects, [4..7] + [8] for tight_rects); they size flatten_ids (list length
+ *       entries) and the workspace.
+ *       means2d == geo == NULL: upstream's lists (every tile of the rectangle), bit-identical flatten_ids /
+ *       isect_offsets.  means2d, geo given ("exact" mode, with tight_rects): the last level keeps only the (Gaussian,
+ *       tile) pairs that can reach alpha >= 1/255 at a pixel centre of the tile -- the lists the blend kernels walk;
+ *       the list is then at most `list length` long.  offsets_with_total != 0: isect_offsets has tile_w * tile_h + 1
+ *       entries, the last one = the final list length (so the blend needs no host-side count).
  *   (3) b2s_bin_isect_ids  : optional, rebuilds upstream's int64 isect_ids for inspection. */
 size_t b2s_bin_depth_workspace_bytes(int N);
-int b2s_bin_sort_depth(const uint32_t *sort_keys, const int32_t *tiles_per_gauss,
-                       const int32_t *tile_rects, int N, int tile_w, int tile_h, int32_t *order,
-                       int64_t *totals, int32_t *n_vis, void *workspace, size_t workspace_bytes,
-                       b2s_stream_t stream);
+int b2s_bin_sort_depth(const uint32_t *sort_keys, int N, int32_t *order, int32_t *n_vis, void *workspace,
+                       size_t workspace_bytes, b2s_stream_t stream);
 size_t b2s_bin_tiles_workspace_bytes(const long long *totals_host, int tile_w, int tile_h);
-int b2s_bin_tiles(const int32_t *tile_rects, const int32_t *order, const int32_t *n_vis,
-                  const long long *totals_host, int N, int tile_size, int tile_w, int tile_h,
+int b2s_bin_tiles(const int32_t *rects, const int32_t *order, const int32_t *n_vis,
+                  const long long *totals_host, int N, int tile_size, int tile_w, int tile_h, int W, int H,
+                  const float *means2d, const float *geo, int offsets_with_total,
                   int32_t *flatten_ids, int32_t *isect_offsets, void *workspace,
                   size_t workspace_bytes, b2s_stream_t stream);
 int b2s_bin_isect_ids(const int32_t *isect_offsets, int n_tiles, const int32_t *flatten_ids,
@@ -139,17 +153,25 @@ int b2s_bin_isect_ids(const int32_t *isect_offsets, int n_tiles, const int32_t *
 
 /* ---- alpha blending (upstream rasterize_to_pixels fwd / bwd; A.3, A.4) ----
  * cdim in {4, 8}; d_out = channels written per pixel (<= cdim); expected_depth != 0 divides channel
- * d_out-1 by max(alpha, 1e-10) in the epilogue (upstream does that in torch).  16x16 tiles only. */
+ * d_out-1 by max(alpha, 1e-10) in the epilogue (upstream does that in torch).  16x16 tiles only.
+ * tile_offsets [tile_w * tile_h + 1] / tile_ids: depth-ordered list per tile (b2s_bin_tiles, either mode; the exact
+ * mode's lists give the same image with ~3x fewer entries).  last_ids [H, W]: index into tile_ids of the last entry
+ * each pixel blended.  records (may be NULL for a forward without backward; 128-byte aligned,
+ * b2s_blend_record_bytes(capacity of tile_ids, tiles, cdim) bytes): the forward stores every list block it walks as
+ * a "walk record" (projected mean, log2-domain conic, opacity, Gaussian id, colours of 128 entries, SoA) through TMA
+ * bulk stores; the backward replays those blocks back to front through double-buffered TMA bulk loads and never
+ * touches the lists or the per-Gaussian arrays.  v_xyabs [N,4] = (v_mean2d xy, |v_mean2d| xy), v_geo [N,4] =
+ * (v_conic abc, v_opacity_eff), v_colpack [N,cdim]: accumulated with 16-byte vector reductions, zero-filled by the
+ * caller (b2s_project_fwd does it). */
+size_t b2s_blend_record_bytes(long long list_capacity, int n_tiles, int cdim);
 int b2s_blend_fwd(const float *means2d, const float *geo, const float *colpack,
-                  const int32_t *isect_offsets, const int32_t *flatten_ids, long long M, int W,
-                  int H, int tile_w, int tile_h, int cdim, int d_out, int expected_depth,
-                  float *render, float *alpha, int32_t *last_ids, b2s_stream_t stream);
-int b2s_blend_bwd(const float *means2d, const float *geo, const float *colpack,
-                  const int32_t *isect_offsets, const int32_t *flatten_ids, long long M, int W,
-                  int H, int tile_w, int tile_h, int cdim, int d_out, int expected_depth,
-                  const float *render, const float *alpha, const int32_t *last_ids,
-                  const float *v_render, const float *v_alpha, float *v_xyabs, float *v_geo,
-                  float *v_colpack, b2s_stream_t stream);
+                  const int32_t *tile_offsets, const int32_t *tile_ids, int W, int H, int tile_w, int tile_h,
+                  int cdim, int d_out, int expected_depth, float *render, float *alpha, int32_t *last_ids,
+                  float *records, b2s_stream_t stream);
+int b2s_blend_bwd(const int32_t *tile_offsets, const float *records, int W, int H, int tile_w, int tile_h,
+                  int cdim, int d_out, int expected_depth, const float *render, const float *alpha,
+                  const int32_t *last_ids, const float *v_render, const float *v_alpha, float *v_xyabs,
+                  float *v_geo, float *v_colpack, b2s_stream_t stream);
 
 /* ---- spherical harmonics (upstream compute_sh fwd / bwd; A.6) ----
  * dirs [N,3], coeffs [N,K,3], masks (uint8, may be NULL), degree in 0..4 with (degree+1)^2 <= K. */

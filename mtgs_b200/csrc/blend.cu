@@ -6,36 +6,41 @@
 //
 // These kernels are FP32-ALU / MUFU.EX2 / shuffle bound, not HBM bound: no tensor cores.
 // Blackwell-first choices:
-//   * one CTA of 128 threads per 16x16 tile, TWO pixels per thread (same column, adjacent rows): the staged
-//     Gaussian record is read from shared memory once per two pixel-pairs and the per-(warp,Gaussian) gradient
-//     reduction in the backward covers 64 pixels instead of 32;
-//   * exact per-tile culling while staging: a (Gaussian, tile) pair whose minimum exponent over the tile's
-//     pixel centres already gives alpha < 1/255 contributes to no pixel, so it is dropped from the staged batch
-//     (ballot compaction).  The isect lists stay bit-identical to upstream; only dead work disappears;
+//   * the lists they walk are the blend's own tile lists (tilelists.cu, exact mode): only (Gaussian, tile) pairs
+//     that can reach alpha >= 1/255 at a pixel centre of the tile.  Upstream's 3-sigma lists contain ~3x more
+//     entries that contribute to no pixel; dropping them changes no output bit;
+//   * forward: one CTA of 128 threads per 16x16 tile, TWO pixels per thread; a batch of 128 list entries is
+//     gathered (id -> projected record) into a shared-memory block in SoA form, and the finished block is handed
+//     to the TMA engine (cp.async.bulk shared -> global, SASS UBLKCP) as a "walk record" while the CTA blends it;
+//     the gathers of the NEXT batch are in flight during the blend of the current one (register double buffer);
+//   * backward: 64 threads per tile, FOUR pixels per thread; it never touches the id lists or the per-Gaussian
+//     arrays: it replays the forward's walk records back to front, each 6-8 KB block arriving by ONE TMA bulk copy
+//     (cp.async.bulk global -> shared on an mbarrier), double buffered, so the next block lands while the
+//     current one is being differentiated -- no gather latency, no staging instructions, no staging barriers;
 //   * exponent evaluated in log2 units (log2e folded into the conic while staging) -> one ex2.approx per pair;
 //   * both kernels are instruction-issue bound, so the per-pixel arithmetic runs on Blackwell's packed fp32x2
 //     instructions (FFMA2 / FMUL2 / FADD2: two IEEE-rn fp32 operations per issue slot, scalar operands broadcast
-//     for free): a thread's vertically adjacent pixels travel as the two halves of a float2.  Every packed op is
-//     the same rn operation the scalar code performed, so the forward image is bit-identical to the scalar kernel;
-//   * backward: the 16 per-Gaussian partial sums (xy, |xy|, conic, opacity, <=8 colour channels) are reduced
+//     for free): a thread's vertically adjacent pixels travel as the two halves of a float2;
+//   * backward: the per-Gaussian partial sums (xy, |xy|, conic, opacity, <=8 colour channels) are reduced
 //     with a transposing butterfly (16 shuffles instead of 16 x 5), parked per warp in shared memory, summed
-//     over the CTA's four warps and flushed with 16-byte vector reductions (red.global.add.v4.f32): at most
+//     over the CTA's two warps and flushed with 16-byte vector reductions (red.global.add.v4.f32): at most
 //     2 + CDIM/4 L2 atomic operations per (tile, Gaussian) instead of upstream's (9 + CDIM) per (warp, Gaussian).
-#include <cstdlib>
-
 #include "common.cuh"
 
 constexpr int BL_THREADS = 128;
-constexpr int BL_WARPS = BL_THREADS / 32;
-constexpr int BL_BATCH = BL_THREADS;
+constexpr int BL_BATCH = 128;  // list entries per walk-record block
+
+// float4s per walk-record block: q[128] = (mx, my, A, B), c[128] = (C, opacity, Gaussian id bits, 0), col[128][CDIM/4]
+template <int CDIM> struct BlkLayout {
+    static constexpr int CQ = CDIM / 4;
+    static constexpr int F4 = BL_BATCH * (2 + CQ);
+    static constexpr unsigned BYTES = F4 * 16;
+};
+// walk-record block index of batch k of a tile whose list starts at `start`: strictly increasing over (tile, k)
+__device__ __forceinline__ size_t blk_index(int start, int tile, int k) { return (size_t)(start >> 7) + tile + k; }
 
 // exponent in log2 units: s = A dx^2 + B dx dy + C dy^2 with A = a/2*log2e, B = b*log2e, C = c/2*log2e.
 // Written with explicit roundings so that forward and backward evaluate identical bits.
-__device__ __forceinline__ float splat_power(float A, float B, float C, float dx, float dy) {
-    float u = fmaf(B, dy, __fmul_rn(A, dx));
-    return fmaf(__fmul_rn(C, dy), dy, __fmul_rn(u, dx));
-}
-
 // ---- packed fp32x2 helpers (sm_100a FFMA2 / FMUL2 / FADD2) ----
 __device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
@@ -43,137 +48,90 @@ __device__ __forceinline__ float2 abs2(float2 a) { return make_float2(fabsf(a.x)
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
 __device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
-// splat_power for two pixels of one column (same dx): identical bits per half as the scalar function
+// two pixels of one column (same dx)
 __device__ __forceinline__ float2 splat_power2(float A, float B, float C, float dx, float2 dy) {
     const float2 u = fma2(bc2(B), dy, bc2(__fmul_rn(A, dx)));
     return fma2(mul2(bc2(C), dy), dy, mul2(u, bc2(dx)));
 }
 
-// Can this Gaussian reach alpha >= 1/255 at any pixel centre of the rectangle [rx0,rx1]x[ry0,ry1]?
-// Conservative (never drops a contributing pair): exact box-constrained minimum of the convex quadratic,
-// compared with log2(255 * opacity) plus a slack that dominates fp32 evaluation error.
-__device__ __forceinline__ bool tile_keep(float mx, float my, float A, float B, float C, float opac, float rx0,
-                                          float ry0, float rx1, float ry1) {
-    if (!(opac >= 0.0039f)) return false;  // opac * e^-sigma <= opac < 1/255 (also drops NaN)
-    float ex = fminf(fmaxf(mx, rx0), rx1) - mx;  // nearest pixel-centre coordinate minus mean (0 if inside)
-    float ey = fminf(fmaxf(my, ry0), ry1) - my;
-    if (ex == 0.f && ey == 0.f) return true;
-    float tau = __log2f(opac * 255.0f);
-    float smin = 3.0e38f, mag = 0.f;
-    if (ex != 0.f) {  // facing vertical edge: dx fixed, minimise over dy
-        float dy = fminf(fmaxf(-B * ex / (2.f * C), ry0 - my), ry1 - my);
-        float t0 = A * ex * ex, t1 = B * ex * dy, t2 = C * dy * dy;
-        float s = t0 + t1 + t2;
-        if (s < smin) { smin = s; mag = fabsf(t0) + fabsf(t1) + fabsf(t2); }
-    }
-    if (ey != 0.f) {  // facing horizontal edge
-        float dx = fminf(fmaxf(-B * ey / (2.f * A), rx0 - mx), rx1 - mx);
-        float t0 = A * dx * dx, t1 = B * dx * ey, t2 = C * ey * ey;
-        float s = t0 + t1 + t2;
-        if (s < smin) { smin = s; mag = fabsf(t0) + fabsf(t1) + fabsf(t2); }
-    }
-    return !(smin > tau + 0.02f + 2e-5f * mag);  // NaN-safe: keep on NaN
-}
-
-struct TileGeom {
-    int x, y0;               // this thread's pixel column and first row (second row is y0 + 1)
-    bool in0, in1;
-    float px, py0, py1;
-    float rx0, ry0, rx1, ry1;  // pixel-centre rectangle of the tile clipped to the image
-    int start, end;
-};
-
-__device__ __forceinline__ TileGeom tile_geom(int tile_w, int tile_h, int W, int H, long long M,
-                                              const int32_t *__restrict__ offsets) {
-    TileGeom g;
-    const int tile = blockIdx.x;
-    const int ti = tile / tile_w, tj = tile - ti * tile_w;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    g.x = tj * 16 + (lane & 15);
-    g.y0 = ti * 16 + 4 * warp + 2 * (lane >> 4);
-    g.in0 = g.x < W && g.y0 < H;
-    g.in1 = g.x < W && (g.y0 + 1) < H;
-    g.px = (float)g.x + 0.5f;
-    g.py0 = (float)g.y0 + 0.5f;
-    g.py1 = g.py0 + 1.0f;
-    g.rx0 = (float)(tj * 16) + 0.5f;
-    g.ry0 = (float)(ti * 16) + 0.5f;
-    g.rx1 = (float)min(tj * 16 + 16, W) - 0.5f;
-    g.ry1 = (float)min(ti * 16 + 16, H) - 0.5f;
-    g.start = offsets[tile];
-    g.end = (tile == tile_w * tile_h - 1) ? (int)M : offsets[tile + 1];
-    return g;
-}
-
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
+struct FwdRec {  // one list entry gathered into registers
+    float4 q, c;
+    float4 col[2];
+};
+template <int CQ>
+__device__ __forceinline__ void fwd_gather(FwdRec &r, int idx, int end, const int32_t *__restrict__ ids,
+                                           const float2 *__restrict__ means2d, const float4 *__restrict__ geo,
+                                           const float4 *__restrict__ colpack) {
+    if (idx < end) {
+        const int g = ids[idx];
+        const float2 m = means2d[g];
+        const float4 ge = geo[g];
+        r.q = make_float4(m.x, m.y, 0.5f * B2S_LOG2E * ge.x, B2S_LOG2E * ge.y);
+        r.c = make_float4(0.5f * B2S_LOG2E * ge.z, ge.w, __int_as_float(g), 0.f);
+#pragma unroll
+        for (int k = 0; k < CQ; ++k) r.col[k] = colpack[(size_t)g * CQ + k];
+    }
+}
+
 template <int CDIM, int DOUT, bool ED>
 __global__ void __launch_bounds__(BL_THREADS)
 k_blend_fwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, const float4 *__restrict__ colpack,
-            const int32_t *__restrict__ offsets, const int32_t *__restrict__ flatten_ids, long long M, int W, int H,
-            int tile_w, int tile_h, float *__restrict__ render, float *__restrict__ alpha_out,
-            int32_t *__restrict__ last_ids) {
+            const int32_t *__restrict__ offsets /* [tiles + 1] */, const int32_t *__restrict__ ids, int W, int H,
+            int tile_w, float *__restrict__ render, float *__restrict__ alpha_out, int32_t *__restrict__ last_ids,
+            float4 *__restrict__ records /* walk-record blocks for the backward, or null */) {
     constexpr int CQ = CDIM / 4;
-    __shared__ float4 s_q[BL_BATCH];        // mx, my, A, B
-    __shared__ float2 s_c[BL_BATCH];        // C, opacity
-    __shared__ int s_idx[BL_BATCH];         // index into the sorted list
-    __shared__ float4 s_col[BL_BATCH][CQ];
-    __shared__ int s_wcnt[BL_WARPS];
+    using BL = BlkLayout<CDIM>;
+    __shared__ __align__(128) float4 s_blk[BL::F4];
+    float4 *s_q = s_blk, *s_c = s_blk + BL_BATCH, *s_col = s_blk + 2 * BL_BATCH;
 
-    const TileGeom tg = tile_geom(tile_w, tile_h, W, H, M, offsets);
+    const int tile = blockIdx.x;
+    const int ti = tile / tile_w, tj = tile - ti * tile_w;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned lt = lanemask_lt();
+    const int x = tj * 16 + (lane & 15);
+    const int y0 = ti * 16 + 4 * warp + 2 * (lane >> 4);  // the thread's pixels: rows y0 and y0 + 1 of column x
+    const bool in0 = x < W && y0 < H, in1 = x < W && (y0 + 1) < H;
+    const float px = (float)x + 0.5f;
+    const int start = offsets[tile], end = offsets[tile + 1];
 
-    // the thread's two pixels (rows y0, y0 + 1) are the halves of every float2 below
+    // the thread's two pixels are the halves of every float2 below
     float2 T = make_float2(1.f, 1.f);
     float2 acc[CDIM];
 #pragma unroll
     for (int k = 0; k < CDIM; ++k) acc[k] = make_float2(0.f, 0.f);
-    const float2 npy = make_float2(-tg.py0, -tg.py1);
+    const float2 npy = make_float2(-((float)y0 + 0.5f), -((float)y0 + 1.5f));
     int cur0 = 0, cur1 = 0;
-    bool done0 = !tg.in0, done1 = !tg.in1;
+    bool done0 = !in0, done1 = !in1;
 
-    for (int base = tg.start; base < tg.end; base += BL_BATCH) {
+    FwdRec nxt;
+    fwd_gather<CQ>(nxt, start + (int)threadIdx.x, end, ids, means2d, geo, colpack);
+    for (int base = start, k = 0; base < end; base += BL_BATCH, ++k) {
+        // the TMA store of the previous block must have read shared memory before the block is overwritten
+        if (records != nullptr && threadIdx.x == 0) b2s_bulk_wait_read();
         if (__syncthreads_and(done0 && done1)) break;
-        const int idx = base + threadIdx.x;
-        bool keep = false;
-        int g = 0;
-        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-        float2 c = make_float2(0.f, 0.f);
-        if (idx < tg.end) {
-            g = flatten_ids[idx];
-            const float2 m = means2d[g];
-            const float4 ge = geo[g];
-            q = make_float4(m.x, m.y, 0.5f * B2S_LOG2E * ge.x, B2S_LOG2E * ge.y);
-            c = make_float2(0.5f * B2S_LOG2E * ge.z, ge.w);
-            keep = tile_keep(m.x, m.y, q.z, q.w, c.x, c.y, tg.rx0, tg.ry0, tg.rx1, tg.ry1);
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) s_wcnt[warp] = __popc(bal);
-        __syncthreads();
-        int off = 0, total = 0;
+        if (base + (int)threadIdx.x < end) {
+            s_q[threadIdx.x] = nxt.q;
+            s_c[threadIdx.x] = nxt.c;
 #pragma unroll
-        for (int w = 0; w < BL_WARPS; ++w) {
-            int n = s_wcnt[w];
-            off += (w < warp) ? n : 0;
-            total += n;
+            for (int j = 0; j < CQ; ++j) s_col[threadIdx.x * CQ + j] = nxt.col[j];
         }
-        if (keep) {
-            const int slot = off + __popc(bal & lt);
-            s_q[slot] = q;
-            s_c[slot] = c;
-            s_idx[slot] = idx;
-#pragma unroll
-            for (int k = 0; k < CQ; ++k) s_col[slot][k] = colpack[(size_t)g * CQ + k];
-        }
+        if (records != nullptr) b2s_fence_async_smem();
         __syncthreads();
+        if (records != nullptr && threadIdx.x == 0) {
+            b2s_bulk_s2g(records + blk_index(start, tile, k) * BL::F4, s_blk, BL::BYTES);
+            b2s_bulk_commit();
+        }
+        // gathers of the next batch fly while this one is blended
+        fwd_gather<CQ>(nxt, base + BL_BATCH + (int)threadIdx.x, end, ids, means2d, geo, colpack);
+        const int total = min(BL_BATCH, end - base);
 
 #pragma unroll 2
         for (int t = 0; t < total; ++t) {
             const float4 sq = s_q[t];
-            const float2 sc = s_c[t];
-            const float dx = sq.x - tg.px;
+            const float4 sc = s_c[t];
+            const float dx = sq.x - px;
             const float2 dy = add2(bc2(sq.y), npy);
             const float2 p = splat_power2(sq.z, sq.w, sc.x, dx, dy);
             const float2 ov = mul2(bc2(sc.y), make_float2(ex2_approx(-p.x), ex2_approx(-p.y)));
@@ -190,20 +148,22 @@ k_blend_fwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
                 vis.y = ap1 ? vis.y : 0.f;
                 T.x = ap0 ? nT.x : T.x;
                 T.y = ap1 ? nT.y : T.y;
-                const int id = s_idx[t];
+                const int id = base + t;
                 cur0 = ap0 ? id : cur0;
                 cur1 = ap1 ? id : cur1;
 #pragma unroll
-                for (int k = 0; k < CQ; ++k) {
-                    const float4 v = s_col[t][k];
-                    acc[4 * k] = fma2(bc2(v.x), vis, acc[4 * k]);
-                    acc[4 * k + 1] = fma2(bc2(v.y), vis, acc[4 * k + 1]);
-                    acc[4 * k + 2] = fma2(bc2(v.z), vis, acc[4 * k + 2]);
-                    acc[4 * k + 3] = fma2(bc2(v.w), vis, acc[4 * k + 3]);
+                for (int j = 0; j < CQ; ++j) {
+                    const float4 v = s_col[t * CQ + j];
+                    acc[4 * j] = fma2(bc2(v.x), vis, acc[4 * j]);
+                    acc[4 * j + 1] = fma2(bc2(v.y), vis, acc[4 * j + 1]);
+                    acc[4 * j + 2] = fma2(bc2(v.z), vis, acc[4 * j + 2]);
+                    acc[4 * j + 3] = fma2(bc2(v.w), vis, acc[4 * j + 3]);
                 }
             }
         }
     }
+    if (records != nullptr && threadIdx.x == 0) b2s_bulk_wait_read();  // shared memory must outlive the last store
+
     const float T0 = T.x, T1 = T.y;
     float acc0[CDIM], acc1[CDIM];
 #pragma unroll
@@ -213,8 +173,8 @@ k_blend_fwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
     }
 
     // epilogue: optional expected-depth normalisation of the last written channel
-    if (tg.in0) {
-        const size_t pid = (size_t)tg.y0 * W + tg.x;
+    if (in0) {
+        const size_t pid = (size_t)y0 * W + x;
         const float al = 1.0f - T0;
         if (ED) acc0[DOUT - 1] = acc0[DOUT - 1] / fmaxf(al, 1e-10f);
         alpha_out[pid] = al;
@@ -226,8 +186,8 @@ k_blend_fwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
             for (int k = 0; k < DOUT; ++k) render[pid * DOUT + k] = acc0[k];
         }
     }
-    if (tg.in1) {
-        const size_t pid = (size_t)(tg.y0 + 1) * W + tg.x;
+    if (in1) {
+        const size_t pid = (size_t)(y0 + 1) * W + x;
         const float al = 1.0f - T1;
         if (ED) acc1[DOUT - 1] = acc1[DOUT - 1] / fmaxf(al, 1e-10f);
         alpha_out[pid] = al;
@@ -348,44 +308,33 @@ __device__ __forceinline__ void load_pixel_cotangent(size_t pid, const float *__
     }
 }
 
-// PX pixels per thread (same column, PX adjacent rows); 256 / PX threads per tile.  PX = 4 halves the number of
-// (warp, Gaussian) reductions and staged-record reads per pixel compared with PX = 2.
-template <int CDIM, int DOUT, bool ED, int PX>
-__global__ void __launch_bounds__(256 / PX, PX == 4 ? (CDIM == 4 ? 9 : 8) : 1)
-k_blend_bwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, const float4 *__restrict__ colpack,
-            const int32_t *__restrict__ offsets, const int32_t *__restrict__ flatten_ids, long long M, int W, int H,
-            int tile_w, int tile_h, const float *__restrict__ render, const float *__restrict__ alpha_in,
+// 64 threads per tile, 4 pixels per thread (same column, 4 adjacent rows) = 2 packed pixel pairs.
+template <int CDIM, int DOUT, bool ED>
+__global__ void __launch_bounds__(64, CDIM == 4 ? 9 : 7)
+k_blend_bwd(const int32_t *__restrict__ offsets /* [tiles + 1] */, const float4 *__restrict__ records, int W, int H,
+            int tile_w, const float *__restrict__ render, const float *__restrict__ alpha_in,
             const int32_t *__restrict__ last_ids, const float *__restrict__ v_render,
             const float *__restrict__ v_alpha, float *__restrict__ v_xyabs, float *__restrict__ v_geo,
             float *__restrict__ v_colpack) {
-    constexpr int THREADS = 256 / PX;
-    constexpr int WARPS = THREADS / 32;
-    constexpr int BATCH = 128;            // staged Gaussians per round
-    constexpr int SPT = BATCH / THREADS;  // staged per thread
+    constexpr int PX = 4, THREADS = 64, WARPS = 2, NP = PX / 2;
     constexpr int CQ = CDIM / 4;
+    constexpr int NV = 8 + CDIM;   // partial sums per Gaussian
     constexpr int NQUAD = 2 + CQ;  // float4 groups flushed per Gaussian
-    __shared__ float4 s_q[BATCH];
-    __shared__ float2 s_c[BATCH];
-    __shared__ int s_idx[BATCH];
-    __shared__ int s_gid[BATCH];
-    __shared__ float4 s_col[BATCH][CQ];
-    __shared__ int s_wcnt[SPT][WARPS];
-    __shared__ __align__(16) float s_acc[WARPS][BATCH][16];
+    using BL = BlkLayout<CDIM>;
+    __shared__ __align__(128) float4 s_blk[2][BL::F4];       // two walk-record blocks in flight
+    constexpr int FL = 64;         // list entries per flush round (half a block: keeps s_acc small, 10+ CTAs per SM)
+    __shared__ __align__(16) float s_acc[WARPS][FL][NV];
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    __shared__ int s_max[WARPS];
 
     const int tile = blockIdx.x;
     const int ti = tile / tile_w, tj = tile - ti * tile_w;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned lt = lanemask_lt();
     const int x = tj * 16 + (lane & 15);
     const int ybase = ti * 16 + 2 * PX * warp + PX * (lane >> 4);
     const float px = (float)x + 0.5f;
-    const float rx0 = (float)(tj * 16) + 0.5f, ry0 = (float)(ti * 16) + 0.5f;
-    const float rx1 = (float)min(tj * 16 + 16, W) - 0.5f, ry1 = (float)min(ti * 16 + 16, H) - 0.5f;
-    const int start = offsets[tile];
-    const int end = (tile == tile_w * tile_h - 1) ? (int)M : offsets[tile + 1];
+    const int start = offsets[tile], end = offsets[tile + 1];
 
-    static_assert(PX % 2 == 0, "pixels travel in pairs");
-    constexpr int NP = PX / 2;  // pixel pairs per thread: rows (ybase + 2 q, ybase + 2 q + 1) are the halves of a float2
     float2 T[NP], Tfvra[NP], npy[NP];
     float2 vrc[NP][CDIM], buf[NP][CDIM];
     int bin[PX];
@@ -415,67 +364,43 @@ k_blend_bwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
             for (int k = 0; k < CDIM; ++k) { vrc[j / 2][k].x = vrcj[k]; buf[j / 2][k].x = 0.f; }
         }
     }
-    // last sorted index any pixel of this tile blended
+    // last list index any pixel of this tile blended
     maxbin = __reduce_max_sync(0xffffffffu, maxbin);
-    if (lane == 0) s_wcnt[0][warp] = maxbin;
+    if (lane == 0) s_max[warp] = maxbin;
+    if (threadIdx.x == 0) {
+        b2s_mbar_init(&s_bar[0], 1);
+        b2s_mbar_init(&s_bar[1], 1);
+    }
     __syncthreads();
-#pragma unroll
-    for (int w = 0; w < WARPS; ++w) maxbin = max(maxbin, s_wcnt[0][w]);
+    maxbin = max(s_max[0], s_max[1]);
     const int hi0 = min(end - 1, maxbin);
+    if (hi0 < start) return;  // nothing was blended in this tile (CTA-uniform)
+    const int nblk = ((hi0 - start) >> 7) + 1;
+    const float4 *blk0 = records + blk_index(start, tile, 0) * BL::F4;
+    if (threadIdx.x == 0) {
+        b2s_mbar_expect_tx(&s_bar[0], BL::BYTES);
+        b2s_bulk_g2s(s_blk[0], blk0 + (size_t)(nblk - 1) * BL::F4, BL::BYTES, &s_bar[0]);
+    }
 
-    for (int hi = hi0; hi >= start; hi -= BATCH) {
-        __syncthreads();  // previous batch fully flushed before its buffers are reused
-        // back to front: slot order == descending sorted index; thread stages entries hi - (q * THREADS + tid)
-        bool keep[SPT];
-        int g[SPT], idx[SPT];
-        float4 q[SPT];
-        float2 c[SPT];
-        unsigned bal[SPT];
-#pragma unroll
-        for (int u = 0; u < SPT; ++u) {
-            idx[u] = hi - (u * THREADS + (int)threadIdx.x);
-            keep[u] = false;
-            g[u] = 0;
-            q[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            c[u] = make_float2(0.f, 0.f);
-            if (idx[u] >= start) {
-                g[u] = flatten_ids[idx[u]];
-                const float2 m = means2d[g[u]];
-                const float4 ge = geo[g[u]];
-                q[u] = make_float4(m.x, m.y, 0.5f * B2S_LOG2E * ge.x, B2S_LOG2E * ge.y);
-                c[u] = make_float2(0.5f * B2S_LOG2E * ge.z, ge.w);
-                keep[u] = tile_keep(m.x, m.y, q[u].z, q[u].w, c[u].x, c[u].y, rx0, ry0, rx1, ry1);
-            }
-            bal[u] = __ballot_sync(0xffffffffu, keep[u]);
-            if (lane == 0) s_wcnt[u][warp] = __popc(bal[u]);
+    for (int k = nblk - 1, it = 0; k >= 0; --k, ++it) {
+        const int st = it & 1;
+        // the other buffer was last read in the previous iteration, which ended with a CTA barrier
+        if (threadIdx.x == 0 && k > 0) {
+            b2s_mbar_expect_tx(&s_bar[st ^ 1], BL::BYTES);
+            b2s_bulk_g2s(s_blk[st ^ 1], blk0 + (size_t)(k - 1) * BL::F4, BL::BYTES, &s_bar[st ^ 1]);
         }
-        __syncthreads();
-        int total = 0;
-#pragma unroll
-        for (int u = 0; u < SPT; ++u) {
-            int off = total;
-#pragma unroll
-            for (int w = 0; w < WARPS; ++w) {
-                const int n = s_wcnt[u][w];
-                off += (w < warp) ? n : 0;
-                total += n;
-            }
-            if (keep[u]) {
-                const int slot = off + __popc(bal[u] & lt);
-                s_q[slot] = q[u];
-                s_c[slot] = c[u];
-                s_idx[slot] = idx[u];
-                s_gid[slot] = g[u];
-#pragma unroll
-                for (int k = 0; k < CQ; ++k) s_col[slot][k] = colpack[(size_t)g[u] * CQ + k];
-            }
-        }
-        __syncthreads();
+        b2s_mbar_wait(&s_bar[st], (it >> 1) & 1);
+        const float4 *s_q = s_blk[st], *s_c = s_blk[st] + BL_BATCH, *s_col = s_blk[st] + 2 * BL_BATCH;
+        const int base = start + (k << 7);
+        const int tmax = min(BL_BATCH - 1, hi0 - base);
 
-        for (int t = 0; t < total; ++t) {
+        for (int t1 = tmax; t1 >= 0; t1 = (t1 & ~(FL - 1)) - 1) {  // flush rounds: entries [t0, t1] share s_acc
+        const int t0 = t1 & ~(FL - 1);
+        if (t1 != tmax) __syncthreads();  // the previous round's flush has read s_acc
+        for (int t = t1; t >= t0; --t) {
             const float4 sq = s_q[t];
-            const float2 sc = s_c[t];
-            const int id = s_idx[t];
+            const float4 sc = s_c[t];
+            const int id = base + t;
             const float dx = sq.x - px;
             float2 dy[NP], al[NP], g[NP];
             bool any_ok = false;
@@ -493,17 +418,17 @@ k_blend_bwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
                 any_ok = any_ok || ok0 || ok1;
             }
             if (!__any_sync(0xffffffffu, any_ok)) {
-                if (lane < 16) s_acc[warp][t][lane] = 0.f;
+                if (lane < NV) s_acc[warp][t - t0][lane] = 0.f;
                 continue;
             }
             float2 v2[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) v2[k] = make_float2(0.f, 0.f);
+            for (int k2 = 0; k2 < 16; ++k2) v2[k2] = make_float2(0.f, 0.f);
             float col[CDIM];
 #pragma unroll
-            for (int k = 0; k < CQ; ++k) {
-                const float4 cv = s_col[t][k];
-                col[4 * k] = cv.x; col[4 * k + 1] = cv.y; col[4 * k + 2] = cv.z; col[4 * k + 3] = cv.w;
+            for (int j = 0; j < CQ; ++j) {
+                const float4 cv = s_col[t * CQ + j];
+                col[4 * j] = cv.x; col[4 * j + 1] = cv.y; col[4 * j + 2] = cv.z; col[4 * j + 3] = cv.w;
             }
             // raw conic (a, b, c) from the log2-domain coefficients: a = 2 A ln2, b = B ln2, c = 2 C ln2
             const float ca = 2.f * B2S_LN2 * sq.z, cb = B2S_LN2 * sq.w, cc = 2.f * B2S_LN2 * sc.x;
@@ -512,30 +437,26 @@ k_blend_bwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
                 pair_grad<CDIM>(v2, T[q], buf[q], vrc[q], Tfvra[q], col, ca, cb, cc, sc.y, dx, dy[q], al[q], g[q]);
             float v[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) v[k] = k < 8 + CDIM ? v2[k].x + v2[k].y : 0.f;
-            const float r = warp_reduce16_transposed<8 + CDIM>(v, lane);
-            if (!(lane & 1)) s_acc[warp][t][lane >> 1] = r;
+            for (int k2 = 0; k2 < 16; ++k2) v[k2] = k2 < NV ? v2[k2].x + v2[k2].y : 0.f;
+            const float r = warp_reduce16_transposed<NV>(v, lane);
+            if (!(lane & 1) && (lane >> 1) < NV) s_acc[warp][t - t0][lane >> 1] = r;
         }
         __syncthreads();
 
-        // flush: item = (slot, quad); consecutive threads read consecutive float4s of s_acc (conflict free)
-#pragma unroll
-        for (int j = 0; j < 4 * BATCH / THREADS; ++j) {
-            const int item = (int)threadIdx.x + THREADS * j;
+        // flush: item = (slot, quad); sum over the two warps, one 16-byte vector reduction per non-zero quad
+        const int nitem = (t1 - t0 + 1) * 4;
+        for (int item = (int)threadIdx.x; item < nitem; item += THREADS) {
             const int slot = item >> 2, quad = item & 3;
-            if (slot < total && quad < NQUAD) {
-                float4 s = reinterpret_cast<const float4 *>(&s_acc[0][slot][0])[quad];
-#pragma unroll
-                for (int w = 1; w < WARPS; ++w) {
-                    const float4 o = reinterpret_cast<const float4 *>(&s_acc[w][slot][0])[quad];
-                    s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
-                }
+            if (quad < NQUAD) {
+                float4 s = *reinterpret_cast<const float4 *>(&s_acc[0][slot][4 * quad]);
+                const float4 o = *reinterpret_cast<const float4 *>(&s_acc[1][slot][4 * quad]);
+                s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
                 // undo the accumulation convention of pair_grad: quad 0 = (-v_x, -v_y, |v_x|, |v_y|),
                 // quad 1 = (-2 v_conic_a, -v_conic_b, -2 v_conic_c, v_opacity), quads >= 2 = v_colour
                 if (quad == 0) { s.x = -s.x; s.y = -s.y; }
                 if (quad == 1) { s.x = -0.5f * s.x; s.y = -s.y; s.z = -0.5f * s.z; }
                 if (s.x != 0.f || s.y != 0.f || s.z != 0.f || s.w != 0.f) {
-                    const int gid = s_gid[slot];
+                    const int gid = __float_as_int(s_c[t0 + slot].z);
                     float *dst = quad == 0 ? v_xyabs + (size_t)gid * 4
                                : quad == 1 ? v_geo + (size_t)gid * 4
                                            : v_colpack + (size_t)gid * CDIM + (quad - 2) * 4;
@@ -543,6 +464,8 @@ k_blend_bwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
                 }
             }
         }
+        }  // flush rounds
+        __syncthreads();  // s_acc and this record buffer are free again
     }
 }
 
@@ -551,37 +474,21 @@ k_blend_bwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
 // ------------------------------------------------------------------------------------------------
 template <int CDIM, int DOUT, bool ED>
 static int launch_fwd(const float *means2d, const float *geo, const float *colpack, const int32_t *offsets,
-                      const int32_t *flatten_ids, long long M, int W, int H, int tile_w, int tile_h, float *render,
-                      float *alpha, int32_t *last_ids, cudaStream_t st) {
+                      const int32_t *ids, int W, int H, int tile_w, int tile_h, float *render, float *alpha,
+                      int32_t *last_ids, float *records, cudaStream_t st) {
     k_blend_fwd<CDIM, DOUT, ED><<<tile_w * tile_h, BL_THREADS, 0, st>>>(
-        (const float2 *)means2d, (const float4 *)geo, (const float4 *)colpack, offsets, flatten_ids, M, W, H, tile_w,
-        tile_h, render, alpha, last_ids);
+        (const float2 *)means2d, (const float4 *)geo, (const float4 *)colpack, offsets, ids, W, H, tile_w, render, alpha,
+        last_ids, (float4 *)records);
     B2S_LAUNCH_CHECK();
     return B2S_OK;
 }
 template <int CDIM, int DOUT, bool ED>
-static int launch_bwd(const float *means2d, const float *geo, const float *colpack, const int32_t *offsets,
-                      const int32_t *flatten_ids, long long M, int W, int H, int tile_w, int tile_h,
+static int launch_bwd(const int32_t *offsets, const float *records, int W, int H, int tile_w, int tile_h,
                       const float *render, const float *alpha, const int32_t *last_ids, const float *v_render,
                       const float *v_alpha, float *v_xyabs, float *v_geo, float *v_colpack, cudaStream_t st) {
-    // pixels per thread in the backward (see k_blend_bwd); B2S_BWD_PX=2 selects the 128-thread variant (tuning knob)
-    static const int px = [] {
-        const char *e = getenv("B2S_BWD_PX");
-        const int v = e ? atoi(e) : 4;
-        return (v == 2 || v == 8) ? v : 4;
-    }();
-    if (px == 2)
-        k_blend_bwd<CDIM, DOUT, ED, 2><<<tile_w * tile_h, 128, 0, st>>>(
-            (const float2 *)means2d, (const float4 *)geo, (const float4 *)colpack, offsets, flatten_ids, M, W, H, tile_w,
-            tile_h, render, alpha, last_ids, v_render, v_alpha, v_xyabs, v_geo, v_colpack);
-    else if (px == 8)
-        k_blend_bwd<CDIM, DOUT, ED, 8><<<tile_w * tile_h, 32, 0, st>>>(
-            (const float2 *)means2d, (const float4 *)geo, (const float4 *)colpack, offsets, flatten_ids, M, W, H, tile_w,
-            tile_h, render, alpha, last_ids, v_render, v_alpha, v_xyabs, v_geo, v_colpack);
-    else
-        k_blend_bwd<CDIM, DOUT, ED, 4><<<tile_w * tile_h, 64, 0, st>>>(
-            (const float2 *)means2d, (const float4 *)geo, (const float4 *)colpack, offsets, flatten_ids, M, W, H, tile_w,
-            tile_h, render, alpha, last_ids, v_render, v_alpha, v_xyabs, v_geo, v_colpack);
+    k_blend_bwd<CDIM, DOUT, ED><<<tile_w * tile_h, 64, 0, st>>>(offsets, (const float4 *)records, W, H, tile_w, render,
+                                                                alpha, last_ids, v_render, v_alpha, v_xyabs, v_geo,
+                                                                v_colpack);
     B2S_LAUNCH_CHECK();
     return B2S_OK;
 }
@@ -609,24 +516,30 @@ static int launch_bwd(const float *means2d, const float *geo, const float *colpa
         return B2S_ERR_UNSUPPORTED;                                                                \
     } while (0)
 
-extern "C" int b2s_blend_fwd(const float *means2d, const float *geo, const float *colpack,
-                             const int32_t *isect_offsets, const int32_t *flatten_ids, long long M, int W, int H,
-                             int tile_w, int tile_h, int cdim, int d_out, int expected_depth, float *render,
-                             float *alpha, int32_t *last_ids, b2s_stream_t stream) {
-    if (W <= 0 || H <= 0 || M < 0 || tile_w * 16 < W || tile_h * 16 < H) return B2S_ERR_ARG;
-    cudaStream_t st = (cudaStream_t)stream;
-    B2S_DISPATCH(launch_fwd, means2d, geo, colpack, isect_offsets, flatten_ids, M, W, H, tile_w, tile_h, render,
-                 alpha, last_ids, st);
+extern "C" size_t b2s_blend_record_bytes(long long list_capacity, int n_tiles, int cdim) {
+    if (list_capacity < 0 || n_tiles < 0 || (cdim != 4 && cdim != 8)) return 0;
+    const size_t blocks = (size_t)(list_capacity >> 7) + (size_t)n_tiles + 1;
+    return blocks * (size_t)BL_BATCH * 16 * (size_t)(2 + cdim / 4);
 }
 
-extern "C" int b2s_blend_bwd(const float *means2d, const float *geo, const float *colpack,
-                             const int32_t *isect_offsets, const int32_t *flatten_ids, long long M, int W, int H,
-                             int tile_w, int tile_h, int cdim, int d_out, int expected_depth, const float *render,
-                             const float *alpha, const int32_t *last_ids, const float *v_render,
-                             const float *v_alpha, float *v_xyabs, float *v_geo, float *v_colpack,
-                             b2s_stream_t stream) {
-    if (W <= 0 || H <= 0 || M < 0 || tile_w * 16 < W || tile_h * 16 < H) return B2S_ERR_ARG;
+extern "C" int b2s_blend_fwd(const float *means2d, const float *geo, const float *colpack,
+                             const int32_t *tile_offsets, const int32_t *tile_ids, int W, int H, int tile_w, int tile_h,
+                             int cdim, int d_out, int expected_depth, float *render, float *alpha, int32_t *last_ids,
+                             float *records, b2s_stream_t stream) {
+    if (W <= 0 || H <= 0 || tile_w * 16 < W || tile_h * 16 < H) return B2S_ERR_ARG;
+    if (records != nullptr && ((uintptr_t)records & 127)) return B2S_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    B2S_DISPATCH(launch_bwd, means2d, geo, colpack, isect_offsets, flatten_ids, M, W, H, tile_w, tile_h, render,
-                 alpha, last_ids, v_render, v_alpha, v_xyabs, v_geo, v_colpack, st);
+    B2S_DISPATCH(launch_fwd, means2d, geo, colpack, tile_offsets, tile_ids, W, H, tile_w, tile_h, render, alpha, last_ids,
+                 records, st);
+}
+
+extern "C" int b2s_blend_bwd(const int32_t *tile_offsets, const float *records, int W, int H, int tile_w, int tile_h,
+                             int cdim, int d_out, int expected_depth, const float *render, const float *alpha,
+                             const int32_t *last_ids, const float *v_render, const float *v_alpha, float *v_xyabs,
+                             float *v_geo, float *v_colpack, b2s_stream_t stream) {
+    if (W <= 0 || H <= 0 || tile_w * 16 < W || tile_h * 16 < H || records == nullptr) return B2S_ERR_ARG;
+    if ((uintptr_t)records & 127) return B2S_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    B2S_DISPATCH(launch_bwd, tile_offsets, records, W, H, tile_w, tile_h, render, alpha, last_ids, v_render, v_alpha,
+                 v_xyabs, v_geo, v_colpack, st);
 }

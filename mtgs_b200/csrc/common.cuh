@@ -10,6 +10,7 @@
 #define B2S_T_EPS 1e-4f
 #define B2S_LOG2E 1.4426950408889634f
 #define B2S_LN2 0.6931471805599453f
+#define B2S_N_TOTALS 9  // list sizes written by the projection: see b2s_project_fwd in include/b200splat.h
 
 // Diagnostic launch counter (api.cu): the library's only mutable global; atomic, never read by a kernel launch path.
 void b2s_count_launch(int n);
@@ -57,6 +58,73 @@ __device__ __forceinline__ float4 ldg_stream4(const float4 *p) {
                  : "l"(p));
     return v;
 }
+
+// Can this Gaussian reach alpha >= 1/255 at any pixel centre of the rectangle [rx0,rx1]x[ry0,ry1]?
+// Conservative (never drops a contributing pair): exact box-constrained minimum of the convex quadratic,
+// compared with log2(255 * opacity) plus a slack that dominates fp32 evaluation error.
+__device__ __forceinline__ bool tile_keep(float mx, float my, float A, float B, float C, float opac, float rx0,
+                                          float ry0, float rx1, float ry1) {
+    if (!(opac >= 0.0039f)) return false;  // opac * e^-sigma <= opac < 1/255 (also drops NaN)
+    float ex = fminf(fmaxf(mx, rx0), rx1) - mx;  // nearest pixel-centre coordinate minus mean (0 if inside)
+    float ey = fminf(fmaxf(my, ry0), ry1) - my;
+    if (ex == 0.f && ey == 0.f) return true;
+    float tau = __log2f(opac * 255.0f);
+    float smin = 3.0e38f, mag = 0.f;
+    if (ex != 0.f) {  // facing vertical edge: dx fixed, minimise over dy
+        float dy = fminf(fmaxf(-B * ex / (2.f * C), ry0 - my), ry1 - my);
+        float t0 = A * ex * ex, t1 = B * ex * dy, t2 = C * dy * dy;
+        float s = t0 + t1 + t2;
+        if (s < smin) { smin = s; mag = fabsf(t0) + fabsf(t1) + fabsf(t2); }
+    }
+    if (ey != 0.f) {  // facing horizontal edge
+        float dx = fminf(fmaxf(-B * ey / (2.f * A), rx0 - mx), rx1 - mx);
+        float t0 = A * dx * dx, t1 = B * dx * ey, t2 = C * ey * ey;
+        float s = t0 + t1 + t2;
+        if (s < smin) { smin = s; mag = fabsf(t0) + fabsf(t1) + fabsf(t2); }
+    }
+    return !(smin > tau + 0.02f + 2e-5f * mag);  // NaN-safe: keep on NaN
+}
+
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) and mbarriers ----
+__device__ __forceinline__ unsigned b2s_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void b2s_mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b2s_smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void b2s_mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b2s_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void b2s_mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "B2S_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra B2S_DONE;\n"
+        "bra B2S_WAIT;\n"
+        "B2S_DONE:\n"
+        "}\n" ::"r"(b2s_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void b2s_bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     b2s_smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(b2s_smem_u32(bar))
+                 : "memory");
+}
+// shared -> global through the bulk async-group of the issuing thread
+__device__ __forceinline__ void b2s_bulk_s2g(void *dst_gmem, const void *src_smem, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(b2s_smem_u32(src_smem)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void b2s_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the issuing thread's bulk stores have finished READING shared memory (the buffer may be overwritten)
+__device__ __forceinline__ void b2s_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// generic-proxy writes to shared memory become visible to the async proxy (TMA)
+__device__ __forceinline__ void b2s_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Peer-memory description of the multi-GPU gradient exchange (exchange.cu), passed to kernels by value.
 #define B2S_MAX_WORLD 8

@@ -8,9 +8,8 @@
 // GAUSSIANS by depth bits followed by an order-preserving bucketing of their intersections by tile (tilelists.cu)
 // gives bit-identical flatten_ids / isect_offsets without ever sorting M 64-bit keys.  This file produces
 //     order[0 .. n_vis)  Gaussian ids in stable depth order (ties: ascending id), culled Gaussians dropped
-//     totals[5]          M = tile intersections, S = tile-row hits, E1 / E3 = row-group and (row, column-group) hits
-//                        (the list sizes of the tile-list hierarchy, tilelists.cu), n_vis
-//     n_vis
+//     n_vis              (the list sizes of the tile-list hierarchy are summed by the projection kernel, so that their
+//                        device->host copy overlaps this sort)
 //
 // A multi-launch LSD radix sort of 2 M keys spent most of its time in launch/drain gaps between ~15 small
 // kernels.  Here a single persistent grid (one launch, cudaLaunchCooperativeKernel, all CTAs co-resident) runs
@@ -68,10 +67,9 @@ __device__ __forceinline__ int ds_block_excl_scan(int v, int *total, int *s_w) {
 }
 
 __global__ void __launch_bounds__(DS_THREADS)
-k_depth_sort_coop(const uint32_t *__restrict__ keys_in, const int32_t *__restrict__ tiles_per_gauss, int N,
+k_depth_sort_coop(const uint32_t *__restrict__ keys_in, int N,
                   uint32_t *kA, uint32_t *vA, uint32_t *kB, uint32_t *vB /* == order */, int32_t *table /* [BINS][G] */,
-                  int32_t *digit_tot /* [BINS] */, const int2 *__restrict__ rects, int rg_shift, int cg_shift,
-                  int64_t *totals_out /* [5]: M, S, E1, E3, n_vis */, int32_t *nvis_out) {
+                  int32_t *digit_tot /* [BINS] */, int32_t *nvis_out) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ int ds_smem[];
     int *s_cnt = ds_smem;                           // [DS_WARPS][DS_BINS]
@@ -80,7 +78,6 @@ k_depth_sort_coop(const uint32_t *__restrict__ keys_in, const int32_t *__restric
     const int G = gridDim.x, b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = lanemask_lt();
-    if (b == 0 && tid == 0) totals_out[0] = totals_out[1] = totals_out[2] = totals_out[3] = 0;  // summed at the end
 
     int n = N;  // items entering the current pass
     for (int pass = 0; pass < DS_PASSES; ++pass) {
@@ -135,10 +132,7 @@ k_depth_sort_coop(const uint32_t *__restrict__ keys_in, const int32_t *__restric
                 ex += loc[k];
             }
             if (pass == 0) {
-                if (b == 0 && tid == 0) {
-                    *nvis_out = tot;
-                    totals_out[4] = tot;
-                }
+                if (b == 0 && tid == 0) *nvis_out = tot;
                 n = tot;  // later passes (and their slices) only see the visible Gaussians
             }
         }
@@ -196,38 +190,6 @@ k_depth_sort_coop(const uint32_t *__restrict__ keys_in, const int32_t *__restric
         grid.sync();
     }
 
-    // ---- totals over the visible Gaussians (sizes of the tile-list hierarchy, tilelists.cu): M = tile
-    // intersections, S = tile-row hits, E1 = row-group hits, E3 = (row, column-group) hits
-    const uint32_t *order = vB;
-    const int per = (n + G - 1) / G;
-    const int begin = min(n, b * per), end = min(n, begin + per);
-    long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
-    for (int i = begin + tid; i < end; i += DS_THREADS) {
-        const int g = (int)order[i];
-        const int2 rc = rects[g];
-        const int x0 = rc.x & 0xffff, x1 = (rc.x >> 16) & 0xffff, y0 = rc.y & 0xffff, y1 = (rc.y >> 16) & 0xffff;
-        const int h = max(0, y1 - y0), w = max(0, x1 - x0);
-        const int rgc = h > 0 ? ((y1 - 1) >> rg_shift) - (y0 >> rg_shift) + 1 : 0;
-        const int cgc = w > 0 ? ((x1 - 1) >> cg_shift) - (x0 >> cg_shift) + 1 : 0;
-        t0 += tiles_per_gauss[g];
-        t1 += h;
-        t2 += rgc;
-        t3 += (long long)h * cgc;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        t0 += __shfl_xor_sync(0xffffffffu, t0, o);
-        t1 += __shfl_xor_sync(0xffffffffu, t1, o);
-        t2 += __shfl_xor_sync(0xffffffffu, t2, o);
-        t3 += __shfl_xor_sync(0xffffffffu, t3, o);
-    }
-    if (lane == 0 && t1 > 0) {
-        unsigned long long *t = reinterpret_cast<unsigned long long *>(totals_out);
-        atomicAdd(t + 0, (unsigned long long)t0);
-        atomicAdd(t + 1, (unsigned long long)t1);
-        atomicAdd(t + 2, (unsigned long long)t2);
-        atomicAdd(t + 3, (unsigned long long)t3);
-    }
 }
 
 static inline size_t ds_align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -252,16 +214,12 @@ extern "C" size_t b2s_bin_depth_workspace_bytes(int N) {
     return 3 * ds_align256(n * 4) + ds_align256((size_t)DS_BINS * 2048 * 4) + ds_align256(DS_BINS * 4) + 1024;
 }
 
-extern "C" int b2s_bin_sort_depth(const uint32_t *sort_keys, const int32_t *tiles_per_gauss, const int32_t *tile_rects,
-                                  int N, int tile_w, int tile_h, int32_t *order, int64_t *totals, int32_t *n_vis,
+extern "C" int b2s_bin_sort_depth(const uint32_t *sort_keys, int N, int32_t *order, int32_t *n_vis,
                                   void *workspace, size_t workspace_bytes, b2s_stream_t stream) {
     if (N < 0) return B2S_ERR_ARG;
-    int rg_shift = 0, cg_shift = 0;
-    if (b2s_tl_shifts(tile_w, tile_h, &rg_shift, &cg_shift) != B2S_OK) return B2S_ERR_UNSUPPORTED;
     if (workspace_bytes < b2s_bin_depth_workspace_bytes(N)) return B2S_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     if (N == 0) {
-        cudaMemsetAsync(totals, 0, 5 * sizeof(int64_t), st);
         cudaMemsetAsync(n_vis, 0, sizeof(int32_t), st);
         return B2S_OK;
     }
@@ -279,11 +237,8 @@ extern "C" int b2s_bin_sort_depth(const uint32_t *sort_keys, const int32_t *tile
     int32_t *table = (int32_t *)w; w += ds_align256((size_t)DS_BINS * 2048 * 4);
     int32_t *digit_tot = (int32_t *)w;
     uint32_t *vB = (uint32_t *)order;
-    const int2 *rects = (const int2 *)tile_rects;
-    void *args[] = {(void *)&sort_keys, (void *)&tiles_per_gauss, (void *)&N,        (void *)&kA,
-                    (void *)&vA,        (void *)&kB,              (void *)&vB,       (void *)&table,
-                    (void *)&digit_tot, (void *)&rects,           (void *)&rg_shift, (void *)&cg_shift,
-                    (void *)&totals,    (void *)&n_vis};
+    void *args[] = {(void *)&sort_keys, (void *)&N,     (void *)&kA,        (void *)&vA,   (void *)&kB,
+                    (void *)&vB,        (void *)&table, (void *)&digit_tot, (void *)&n_vis};
     cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_depth_sort_coop, dim3(G), dim3(DS_THREADS), args,
                                                 DS_SMEM, st);
     if (e != cudaSuccess) {

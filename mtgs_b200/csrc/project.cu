@@ -96,9 +96,15 @@ k_project_fwd(const float *__restrict__ means, const float *__restrict__ quats, 
               int d_in, int with_depth, int32_t *__restrict__ radii, float2 *__restrict__ means2d,
               float *__restrict__ depths, float4 *__restrict__ geo, float *__restrict__ comps,
               float *__restrict__ colpack, int32_t *__restrict__ tiles_per_gauss,
-              uint32_t *__restrict__ sort_keys, int2 *__restrict__ tile_rects) {
-    int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= N) return;
+              uint32_t *__restrict__ sort_keys, int2 *__restrict__ tile_rects, int2 *__restrict__ tight_rects,
+              int rg_shift, int cg_shift, unsigned long long *__restrict__ totals /* [B2S_N_TOTALS], pre-zeroed */,
+              float4 *__restrict__ bwd_arena /* [N * (2 + CDIM / 4)] or null: zero-filled for the blend backward */) {
+    __shared__ int s_tot[B2S_N_TOTALS];
+    if (threadIdx.x < B2S_N_TOTALS) s_tot[threadIdx.x] = 0;
+    __syncthreads();
+    const int g_raw = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = g_raw < N;
+    const int g = valid ? g_raw : N - 1;  // out-of-range threads recompute the last Gaussian and write nothing
     CamParams cam;
     load_camera(viewmat, K, W, H, cam);
 
@@ -111,6 +117,7 @@ k_project_fwd(const float *__restrict__ means, const float *__restrict__ quats, 
     int32_t radius_i = 0;
     int32_t ntiles = 0;
     int2 rect = make_int2(0, 0);  // (x0 | x1 << 16, y0 | y1 << 16) in tiles, max exclusive
+    int rx0 = 0, rx1 = 0, ry0 = 0, ry1 = 0;
     float mx = 0.f, my = 0.f, ca = 0.f, cb = 0.f, cc = 0.f, comp = 1.f;
     float z = pc[2];
     bool ok = !(z < near_plane || z > far_plane);
@@ -169,19 +176,80 @@ k_project_fwd(const float *__restrict__ means, const float *__restrict__ quats, 
                 int y1 = fy1 <= 0.f ? 0 : (fy1 >= (float)tile_h ? tile_h : (int)fy1);
                 ntiles = (y1 - y0) * (x1 - x0);
                 rect = make_int2(x0 | (x1 << 16), y0 | (y1 << 16));
+                rx0 = x0; rx1 = x1; ry0 = y0; ry1 = y1;
             }
         }
+    }
+    // ---- tight rectangle for the blend's own tile lists: tiles whose pixel centres the footprint
+    // {alpha >= 1/255} = {sigma <= ln(255 opacity)} can reach, intersected with upstream's 3-sigma rectangle.  Not
+    // part of upstream's outputs (info["tiles_per_gauss"] / flatten_ids stay upstream's): it only removes
+    // (Gaussian, tile) pairs that contribute to no pixel.  Extents of the ellipse defined by the STORED conic (what
+    // the blend evaluates), discriminant in double (4AC - B^2 cancels for thin splats), plus slack for the blend's
+    // fp32 evaluation error; the exact per-tile test follows in the last level of the tile lists.
+    float op = 0.f;
+    int2 trect = make_int2(0, 0);
+    int tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0;
+    if (radius_i > 0) {
+        op = opacities[g];
+        if (calc_comp) op = MUL(op, comp);
+        if (op >= 0.0039f) {
+            tx0 = rx0; tx1 = rx1; ty0 = ry0; ty1 = ry1;
+            const float A2 = (0.5f * B2S_LOG2E) * ca, B2 = B2S_LOG2E * cb, C2 = (0.5f * B2S_LOG2E) * cc;
+            const double disc = 4.0 * (double)A2 * (double)C2 - (double)B2 * (double)B2;
+            if (disc > 0.0 && A2 > 0.f && C2 > 0.f) {
+                const float Rb = (float)radius_i + 16.0f;
+                const float tau = __log2f(op * 255.0f) + 0.02f + 4e-7f * (A2 + fabsf(B2) + C2) * Rb * Rb;
+                const float hx = fminf((float)sqrt(4.0 * (double)C2 * (double)tau / disc) * 1.0001f + 0.01f, 1e6f);
+                const float hy = fminf((float)sqrt(4.0 * (double)A2 * (double)tau / disc) * 1.0001f + 0.01f, 1e6f);
+                // tile k holds the pixel centres 16 k + 0.5 .. 16 k + 15.5
+                const float mxc = fminf(fmaxf(mx, -1e6f), 1e6f), myc = fminf(fmaxf(my, -1e6f), 1e6f);
+                tx0 = max(tx0, (int)ceilf((mxc - hx - 15.5f) * 0.0625f));
+                tx1 = min(tx1, (int)floorf((mxc + hx - 0.5f) * 0.0625f) + 1);
+                ty0 = max(ty0, (int)ceilf((myc - hy - 15.5f) * 0.0625f));
+                ty1 = min(ty1, (int)floorf((myc + hy - 0.5f) * 0.0625f) + 1);
+            }
+            if (tx1 <= tx0 || ty1 <= ty0) tx0 = tx1 = ty0 = ty1 = 0;
+            trect = make_int2(tx0 | (tx1 << 16), ty0 | (ty1 << 16));
+        }
+    }
+    // ---- list sizes of both tile-list builds (tilelists.cu): upstream's rectangles [0..3], tight rectangles [4..7],
+    // visible Gaussians [8]; one integer warp reduction (redux.sync) per value, 9 atomics per CTA
+    {
+        int v[B2S_N_TOTALS];
+        const int h = ry1 - ry0, w = rx1 - rx0, th_ = ty1 - ty0, tw_ = tx1 - tx0;
+        v[0] = valid ? ntiles : 0;
+        v[1] = valid ? h : 0;
+        v[2] = (valid && h > 0) ? ((ry1 - 1) >> rg_shift) - (ry0 >> rg_shift) + 1 : 0;
+        v[3] = (valid && w > 0) ? h * (((rx1 - 1) >> cg_shift) - (rx0 >> cg_shift) + 1) : 0;
+        v[4] = valid ? th_ * tw_ : 0;
+        v[5] = valid ? th_ : 0;
+        v[6] = (valid && th_ > 0) ? ((ty1 - 1) >> rg_shift) - (ty0 >> rg_shift) + 1 : 0;
+        v[7] = (valid && tw_ > 0) ? th_ * (((tx1 - 1) >> cg_shift) - (tx0 >> cg_shift) + 1) : 0;
+        v[8] = (valid && radius_i > 0) ? 1 : 0;
+#pragma unroll
+        for (int k = 0; k < B2S_N_TOTALS; ++k) {
+            const int sum = __reduce_add_sync(0xffffffffu, v[k]);
+            if ((threadIdx.x & 31) == 0 && sum != 0) atomicAdd(&s_tot[k], sum);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < B2S_N_TOTALS && s_tot[threadIdx.x] != 0)
+        atomicAdd(totals + threadIdx.x, (unsigned long long)s_tot[threadIdx.x]);
+    if (!valid) return;
+    if (bwd_arena != nullptr) {
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        bwd_arena[g] = z4;
+        bwd_arena[(size_t)N + g] = z4;
+#pragma unroll
+        for (int k = 0; k < CDIM / 4; ++k) bwd_arena[2 * (size_t)N + (size_t)g * (CDIM / 4) + k] = z4;
     }
     radii[g] = radius_i;
     tiles_per_gauss[g] = ntiles;
     tile_rects[g] = rect;
+    tight_rects[g] = trect;
     sort_keys[g] = radius_i > 0 ? __float_as_uint(z) : 0xFFFFFFFFu;
     if (radius_i > 0) {
-        float op = opacities[g];
-        if (calc_comp) {
-            comps[g] = comp;
-            op = MUL(op, comp);
-        }
+        if (calc_comp) comps[g] = comp;
         means2d[g] = make_float2(mx, my);
         depths[g] = z;
         geo[g] = make_float4(ca, cb, cc, op);
@@ -496,9 +564,11 @@ extern "C" int b2s_project_fwd(const float *means, const float *quats, const flo
                                float eps2d, float near_plane, float far_plane, float radius_clip, int calc_comp,
                                int d_in, int with_depth, int cdim, int32_t *radii, float *means2d, float *depths,
                                float *geo, float *comps, float *colpack, int32_t *tiles_per_gauss,
-                               uint32_t *sort_keys, int32_t *tile_rects,
-                               b2s_stream_t stream) {
-    if (N < 0 || W <= 0 || H <= 0) return B2S_ERR_ARG;
+                               uint32_t *sort_keys, int32_t *tile_rects, int32_t *tight_rects, int64_t *totals,
+                               float *bwd_arena, b2s_stream_t stream) {
+    if (N < 0 || W <= 0 || H <= 0 || totals == nullptr || tight_rects == nullptr) return B2S_ERR_ARG;
+    int rg_shift = 0, cg_shift = 0;
+    if (b2s_tl_shifts(tile_w, tile_h, &rg_shift, &cg_shift) != B2S_OK) return B2S_ERR_UNSUPPORTED;
     if (tile_size != 16 || tile_w > 32767 || tile_h > 32767) return B2S_ERR_UNSUPPORTED;
     if (cdim != 4 && cdim != 8) return B2S_ERR_UNSUPPORTED;
     if (d_in < 0 || d_in + (with_depth ? 1 : 0) > cdim) return B2S_ERR_ARG;
@@ -511,7 +581,8 @@ extern "C" int b2s_project_fwd(const float *means, const float *quats, const flo
                                               tile_w, tile_h, eps2d, near_plane, far_plane, radius_clip,     \
                                               calc_comp, d_in, with_depth, radii, (float2 *)means2d, depths, \
                                               (float4 *)geo, comps, colpack, tiles_per_gauss, sort_keys, \
-                                              (int2 *)tile_rects)
+                                              (int2 *)tile_rects, (int2 *)tight_rects, rg_shift, cg_shift,  \
+                                              (unsigned long long *)totals, (float4 *)bwd_arena)
     if (cdim == 4) LAUNCH(4);
     else LAUNCH(8);
 #undef LAUNCH

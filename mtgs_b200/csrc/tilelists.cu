@@ -37,6 +37,9 @@ static inline int tl_ch(int k) { return (k <= 2 ? 128 : 256) * TL_WARPS; }
 
 struct TlGeom {
     int tile_w, tile_h;
+    int W, H;                // image size in pixels (exact mode: pixel-centre boxes of the tiles)
+    int exact;               // level 4 keeps only (Gaussian, tile) pairs that can reach alpha >= 1/255 (tile_keep)
+    int offs_total;          // isect_offsets has tile_w * tile_h + 1 entries; the last one receives the list length
     int rg_shift, cg_shift;  // tile rows per row group = 1 << rg_shift, tile columns per column group = 1 << cg_shift
     int nrg, ncg;            // number of row groups / column groups (<= 32)
 };
@@ -155,14 +158,36 @@ __device__ __forceinline__ int tl_slice_count(const TlGeom &g, int NB, int L, in
     return tl_warp_incl_scan(s_d[lane], lane);  // lanes >= NB hold garbage-free zeros or are ignored by the callers
 }
 
+// Exact mode, level 4: bit b of the result = "the Gaussian of item `it` can reach alpha >= 1/255 at a pixel centre of
+// child tile b of list L" (tile_keep, the test the blend kernels used to run while staging; conservative, so the
+// image is unchanged).  Only the children [lo, hi) of the item's tight column range are tested.
+__device__ __forceinline__ unsigned tl_tile_mask(const TlGeom &g, int L, int2 it, const float2 *__restrict__ means2d,
+                                                 const float4 *__restrict__ geo) {
+    int lo, hi;
+    tl_bins<4>(it.y, L, g, lo, hi);
+    if (hi <= lo) return 0u;
+    const float2 m = means2d[it.x];
+    const float4 ge = geo[it.x];
+    const float A = 0.5f * B2S_LOG2E * ge.x, B = B2S_LOG2E * ge.y, C = 0.5f * B2S_LOG2E * ge.z;
+    const int ty = L / g.ncg, tx0 = (L % g.ncg) << g.cg_shift;
+    const float ry0 = (float)(ty * 16) + 0.5f, ry1 = (float)min(ty * 16 + 16, g.H) - 0.5f;
+    unsigned mask = 0u;
+    for (int b = lo; b < hi; ++b) {
+        const int tx = tx0 + b;
+        const float rx0 = (float)(tx * 16) + 0.5f, rx1 = (float)min(tx * 16 + 16, g.W) - 0.5f;
+        if (tile_keep(m.x, m.y, A, B, C, ge.w, rx0, ry0, rx1, ry1)) mask |= 1u << b;
+    }
+    return mask;
+}
+
 // ---- count: table[b * nch + c] = items of chunk c covering child b
 template <int K>
 __global__ void __launch_bounds__(32 * TL_WARPS)
-k_level_count(const TlGeom g, const int2 *__restrict__ in, const int32_t *__restrict__ order,
+k_level_count(const TlGeom g, int2 *__restrict__ in, const int32_t *__restrict__ order,
               const int2 *__restrict__ rects, const int32_t *__restrict__ n_vis, int nlists,
               const int32_t *__restrict__ list_off, const int32_t *__restrict__ chunk_off, int nch,
               int32_t *__restrict__ table, int32_t *__restrict__ slice_cnt /* [nch][TL_WARPS][32] */,
-              unsigned *__restrict__ ticket) {
+              unsigned *__restrict__ ticket, const float2 *__restrict__ means2d, const float4 *__restrict__ geo) {
     __shared__ int s_cnt[TL_WARPS][32];
     __shared__ int s_diff[TL_WARPS][33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -172,7 +197,24 @@ k_level_count(const TlGeom g, const int2 *__restrict__ in, const int32_t *__rest
     if (!tl_chunk<K>(c, nlists, list_off, chunk_off, n_vis, L, begin, end)) return;  // CTA-uniform
     const int NB = tl_nb<K>(g);
     const int sb = min(end, begin + warp * TlCh<K>::slice), se = min(end, sb + TlCh<K>::slice);
-    const int mine = tl_slice_count<K>(g, NB, L, sb, se, lane, s_diff[warp], in, order, rects);
+    int mine;
+    if (K == 4 && g.exact) {
+        // exact tile masks, stored in place of the item's column range for the fill kernel
+        mine = 0;
+        for (int i0 = sb; i0 < se; i0 += 32) {
+            unsigned mask = 0u;
+            if (i0 + lane < se) {
+                mask = tl_tile_mask(g, L, in[i0 + lane], means2d, geo);
+                in[i0 + lane].y = (int)mask;
+            }
+            for (int b = 0; b < NB; ++b) {
+                const int c = __popc(__ballot_sync(0xffffffffu, (mask >> b) & 1u));
+                if (lane == b) mine += c;
+            }
+        }
+    } else {
+        mine = tl_slice_count<K>(g, NB, L, sb, se, lane, s_diff[warp], in, order, rects);
+    }
     s_cnt[warp][lane] = lane < NB ? mine : 0;
     __syncthreads();
     // exclusive prefix over the slices (read back by the fill kernel) and the chunk's total
@@ -304,6 +346,7 @@ k_level_prefix(const TlGeom g, const int32_t *__restrict__ n_vis, int nlists, co
     if (tid == 0) {
         out_off[nout] = carry_e;
         if (K < 4) out_chunk_off[nout] = carry_c;
+        if (K == 4 && g.offs_total) isect_offsets[g.tile_w * g.tile_h] = carry_e;
     }
 }
 
@@ -332,12 +375,14 @@ k_level_fill(const TlGeom g, const int2 *__restrict__ in, const int32_t *__restr
     for (int i0 = sb; i0 < se; i0 += 32) {
         const int2 it = nxt;
         int lo = 0, hi = 0;
-        if (i0 + lane < se) tl_bins<K>(it.y, L, g, lo, hi);
+        const bool masked = K == 4 && g.exact;  // it.y holds the exact tile mask written by the count kernel
+        if (i0 + lane < se && !masked) tl_bins<K>(it.y, L, g, lo, hi);
+        const unsigned mask = (masked && i0 + lane < se) ? (unsigned)it.y : 0u;
         if (i0 + 32 + lane < se) nxt = tl_item<K>(i0 + 32 + lane, in, order, rects);  // prefetch
         int2 pay = it;
         if (K == 2 && hi > lo) pay.y = rects[it.x].x;  // rows are resolved: carry the column range from here on
         for (int b = 0; b < NB; ++b) {
-            const bool hit = lo <= b && b < hi;
+            const bool hit = masked ? ((mask >> b) & 1u) != 0u : (lo <= b && b < hi);
             const unsigned bal = __ballot_sync(0xffffffffu, hit);
             if (bal == 0u) continue;
             const int base = __shfl_sync(0xffffffffu, cur, b);
@@ -400,8 +445,9 @@ extern "C" size_t b2s_bin_tiles_workspace_bytes(const long long *totals_host, in
 
 template <int K>
 static int tl_run_level(const TlGeom &g, const TlLayout &L, char *w, const int32_t *order, const int2 *rects,
-                        const int32_t *n_vis, int32_t *flatten_ids, int32_t *isect_offsets, cudaStream_t st) {
-    const int2 *in = K == 1 ? nullptr : (const int2 *)(w + L.out[K - 1]);
+                        const int32_t *n_vis, int32_t *flatten_ids, int32_t *isect_offsets, const float2 *means2d,
+                        const float4 *geo, cudaStream_t st) {
+    int2 *in = K == 1 ? nullptr : (int2 *)(w + L.out[K - 1]);
     const int32_t *list_off = K == 1 ? nullptr : (const int32_t *)(w + L.out_off[K - 1]);
     const int32_t *chunk_off = K == 1 ? nullptr : (const int32_t *)(w + L.chunk_off[K - 1]);
     int32_t *table = (int32_t *)(w + L.table[K]);
@@ -414,7 +460,7 @@ static int tl_run_level(const TlGeom &g, const TlLayout &L, char *w, const int32
     const int nlists = L.nl[K];
     const int nch = (int)L.nch[K];
     k_level_count<K><<<nch, 32 * TL_WARPS, 0, st>>>(g, in, order, rects, n_vis, nlists, list_off, chunk_off, nch, table,
-                                                    slice_cnt, ticket);
+                                                    slice_cnt, ticket, means2d, geo);
     B2S_LAUNCH_CHECK();
     const int nout = nlists * L.nb[K];
     k_level_prefix<K><<<K >= 3 ? b2s_div_up(nout, TL_PT / 32) : nout, TL_PT, 0, st>>>(g, n_vis, nlists, chunk_off, nch, table, out_len, out_off,
@@ -427,10 +473,13 @@ static int tl_run_level(const TlGeom &g, const TlLayout &L, char *w, const int32
 }
 
 extern "C" int b2s_bin_tiles(const int32_t *tile_rects, const int32_t *order, const int32_t *n_vis,
-                             const long long *totals_host, int N, int tile_size, int tile_w, int tile_h,
+                             const long long *totals_host, int N, int tile_size, int tile_w, int tile_h, int W, int H,
+                             const float *means2d, const float *geo, int offsets_with_total,
                              int32_t *flatten_ids, int32_t *isect_offsets, void *workspace, size_t workspace_bytes,
                              b2s_stream_t stream) {
     if (N < 0 || !totals_host || tile_w <= 0 || tile_h <= 0) return B2S_ERR_ARG;
+    if ((means2d == nullptr) != (geo == nullptr)) return B2S_ERR_ARG;
+    if (means2d != nullptr && (W <= 0 || H <= 0 || tile_w * 16 < W || tile_h * 16 < H)) return B2S_ERR_ARG;
     const long long M = totals_host[0];
     for (int k = 0; k < 5; ++k)
         if (totals_host[k] < 0 || totals_host[k] >= (1LL << 31)) return B2S_ERR_ARG;
@@ -439,25 +488,31 @@ extern "C" int b2s_bin_tiles(const int32_t *tile_rects, const int32_t *order, co
     TlLayout L;
     if (!tl_layout(totals_host, tile_w, tile_h, g, L)) return B2S_ERR_UNSUPPORTED;
     if (workspace_bytes < L.total) return B2S_ERR_WORKSPACE;
+    g.W = W;
+    g.H = H;
+    g.exact = means2d != nullptr;
+    g.offs_total = offsets_with_total != 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int T = tile_w * tile_h;
     if (M == 0 || N == 0) {
-        cudaMemsetAsync(isect_offsets, 0, sizeof(int32_t) * (size_t)T, st);
+        cudaMemsetAsync(isect_offsets, 0, sizeof(int32_t) * (size_t)(T + (g.offs_total ? 1 : 0)), st);
         return B2S_OK;
     }
+    const float2 *m2 = (const float2 *)means2d;
+    const float4 *ge = (const float4 *)geo;
     char *w = (char *)workspace;
     const int2 *rects = (const int2 *)tile_rects;
     int rc;
-    if ((rc = tl_run_level<1>(g, L, w, order, rects, n_vis, flatten_ids, isect_offsets, st)) != B2S_OK) return rc;
-    if ((rc = tl_run_level<2>(g, L, w, order, rects, n_vis, flatten_ids, isect_offsets, st)) != B2S_OK) return rc;
-    if ((rc = tl_run_level<3>(g, L, w, order, rects, n_vis, flatten_ids, isect_offsets, st)) != B2S_OK) return rc;
-    if ((rc = tl_run_level<4>(g, L, w, order, rects, n_vis, flatten_ids, isect_offsets, st)) != B2S_OK) return rc;
+    if ((rc = tl_run_level<1>(g, L, w, order, rects, n_vis, flatten_ids, isect_offsets, m2, ge, st)) != B2S_OK) return rc;
+    if ((rc = tl_run_level<2>(g, L, w, order, rects, n_vis, flatten_ids, isect_offsets, m2, ge, st)) != B2S_OK) return rc;
+    if ((rc = tl_run_level<3>(g, L, w, order, rects, n_vis, flatten_ids, isect_offsets, m2, ge, st)) != B2S_OK) return rc;
+    if ((rc = tl_run_level<4>(g, L, w, order, rects, n_vis, flatten_ids, isect_offsets, m2, ge, st)) != B2S_OK) return rc;
     return B2S_OK;
 }
 
 // Row-group / column-group geometry used by b2s_bin_sort_depth for the E1 / E3 totals (same rule as tl_geom).
 int b2s_tl_shifts(int tile_w, int tile_h, int *rg_shift, int *cg_shift) {
-    TlGeom g;
+    TlGeom g = {};
     if (!tl_geom(tile_w, tile_h, g)) return B2S_ERR_UNSUPPORTED;
     *rg_shift = g.rg_shift;
     *cg_shift = g.cg_shift;

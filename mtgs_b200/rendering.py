@@ -70,17 +70,21 @@ def padded_channels(ch: int) -> int:
 
 
 class Meta(dict):
-    """``info`` dict.  ``isect_ids`` (upstream's int64 keys) is rebuilt on first access: the two-level
-    sort never materialises them, and MTGS never reads them."""
+    """``info`` dict.  ``flatten_ids`` / ``isect_offsets`` / ``isect_ids`` (upstream's lists over the full 3-sigma
+    rectangles) are built on first access: the blend kernels walk their own, exactly culled lists, and MTGS never
+    reads these keys.  When read they are bit-identical to upstream's."""
 
+    _LAZY = ("flatten_ids", "isect_offsets", "isect_ids")
     _lazy = None
 
     def __missing__(self, key):
-        if key == "isect_ids" and self._lazy is not None:
-            val = self._lazy()
-            self[key] = val
-            return val
+        if key in self._LAZY and self._lazy is not None:
+            self.update(self._lazy(key))
+            return dict.__getitem__(self, key)
         raise KeyError(key)
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or (key in self._LAZY and self._lazy is not None)
 
     def get(self, key, default=None):
         try:
@@ -95,7 +99,7 @@ class _Project(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means, quats, scales, opacities, colors, viewmat, K, W, H, tile_w, tile_h, eps2d, near, far,
-                radius_clip, calc_comp, with_depth, cdim):
+                radius_clip, calc_comp, with_depth, cdim, want_arena):
         lib = _lib.load()
         N = means.shape[0]
         d_in = 0 if colors is None else colors.shape[1]
@@ -110,18 +114,23 @@ class _Project(torch.autograd.Function):
         tiles = torch.empty(N, dtype=torch.int32, device=dev)
         keys = torch.empty(N, dtype=torch.int32, device=dev)
         rects = torch.empty(N, 2, dtype=torch.int32, device=dev)
+        tight = torch.empty(N, 2, dtype=torch.int32, device=dev)
+        totals = torch.zeros(9, dtype=torch.int64, device=dev)
+        # accumulation buffers of the blend backward (v_xyabs | v_geo | v_colpack), zero-filled by the kernel
+        arena = torch.empty(N * (8 + cdim) if want_arena else 0, dtype=torch.float32, device=dev)
         with _timed("project_fwd"):
             _lib.check(lib.b2s_project_fwd(_ptr(means), _ptr(quats), _ptr(scales), _ptr(opacities), _ptr(colors),
                                            _ptr(viewmat), _ptr(K), N, W, H, 16, tile_w, tile_h, eps2d, near, far,
                                            radius_clip, int(calc_comp), d_in, int(with_depth), cdim, _ptr(radii),
                                            _ptr(means2d), _ptr(depths), _ptr(geo), _ptr(comps), _ptr(colpack),
-                                           _ptr(tiles), _ptr(keys), _ptr(rects), _stream()),
+                                           _ptr(tiles), _ptr(keys), _ptr(rects), _ptr(tight), _ptr(totals),
+                                           _ptr(arena) if want_arena and N > 0 else None, _stream()),
                        "b2s_project_fwd")
         ctx.save_for_backward(means, quats, scales, opacities, viewmat, K, radii, geo, comps)
         ctx.cfg = (W, H, eps2d, calc_comp, d_in, with_depth, cdim)
         ctx.has_colors = colors is not None
-        ctx.mark_non_differentiable(radii, depths, tiles, keys, rects)
-        return means2d, geo, colpack, radii, depths, tiles, keys, rects
+        ctx.mark_non_differentiable(radii, depths, tiles, keys, rects, tight, totals, arena)
+        return means2d, geo, colpack, radii, depths, tiles, keys, rects, tight, totals, arena
 
     @staticmethod
     def backward(ctx, v_means2d, v_geo, v_colpack, *_unused):
@@ -161,15 +170,13 @@ class _Project(torch.autograd.Function):
             else:
                 ex.launch(ex._phases, args)
             gv = ex.grad_views(N)
+            if ex.exchange_colors and N > ex.n_shared:  # rank-local rows: colour gradients join the arena as they are
+                gv["colors"][ex.n_shared:] = v_colpack[ex.n_shared:, :d_in]
             if not ex.zero_copy:
                 gv = {k: v.clone() for k, v in gv.items()}
-            if not ex.exchange_colors:
-                v_colors = v_colpack[:, :d_in]  # view-dependent colours: reduced at their own leaves by the caller
-            else:
-                v_colors = gv["colors"]
-                if N > ex.n_shared:
-                    v_colors[ex.n_shared:] = v_colpack[ex.n_shared:, :d_in]
-            return (gv["means"], gv["quats"], gv["scales"], gv["opacities"], v_colors, v_view) + (None,) * 12
+            # view-dependent colours (exchange_colors=False) are reduced at their own leaves by the caller
+            v_colors = gv["colors"] if ex.exchange_colors else v_colpack[:, :d_in]
+            return (gv["means"], gv["quats"], gv["scales"], gv["opacities"], v_colors, v_view) + (None,) * 13
         v_means = torch.empty_like(means)
         v_quats = torch.empty_like(quats)
         v_scales = torch.empty_like(scales)
@@ -182,7 +189,7 @@ class _Project(torch.autograd.Function):
                                            _ptr(v_quats), _ptr(v_scales), _ptr(v_opac), _ptr(v_view), _stream()),
                        "b2s_project_bwd")
         v_colors = v_colpack[:, :d_in] if (ctx.has_colors and ctx.needs_input_grad[4]) else None
-        return (v_means, v_quats, v_scales, v_opac, v_colors, v_view) + (None,) * 12
+        return (v_means, v_quats, v_scales, v_opac, v_colors, v_view) + (None,) * 13
 
 
 class _Blend(torch.autograd.Function):
@@ -190,78 +197,104 @@ class _Blend(torch.autograd.Function):
     exactly as with upstream (mtgs_scene_graph.py:666-667, 1171-1174)."""
 
     @staticmethod
-    def forward(ctx, means2d, geo, colpack, offsets, flatten_ids, W, H, tile_w, tile_h, cdim, d_out, ed, absgrad):
+    def forward(ctx, means2d, geo, colpack, offsets, ids, arena, W, H, tile_w, tile_h, cdim, d_out, ed, absgrad):
         lib = _lib.load()
         dev = means2d.device
-        M = flatten_ids.shape[0]
         render = torch.empty(1, H, W, d_out, dtype=torch.float32, device=dev)
         alpha = torch.empty(1, H, W, 1, dtype=torch.float32, device=dev)
         last_ids = torch.empty(H, W, dtype=torch.int32, device=dev)
+        records = None
+        if arena.numel() > 0:  # a backward may follow: keep the walk records
+            nbytes = int(lib.b2s_blend_record_bytes(ids.numel(), tile_w * tile_h, cdim))
+            records = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
         with _timed("blend_fwd"):
-            _lib.check(lib.b2s_blend_fwd(_ptr(means2d), _ptr(geo), _ptr(colpack), _ptr(offsets), _ptr(flatten_ids),
-                                         M, W, H, tile_w, tile_h, cdim, d_out, int(ed), _ptr(render), _ptr(alpha),
-                                         _ptr(last_ids), _stream()), "b2s_blend_fwd")
-        ctx.save_for_backward(means2d, geo, colpack, offsets, flatten_ids, render, alpha, last_ids)
-        ctx.cfg = (W, H, tile_w, tile_h, cdim, d_out, ed, absgrad)
+            _lib.check(lib.b2s_blend_fwd(_ptr(means2d), _ptr(geo), _ptr(colpack), _ptr(offsets), _ptr(ids), W, H,
+                                         tile_w, tile_h, cdim, d_out, int(ed), _ptr(render), _ptr(alpha),
+                                         _ptr(last_ids), _ptr(records), _stream()), "b2s_blend_fwd")
+        ctx.save_for_backward(means2d, offsets, render, alpha, last_ids, records, arena)
+        ctx.cfg = (W, H, tile_w, tile_h, cdim, d_out, ed, absgrad, geo.shape[0])
+        ctx.arena_clean = True
         ctx.mark_non_differentiable(last_ids)
         return render, alpha, last_ids
 
     @staticmethod
     def backward(ctx, v_render, v_alpha, _v_last=None):
         lib = _lib.load()
-        means2d, geo, colpack, offsets, flatten_ids, render, alpha, last_ids = ctx.saved_tensors
-        W, H, tile_w, tile_h, cdim, d_out, ed, absgrad = ctx.cfg
-        dev = means2d.device
-        N = geo.shape[0]
-        M = flatten_ids.shape[0]
+        means2d, offsets, render, alpha, last_ids, records, arena = ctx.saved_tensors
+        W, H, tile_w, tile_h, cdim, d_out, ed, absgrad, N = ctx.cfg
+        if records is None:
+            raise RuntimeError("rasterization was run without gradient tracking; no backward is possible")
         v_render = torch.zeros_like(render) if v_render is None else v_render.contiguous()
         v_alpha = torch.zeros_like(alpha) if v_alpha is None else v_alpha.contiguous()
-        # one zero-filled arena (one memset launch) holding the three 16-byte-row accumulation buffers
-        arena = torch.zeros(N * (8 + cdim), dtype=torch.float32, device=dev)
+        if not ctx.arena_clean:  # a second backward through the same graph (retain_graph=True)
+            arena = torch.zeros_like(arena)
+        ctx.arena_clean = False
+        # one arena holding the three 16-byte-row accumulation buffers, zero-filled by the projection forward
         v_xyabs = arena[: 4 * N].view(N, 4)
         v_geo = arena[4 * N: 8 * N].view(N, 4)
         v_colpack = arena[8 * N:].view(N, cdim)
-        with _timed("blend_bwd"):
-            _lib.check(lib.b2s_blend_bwd(_ptr(means2d), _ptr(geo), _ptr(colpack), _ptr(offsets), _ptr(flatten_ids),
-                                         M, W, H, tile_w, tile_h, cdim, d_out, int(ed), _ptr(render), _ptr(alpha),
-                                         _ptr(last_ids), _ptr(v_render), _ptr(v_alpha), _ptr(v_xyabs), _ptr(v_geo),
-                                         _ptr(v_colpack), _stream()), "b2s_blend_bwd")
+        if N > 0:
+            with _timed("blend_bwd"):
+                _lib.check(lib.b2s_blend_bwd(_ptr(offsets), _ptr(records), W, H, tile_w, tile_h, cdim, d_out, int(ed),
+                                             _ptr(render), _ptr(alpha), _ptr(last_ids), _ptr(v_render), _ptr(v_alpha),
+                                             _ptr(v_xyabs), _ptr(v_geo), _ptr(v_colpack), _stream()), "b2s_blend_bwd")
         if absgrad:
             # upstream: `means2d.absgrad = v_means2d_abs` on the tensor object handed in by the caller
             means2d.absgrad = v_xyabs[:, 2:4].unsqueeze(0)
-        return (v_xyabs[:, 0:2].unsqueeze(0), v_geo, v_colpack) + (None,) * 10
+        return (v_xyabs[:, 0:2].unsqueeze(0), v_geo, v_colpack) + (None,) * 11
 
 
 # ------------------------------------------------------------------------------------------------
-def _bin(rects: Tensor, tiles: Tensor, keys: Tensor, tile_w: int, tile_h: int) -> Tuple[Tensor, Tensor, Tensor]:
-    """Depth order + tile lists.  Returns (flatten_ids [M] int32, offsets [th,tw] int32)."""
+_PINNED_TOTALS: Dict[int, Tensor] = {}
+
+
+def _sort_and_read_totals(keys: Tensor, totals: Tensor):
+    """Depth order of the visible Gaussians; the list sizes summed by the projection kernel travel to the host
+    WHILE the sort runs (the one device->host read of the path; it sizes the tile lists)."""
     lib = _lib.load()
-    dev = rects.device
-    N = tiles.shape[0]
+    dev = keys.device
+    N = keys.shape[0]
+    host = _PINNED_TOTALS.get(dev.index)
+    if host is None:
+        host = _PINNED_TOTALS[dev.index] = torch.zeros(9, dtype=torch.int64).pin_memory()
+    host.copy_(totals, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
     order = torch.empty(N, dtype=torch.int32, device=dev)
-    totals = torch.empty(5, dtype=torch.int64, device=dev)
     n_vis = torch.empty(1, dtype=torch.int32, device=dev)
     wsb = int(lib.b2s_bin_depth_workspace_bytes(N))
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     with _timed("bin_sort_depth"):
-        _lib.check(lib.b2s_bin_sort_depth(_ptr(keys), _ptr(tiles), _ptr(rects), N, tile_w, tile_h, _ptr(order),
-                                          _ptr(totals), _ptr(n_vis), _ptr(ws), wsb, _stream()), "b2s_bin_sort_depth")
-    # the one unavoidable device->host read: M sizes flatten_ids, the other totals the tile-list workspace
-    tot = (C.c_longlong * 5)(*[int(v) for v in totals.tolist()])
-    M = int(tot[0])
-    if M >= 2 ** 31:
-        raise RuntimeError(f"{M} tile intersections exceed the int32 offset range (same limit as upstream)")
-    flatten_ids = torch.empty(M, dtype=torch.int32, device=dev)
-    offsets = torch.empty(tile_h, tile_w, dtype=torch.int32, device=dev)
-    wsb2 = int(lib.b2s_bin_tiles_workspace_bytes(tot, tile_w, tile_h))
-    if wsb2 == 0:
+        _lib.check(lib.b2s_bin_sort_depth(_ptr(keys), N, _ptr(order), _ptr(n_vis), _ptr(ws), wsb, _stream()),
+                   "b2s_bin_sort_depth")
+    ev.synchronize()
+    tot = [int(v) for v in host.tolist()]
+    if tot[0] >= 2 ** 31:
+        raise RuntimeError(f"{tot[0]} tile intersections exceed the int32 offset range (same limit as upstream)")
+    return order, n_vis, tot
+
+
+def _tile_lists(rects: Tensor, order: Tensor, n_vis: Tensor, sizes, tile_w: int, tile_h: int, W: int, H: int,
+                means2d: Optional[Tensor], geo: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+    """Per-tile depth-ordered lists.  ``means2d`` / ``geo`` given: the blend's own lists (tight rectangles + exact
+    per-tile test), offsets with a trailing total; otherwise upstream's lists.  ``sizes`` = (list length, S, E1, E3,
+    n_vis) as summed by the projection kernel for ``rects``."""
+    lib = _lib.load()
+    dev = rects.device
+    N = rects.shape[0]
+    exact = means2d is not None
+    tot = (C.c_longlong * 5)(*sizes)
+    ids = torch.empty(sizes[0], dtype=torch.int32, device=dev)
+    offsets = torch.empty(tile_h * tile_w + (1 if exact else 0), dtype=torch.int32, device=dev)
+    wsb = int(lib.b2s_bin_tiles_workspace_bytes(tot, tile_w, tile_h))
+    if wsb == 0:
         raise NotImplementedError(f"tile grid {tile_w}x{tile_h} not supported")
-    ws2 = torch.empty(wsb2, dtype=torch.uint8, device=dev)
-    with _timed("bin_tiles"):
-        _lib.check(lib.b2s_bin_tiles(_ptr(rects), _ptr(order), _ptr(n_vis), tot, N, 16, tile_w, tile_h,
-                                     _ptr(flatten_ids), _ptr(offsets), _ptr(ws2), wsb2, _stream()),
-                   "b2s_bin_tiles")
-    return flatten_ids, offsets
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    with _timed("bin_tiles" if exact else "bin_tiles_upstream_lists"):
+        _lib.check(lib.b2s_bin_tiles(_ptr(rects), _ptr(order), _ptr(n_vis), tot, N, 16, tile_w, tile_h, W, H,
+                                     _ptr(means2d), _ptr(geo), int(exact), _ptr(ids), _ptr(offsets), _ptr(ws), wsb,
+                                     _stream()), "b2s_bin_tiles")
+    return ids, offsets
 
 
 def _isect_ids(offsets: Tensor, flatten_ids: Tensor, depths: Tensor) -> Tensor:
@@ -286,18 +319,31 @@ def _rasterize_one(means, quats, scales, opacities, colors, viewmat, K, width, h
     tile_w = math.ceil(width / 16.0)
     tile_h = math.ceil(height / 16.0)
     calc_comp = rasterize_mode == "antialiased"
-    means2d, geo, colpack, radii, depths, tiles, keys, rects = _Project.apply(
+    want_grad = torch.is_grad_enabled() and any(
+        t is not None and t.requires_grad for t in (means, quats, scales, opacities, cols, viewmat))
+    means2d, geo, colpack, radii, depths, tiles, keys, rects, tight, totals, arena = _Project.apply(
         means, quats, scales, opacities, cols, viewmat, K, width, height, tile_w, tile_h, float(eps2d),
-        float(near_plane), float(far_plane), float(radius_clip), calc_comp, with_depth, cdim)
-    flatten_ids, offsets = _bin(rects, tiles, keys, tile_w, tile_h)
-    render, alpha, last_ids = _Blend.apply(means2d, geo, colpack, offsets, flatten_ids, width, height, tile_w, tile_h,
-                                           cdim, d_out, ed, bool(absgrad))
+        float(near_plane), float(far_plane), float(radius_clip), calc_comp, with_depth, cdim, want_grad)
+    order, n_vis, tot = _sort_and_read_totals(keys, totals)
+    # the lists the blend walks: tight rectangles + exact per-tile test (never more than tot[4] entries)
+    walk_ids, walk_offsets = _tile_lists(tight, order, n_vis, (tot[4], tot[5], tot[6], tot[7], tot[8]), tile_w, tile_h,
+                                         width, height, means2d.detach(), geo.detach())
+    render, alpha, last_ids = _Blend.apply(means2d, geo, colpack, walk_offsets, walk_ids, arena, width, height,
+                                           tile_w, tile_h, cdim, d_out, ed, bool(absgrad))
     # keys with a leading underscore are not part of upstream's info dict (bench.py reads them for K_pairs)
     meta = dict(radii=radii.unsqueeze(0), means2d=means2d, depths=depths.unsqueeze(0),
                 conics=geo.detach()[:, :3].unsqueeze(0), opacities=geo.detach()[:, 3].unsqueeze(0),
-                tiles_per_gauss=tiles.unsqueeze(0), flatten_ids=flatten_ids, isect_offsets=offsets.unsqueeze(0),
-                _last_ids=last_ids, _walk_ids=flatten_ids, _walk_offsets=offsets)
-    return render, alpha, meta
+                tiles_per_gauss=tiles.unsqueeze(0), _last_ids=last_ids, _walk_ids=walk_ids, _walk_offsets=walk_offsets)
+
+    def upstream_lists(_key):
+        """upstream's flatten_ids / isect_offsets / isect_ids, on demand (bit-identical to the 64-bit sort)."""
+        with torch.cuda.device(rects.device):
+            flat, offs = _tile_lists(rects, order, n_vis, (tot[0], tot[1], tot[2], tot[3], tot[8]), tile_w, tile_h, width,
+                                     height, None, None)
+            return dict(flatten_ids=flat, isect_offsets=offs.view(1, tile_h, tile_w),
+                        isect_ids=_isect_ids(offs, flat, depths))
+
+    return render, alpha, meta, upstream_lists
 
 
 def rasterization(
@@ -372,7 +418,7 @@ def rasterization(
 
     means, quats, scales, opacities = _f32c(means), _f32c(quats), _f32c(scales), _f32c(opacities)
     viewmats, Ks = _f32c(viewmats), _f32c(Ks)
-    renders, alphas, metas = [], [], []
+    renders, alphas, metas, lazies = [], [], [], []
     with torch.cuda.device(means.device):
         for c in range(C_):
             if sh_degree is not None:
@@ -383,9 +429,10 @@ def rasterization(
             else:
                 cols = colors if colors.dim() == 2 else colors[c]
             cols = _f32c(cols)
-            r, a, m = _rasterize_one(means, quats, scales, opacities, cols, viewmats[c], Ks[c], int(width),
-                                     int(height), near_plane, far_plane, radius_clip, eps2d, render_mode, absgrad,
-                                     rasterize_mode)
+            r, a, m, lz = _rasterize_one(means, quats, scales, opacities, cols, viewmats[c], Ks[c], int(width),
+                                         int(height), near_plane, far_plane, radius_clip, eps2d, render_mode, absgrad,
+                                         rasterize_mode)
+            lazies.append(lz)
             if backgrounds is not None and render_mode not in ("D", "ED"):
                 nb = backgrounds.shape[-1]
                 r = torch.cat([r[..., :nb] + (1.0 - a) * backgrounds[c].reshape(1, 1, 1, nb), r[..., nb:]], dim=-1)
@@ -398,18 +445,24 @@ def rasterization(
     meta = Meta(tile_width=tile_w, tile_height=tile_h, width=width, height=height, tile_size=tile_size,
                 n_cameras=C_, camera_ids=None, gaussian_ids=None)
     if C_ == 1:
-        m = metas[0]
-        meta.update(m)
-        depths0 = m["depths"][0]
-        meta._lazy = lambda: _isect_ids(m["isect_offsets"][0].contiguous(), m["flatten_ids"], depths0)
+        meta.update(metas[0])
+        meta._lazy = lazies[0]
         return renders[0], alphas[0], meta
     # C > 1: per-camera results stacked; flatten_ids / offsets follow upstream's camera-major numbering
     for k in ("radii", "means2d", "depths", "conics", "opacities", "tiles_per_gauss"):
         meta[k] = torch.cat([m[k] for m in metas], dim=0)
-    m_before, offs = 0, []
-    for m in metas:
-        offs.append(m["isect_offsets"] + m_before)
-        m_before += m["flatten_ids"].shape[0]
-    meta["isect_offsets"] = torch.cat(offs, dim=0)
-    meta["flatten_ids"] = torch.cat([m["flatten_ids"] + c * N for c, m in enumerate(metas)], dim=0)
+
+    def stacked_lists(_key):
+        per_cam = [lz(_key) for lz in lazies]
+        m_before, offs = 0, []
+        for d in per_cam:
+            offs.append(d["isect_offsets"] + m_before)
+            m_before += d["flatten_ids"].shape[0]
+        n_tiles = tile_w * tile_h
+        tile_bits = int(math.floor(math.log2(n_tiles))) + 1
+        return dict(isect_offsets=torch.cat(offs, dim=0),
+                    flatten_ids=torch.cat([d["flatten_ids"] + c * N for c, d in enumerate(per_cam)], dim=0),
+                    isect_ids=torch.cat([d["isect_ids"] | (c << (32 + tile_bits)) for c, d in enumerate(per_cam)], dim=0))
+
+    meta._lazy = stacked_lists
     return torch.cat(renders, dim=0), torch.cat(alphas, dim=0), meta

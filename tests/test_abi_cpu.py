@@ -172,8 +172,11 @@ def test_padded_channels_and_lazy_meta():
         padded_channels(9)
     m = Meta(a=1)
     calls = []
-    m._lazy = lambda: calls.append(1) or "ids"
-    assert m.get("isect_ids") == "ids" and m["isect_ids"] == "ids" and len(calls) == 1  # built once, on first access
+    # upstream's lists are built together, once, on the first access to any of the three keys
+    m._lazy = lambda key: calls.append(key) or dict(flatten_ids="flat", isect_offsets="offs", isect_ids="ids")
+    assert "isect_ids" in m and "flatten_ids" in m and "nothing" not in m
+    assert m.get("isect_ids") == "ids" and m["isect_ids"] == "ids" and m["flatten_ids"] == "flat"
+    assert m["isect_offsets"] == "offs" and calls == ["isect_ids"]
     assert m.get("missing", 7) == 7
     with pytest.raises(KeyError):
         m["missing"]

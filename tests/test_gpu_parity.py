@@ -147,6 +147,62 @@ def test_backward_parity(oracle, cuda_device, scene, mode, rmode, d_in):
     assert torch.all(meta["means2d"].grad[0][torch.tensor(culled, device=cuda_device)] == 0)
 
 
+@pytest.mark.parametrize("scene", ["tiny_ragged", "config1", "street20k", "street20k_540p"])
+def test_walk_lists_are_upstream_lists_minus_dead_pairs(cuda_device, scene):
+    """The lists the blend kernels walk (tight rectangles + exact per-tile test) must be upstream's (tile, depth)-sorted
+    lists with ONLY non-contributing pairs removed: same order, and every pair that reaches alpha >= 1/255 at some pixel
+    centre of its tile (brute force in float64 over all 256 pixels) is present."""
+    s = SCENES[scene]()
+    t = _to_dev(s, cuda_device)
+    W, H, N = s["width"], s["height"], s["means"].shape[0]
+    with torch.no_grad():
+        _, _, meta = _gpu_raster(t, s, render_mode="RGB+ED", rasterize_mode="antialiased")
+    dev = cuda_device
+    tw, th = meta["tile_width"], meta["tile_height"]
+    flat, offs = meta["flatten_ids"].long(), meta["isect_offsets"].reshape(-1).long()
+    M = flat.numel()
+    w_offs = meta["_walk_offsets"].long()
+    Mw = int(w_offs[-1])
+    w_ids = meta["_walk_ids"].long()[:Mw]
+    assert w_offs.numel() == tw * th + 1 and bool((w_offs[1:] >= w_offs[:-1]).all()) and int(w_offs[0]) == 0
+    tile_up = torch.searchsorted(offs, torch.arange(M, device=dev), right=True) - 1
+    tile_wk = torch.searchsorted(w_offs[:-1].contiguous(), torch.arange(Mw, device=dev), right=True) - 1
+    key_up, key_wk = tile_up * N + flat, tile_wk * N + w_ids
+    # subsequence: every walked pair exists upstream, and positions in upstream's list increase along the walk list
+    srt, perm = torch.sort(key_up)
+    at = torch.searchsorted(srt, key_wk).clamp(max=M - 1)
+    assert bool((srt[at] == key_wk).all()), "walk list holds a pair upstream's list does not"
+    pos = perm[at]
+    assert bool((pos[1:] > pos[:-1]).all()), "walk list is not in upstream's (tile, depth, id) order"
+    in_walk = torch.zeros(M, dtype=torch.bool, device=dev)
+    in_walk[pos] = True
+    # brute force: best alpha of every upstream pair over the pixel centres of its tile
+    m2 = meta["means2d"][0].double()
+    con = meta["conics"][0].double()
+    op = meta["opacities"][0].double()
+    best = torch.empty(M, dtype=torch.float64, device=dev)
+    jj, ii = torch.meshgrid(torch.arange(16, device=dev), torch.arange(16, device=dev), indexing="ij")
+    for lo in range(0, M, 65536):
+        hi = min(M, lo + 65536)
+        g, tl = flat[lo:hi], tile_up[lo:hi]
+        px = ((tl % tw) * 16)[:, None] + ii.reshape(1, -1)
+        py = ((tl // tw) * 16)[:, None] + jj.reshape(1, -1)
+        valid = (px < W) & (py < H)
+        dx = m2[g, 0:1] - (px + 0.5)
+        dy = m2[g, 1:2] - (py + 0.5)
+        sig = 0.5 * (con[g, 0:1] * dx * dx + con[g, 2:3] * dy * dy) + con[g, 1:2] * dx * dy
+        al = torch.clamp(op[g][:, None] * torch.exp(-sig), max=0.999)
+        al = torch.where(valid & (sig >= 0), al, torch.zeros_like(al))
+        best[lo:hi] = al.max(dim=1).values
+    must = best >= (1.0 / 255.0) * (1 + 1e-3)
+    assert int(must.sum()) > 0
+    missing = must & ~in_walk
+    assert int(missing.sum()) == 0, f"{int(missing.sum())} contributing pairs were dropped (best alpha up to {float(best[missing].max()):.4f})"
+    dead_kept = in_walk & (best < (1.0 / 255.0) * (1 - 2e-2))
+    assert float(dead_kept.sum()) <= 0.15 * Mw + 8, (int(dead_kept.sum()), Mw)
+    assert Mw < M
+
+
 def test_golden_fixture_through_c_abi(cuda_device):
     """Committed fixture (tests/golden/oracle_tiny_golden.npz): no oracle code runs in this test."""
     g = np.load(os.path.join(GOLD, "oracle_tiny_golden.npz"))
