@@ -6,13 +6,16 @@
 //
 // These kernels are FP32-ALU / MUFU.EX2 / shuffle bound, not HBM bound: no tensor cores.
 // Blackwell-first choices:
-//   * the lists they walk are the blend's own tile lists (tilelists.cu, exact mode): only (Gaussian, tile) pairs
-//     that can reach alpha >= 1/255 at a pixel centre of the tile.  Upstream's 3-sigma lists contain ~3x more
-//     entries that contribute to no pixel; dropping them changes no output bit;
+//   * the lists they walk are built from TIGHT rectangles (project.cu: upstream's 3-sigma rectangle intersected with
+//     the extents of the footprint {alpha >= 1/255}), and while staging a batch the forward applies the exact
+//     per-tile test (tile_keep: can the pair reach alpha >= 1/255 at any pixel centre of the tile?) and compacts the
+//     survivors with warp ballots.  Upstream's lists hold ~3x more entries that contribute to no pixel; dropping
+//     them changes no output bit.  The test runs lazily, only for the part of a list that is walked before the
+//     tile saturates (running it inside the tile-list build for all pairs was measured 90 us slower);
 //   * forward: one CTA of 128 threads per 16x16 tile, TWO pixels per thread; a batch of 128 list entries is
-//     gathered (id -> projected record) into a shared-memory block in SoA form, and the finished block is handed
-//     to the TMA engine (cp.async.bulk shared -> global, SASS UBLKCP) as a "walk record" while the CTA blends it;
-//     the gathers of the NEXT batch are in flight during the blend of the current one (register double buffer);
+//     gathered (id -> projected record), compacted into a shared-memory block in SoA form, and the finished block
+//     is handed to the TMA engine (cp.async.bulk shared -> global, SASS UBLKCP) as a "walk record" while the CTA
+//     blends it; the gathers of the NEXT batch are in flight during the blend of the current one;
 //   * backward: 64 threads per tile, FOUR pixels per thread; it never touches the id lists or the per-Gaussian
 //     arrays: it replays the forward's walk records back to front, each 6-8 KB block arriving by ONE TMA bulk copy
 //     (cp.async.bulk global -> shared on an mbarrier), double buffered, so the next block lands while the
@@ -30,10 +33,12 @@
 constexpr int BL_THREADS = 128;
 constexpr int BL_BATCH = 128;  // list entries per walk-record block
 
-// float4s per walk-record block: q[128] = (mx, my, A, B), c[128] = (C, opacity, Gaussian id bits, 0), col[128][CDIM/4]
+// float4s per walk-record block: q[128] = (mx, my, A, B), c[128] = (C, opacity, Gaussian id bits, 0), col[128][CDIM/4],
+// then one header float4 whose .x holds the number of entries of the block (as int bits)
 template <int CDIM> struct BlkLayout {
     static constexpr int CQ = CDIM / 4;
-    static constexpr int F4 = BL_BATCH * (2 + CQ);
+    static constexpr int HDR = BL_BATCH * (2 + CQ);  // index of the header
+    static constexpr int F4 = HDR + 1;
     static constexpr unsigned BYTES = F4 * 16;
 };
 // walk-record block index of batch k of a tile whose list starts at `start`: strictly increasing over (tile, k)
@@ -60,19 +65,27 @@ __device__ __forceinline__ float2 splat_power2(float A, float B, float C, float 
 struct FwdRec {  // one list entry gathered into registers
     float4 q, c;
     float4 col[2];
+    bool keep;
 };
+// id -> projected record, plus the exact per-tile test: a (Gaussian, tile) pair whose minimum exponent over the tile's
+// pixel centres already gives alpha < 1/255 contributes to no pixel and is dropped while staging (tile_keep).
 template <int CQ>
 __device__ __forceinline__ void fwd_gather(FwdRec &r, int idx, int end, const int32_t *__restrict__ ids,
                                            const float2 *__restrict__ means2d, const float4 *__restrict__ geo,
-                                           const float4 *__restrict__ colpack) {
+                                           const float4 *__restrict__ colpack, float rx0, float ry0, float rx1,
+                                           float ry1) {
+    r.keep = false;
     if (idx < end) {
         const int g = ids[idx];
         const float2 m = means2d[g];
         const float4 ge = geo[g];
         r.q = make_float4(m.x, m.y, 0.5f * B2S_LOG2E * ge.x, B2S_LOG2E * ge.y);
         r.c = make_float4(0.5f * B2S_LOG2E * ge.z, ge.w, __int_as_float(g), 0.f);
+        r.keep = tile_keep(m.x, m.y, r.q.z, r.q.w, r.c.x, ge.w, rx0, ry0, rx1, ry1);
+        if (r.keep) {
 #pragma unroll
-        for (int k = 0; k < CQ; ++k) r.col[k] = colpack[(size_t)g * CQ + k];
+            for (int k = 0; k < CQ; ++k) r.col[k] = colpack[(size_t)g * CQ + k];
+        }
     }
 }
 
@@ -105,18 +118,37 @@ k_blend_fwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
     int cur0 = 0, cur1 = 0;
     bool done0 = !in0, done1 = !in1;
 
+    // pixel-centre rectangle of the tile clipped to the image
+    const float rx0 = (float)(tj * 16) + 0.5f, ry0 = (float)(ti * 16) + 0.5f;
+    const float rx1 = (float)min(tj * 16 + 16, W) - 0.5f, ry1 = (float)min(ti * 16 + 16, H) - 0.5f;
+    const unsigned lt = lanemask_lt();
+    __shared__ int s_wcnt[BL_THREADS / 32];
+
     FwdRec nxt;
-    fwd_gather<CQ>(nxt, start + (int)threadIdx.x, end, ids, means2d, geo, colpack);
+    fwd_gather<CQ>(nxt, start + (int)threadIdx.x, end, ids, means2d, geo, colpack, rx0, ry0, rx1, ry1);
     for (int base = start, k = 0; base < end; base += BL_BATCH, ++k) {
         // the TMA store of the previous block must have read shared memory before the block is overwritten
         if (records != nullptr && threadIdx.x == 0) b2s_bulk_wait_read();
         if (__syncthreads_and(done0 && done1)) break;
-        if (base + (int)threadIdx.x < end) {
-            s_q[threadIdx.x] = nxt.q;
-            s_c[threadIdx.x] = nxt.c;
+        // ballot compaction of the kept entries: slot order == list order
+        const unsigned bal = __ballot_sync(0xffffffffu, nxt.keep);
+        if (lane == 0) s_wcnt[warp] = __popc(bal);
+        __syncthreads();
+        int off = 0, total = 0;
 #pragma unroll
-            for (int j = 0; j < CQ; ++j) s_col[threadIdx.x * CQ + j] = nxt.col[j];
+        for (int w = 0; w < BL_THREADS / 32; ++w) {
+            const int nw = s_wcnt[w];
+            off += (w < warp) ? nw : 0;
+            total += nw;
         }
+        if (nxt.keep) {
+            const int slot = off + __popc(bal & lt);
+            s_q[slot] = nxt.q;
+            s_c[slot] = nxt.c;
+#pragma unroll
+            for (int j = 0; j < CQ; ++j) s_col[slot * CQ + j] = nxt.col[j];
+        }
+        if (threadIdx.x == 0) s_blk[BL::HDR] = make_float4(__int_as_float(total), 0.f, 0.f, 0.f);
         if (records != nullptr) b2s_fence_async_smem();
         __syncthreads();
         if (records != nullptr && threadIdx.x == 0) {
@@ -124,8 +156,7 @@ k_blend_fwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
             b2s_bulk_commit();
         }
         // gathers of the next batch fly while this one is blended
-        fwd_gather<CQ>(nxt, base + BL_BATCH + (int)threadIdx.x, end, ids, means2d, geo, colpack);
-        const int total = min(BL_BATCH, end - base);
+        fwd_gather<CQ>(nxt, base + BL_BATCH + (int)threadIdx.x, end, ids, means2d, geo, colpack, rx0, ry0, rx1, ry1);
 
 #pragma unroll 2
         for (int t = 0; t < total; ++t) {
@@ -392,7 +423,8 @@ k_blend_bwd(const int32_t *__restrict__ offsets /* [tiles + 1] */, const float4 
         b2s_mbar_wait(&s_bar[st], (it >> 1) & 1);
         const float4 *s_q = s_blk[st], *s_c = s_blk[st] + BL_BATCH, *s_col = s_blk[st] + 2 * BL_BATCH;
         const int base = start + (k << 7);
-        const int tmax = min(BL_BATCH - 1, hi0 - base);
+        const int cnt = __float_as_int(s_blk[st][BL::HDR].x);  // entries the forward kept in this block
+        const int tmax = min(cnt - 1, hi0 - base);
 
         for (int t1 = tmax; t1 >= 0; t1 = (t1 & ~(FL - 1)) - 1) {  // flush rounds: entries [t0, t1] share s_acc
         const int t0 = t1 & ~(FL - 1);
@@ -519,7 +551,7 @@ static int launch_bwd(const int32_t *offsets, const float *records, int W, int H
 extern "C" size_t b2s_blend_record_bytes(long long list_capacity, int n_tiles, int cdim) {
     if (list_capacity < 0 || n_tiles < 0 || (cdim != 4 && cdim != 8)) return 0;
     const size_t blocks = (size_t)(list_capacity >> 7) + (size_t)n_tiles + 1;
-    return blocks * (size_t)BL_BATCH * 16 * (size_t)(2 + cdim / 4);
+    return blocks * ((size_t)BL_BATCH * (size_t)(2 + cdim / 4) + 1) * 16;  // + header
 }
 
 extern "C" int b2s_blend_fwd(const float *means2d, const float *geo, const float *colpack,

@@ -11,32 +11,38 @@
 //     n_vis              (the list sizes of the tile-list hierarchy are summed by the projection kernel, so that their
 //                        device->host copy overlaps this sort)
 //
-// A multi-launch LSD radix sort of 2 M keys spent most of its time in launch/drain gaps between ~15 small
-// kernels.  Here a single persistent grid (one launch, cudaLaunchCooperativeKernel, all CTAs co-resident) runs
-// 3 passes of an 11-bit stable radix sort separated by grid-wide barriers:
-//     histogram of the CTA's slice -> grid.sync -> per-digit exclusive scan over CTAs (one warp per digit row)
-//     -> grid.sync -> digit bases (redundantly per CTA) + stable ranking (match.any groups, per-warp counters)
-//     + scatter -> grid.sync
+// One persistent grid (cudaLaunchCooperativeKernel, all CTAs co-resident, two per SM) runs 4 passes of an 8-bit
+// stable LSD radix sort; the whole working set (keys + ids of the visible Gaussians, ~10 MB) lives in the 126 MB L2.
+// Per pass and CTA (a CTA owns a contiguous slice of the input):
+//     (a) digit histogram of the slice (warp-aggregated shared-memory atomics) -> table[digit][cta]   -> grid barrier
+//     (b) every CTA derives the global start of ITS run of every digit from the table (one warp per 16 digit rows,
+//         coalesced row reads), then sub-tile by sub-tile (4096 items): stable ranks from match.any groups and
+//         per-warp digit counters, a pass through shared memory that makes each digit's items contiguous, and a
+//         scatter whose stores are coalesced runs (average run = 16 items at 8 bits per digit)        -> grid barrier
+// The round-1 version used 11-bit digits (3 passes): 2048 counters per 4096-item sub-tile made the cross-warp prefix
+// cost more shared-memory operations than there are items, and runs of 2-4 items made the scatter a sector-granular
+// 4-byte write (profiles/r01g_kernels_ncu.txt: IPC 0.40, barrier + scoreboard stalls, 167 us).
 // Pass 0 reads the projection's keys directly and drops the culled ones (key 0xFFFFFFFF), so the later passes and
-// everything downstream only touch n_vis items; the value payload of pass 0 is the index itself.  The M / S totals
-// ride on the same grid.  Integer work on L2-resident data; no tensor cores.
+// everything downstream only touch n_vis items; the value payload of pass 0 is the index itself.
+// Integer work on L2-resident data; no tensor cores.
 #include <cooperative_groups.h>
 
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
 
-constexpr int DS_THREADS = 256;
+constexpr int DS_THREADS = 512;
 constexpr int DS_WARPS = DS_THREADS / 32;
-constexpr int DS_ROUNDS = 16;                     // items per thread per sub-tile
+constexpr int DS_ROUNDS = 8;                      // items per thread per sub-tile
 constexpr int DS_TILE = DS_THREADS * DS_ROUNDS;   // 4096 items per sub-tile
-constexpr int DS_BITS = 11;
+constexpr int DS_BITS = 8;
 constexpr int DS_BINS = 1 << DS_BITS;
 constexpr unsigned DS_MASK = DS_BINS - 1;
-constexpr int DS_PASSES = 3;                      // 33 bits >= 32
+constexpr int DS_PASSES = 4;
+constexpr int DS_MAX_GRID = 1024;
 constexpr unsigned DS_CULLED = 0xFFFFFFFFu;
-// shared memory: per-warp counters [8][2048] (also the histogram) + running digit bases [2048] + scan scratch
-constexpr size_t DS_SMEM = ((size_t)DS_WARPS * DS_BINS + DS_BINS + 64) * sizeof(int);
+// shared memory: reordered keys + values of a sub-tile, per-warp digit counters, per-digit bookkeeping, scan scratch
+constexpr size_t DS_SMEM = (size_t)DS_TILE * 8 + (size_t)DS_WARPS * DS_BINS * 4 + (size_t)DS_BINS * 4 * 4 + 256;
 
 __device__ __forceinline__ int ds_warp_incl_scan(int v, int lane) {
 #pragma unroll
@@ -47,34 +53,43 @@ __device__ __forceinline__ int ds_warp_incl_scan(int v, int lane) {
     return v;
 }
 
-// block-wide exclusive scan of one int per thread (256 threads); s_w needs DS_WARPS + 1 ints
-__device__ __forceinline__ int ds_block_excl_scan(int v, int *total, int *s_w) {
+// exclusive scan over the DS_BINS values held by threads 0 .. DS_BINS-1 (one per thread); s_w: DS_BINS / 32 + 1 ints.
+// Returns the exclusive prefix for threads < DS_BINS and the grand total through *total.  Contains CTA barriers.
+__device__ __forceinline__ int ds_bins_excl_scan(int v, int *total, int *s_w) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int incl = ds_warp_incl_scan(v, lane);
-    if (lane == 31) s_w[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        int w = lane < DS_WARPS ? s_w[lane] : 0;
-        int wi = ds_warp_incl_scan(w, lane);
-        if (lane < DS_WARPS) s_w[lane] = wi - w;
-        if (lane == DS_WARPS - 1) s_w[DS_WARPS] = wi;
+    constexpr int NW = DS_BINS / 32;
+    int incl = 0;
+    if (warp < NW) {
+        incl = ds_warp_incl_scan(v, lane);
+        if (lane == 31) s_w[warp] = incl;
     }
     __syncthreads();
-    const int res = s_w[warp] + incl - v;
-    *total = s_w[DS_WARPS];
+    if (warp == 0) {
+        int w = lane < NW ? s_w[lane] : 0;
+        int wi = ds_warp_incl_scan(w, lane);
+        if (lane < NW) s_w[lane] = wi - w;
+        if (lane == NW - 1) s_w[NW] = wi;
+    }
+    __syncthreads();
+    const int res = warp < NW ? s_w[warp] + incl - v : 0;
+    *total = s_w[NW];
     __syncthreads();
     return res;
 }
 
-__global__ void __launch_bounds__(DS_THREADS)
-k_depth_sort_coop(const uint32_t *__restrict__ keys_in, int N,
-                  uint32_t *kA, uint32_t *vA, uint32_t *kB, uint32_t *vB /* == order */, int32_t *table /* [BINS][G] */,
-                  int32_t *digit_tot /* [BINS] */, int32_t *nvis_out) {
+__global__ void __launch_bounds__(DS_THREADS, 2)
+k_depth_sort_coop(const uint32_t *__restrict__ keys_in, int N, uint32_t *kA, uint32_t *vA, uint32_t *kB,
+                  uint32_t *vB /* == order */, int32_t *table /* [BINS][G] */, int32_t *nvis_out) {
     cg::grid_group grid = cg::this_grid();
-    extern __shared__ int ds_smem[];
-    int *s_cnt = ds_smem;                           // [DS_WARPS][DS_BINS]
-    int *s_run = ds_smem + DS_WARPS * DS_BINS;      // [DS_BINS]
-    int *s_w = s_run + DS_BINS;                     // scan scratch
+    extern __shared__ __align__(16) unsigned char ds_smem_raw[];
+    uint32_t *s_k = reinterpret_cast<uint32_t *>(ds_smem_raw);    // [DS_TILE] keys in digit-major order
+    uint32_t *s_v = s_k + DS_TILE;                                // [DS_TILE] values
+    int *s_cnt = reinterpret_cast<int *>(s_v + DS_TILE);          // [DS_WARPS][DS_BINS]
+    int *s_run = s_cnt + DS_WARPS * DS_BINS;                      // [DS_BINS] global cursor of this CTA's run per digit
+    int *s_tcnt = s_run + DS_BINS;                                // [DS_BINS] items per digit (all CTAs / this sub-tile)
+    int *s_toff = s_tcnt + DS_BINS;                               // [DS_BINS] start of the digit's run inside the sub-tile
+    int *s_gdst = s_toff + DS_BINS;                               // [DS_BINS] s_run - s_toff (global = local + this)
+    int *s_w = s_gdst + DS_BINS;                                  // scan scratch
     const int G = gridDim.x, b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = lanemask_lt();
@@ -82,69 +97,81 @@ k_depth_sort_coop(const uint32_t *__restrict__ keys_in, int N,
     int n = N;  // items entering the current pass
     for (int pass = 0; pass < DS_PASSES; ++pass) {
         const int shift = DS_BITS * pass;
-        const uint32_t *ksrc = pass == 0 ? keys_in : (pass == 1 ? kB : kA);
-        const uint32_t *vsrc = pass == 0 ? nullptr : (pass == 1 ? vB : vA);
-        uint32_t *kdst = pass == 1 ? kA : kB;
-        uint32_t *vdst = pass == 1 ? vA : vB;
-        const int per = (n + G - 1) / G;
+        // ping-pong: keys_in -> A -> B -> A -> B (= order)
+        const uint32_t *ksrc = pass == 0 ? keys_in : ((pass & 1) ? kA : kB);
+        const uint32_t *vsrc = pass == 0 ? nullptr : ((pass & 1) ? vA : vB);
+        uint32_t *kdst = (pass & 1) ? kB : kA;
+        uint32_t *vdst = (pass & 1) ? vB : vA;
+        // slices are multiples of 4 items so that 16-byte loads stay aligned
+        const int per = (((n + G - 1) / G) + 3) & ~3;
         const int begin = min(n, b * per), end = min(n, begin + per);
 
-        // ---- phase 1: histogram of this CTA's slice
+        // ---- (a) histogram of this CTA's slice
         for (int d = tid; d < DS_BINS; d += DS_THREADS) s_cnt[d] = 0;
         __syncthreads();
-        for (int i = begin + tid; i < end; i += DS_THREADS) {
-            const uint32_t k = ksrc[i];
-            if (pass > 0 || k != DS_CULLED) atomicAdd(&s_cnt[(k >> shift) & DS_MASK], 1);
+        for (int w0 = begin + warp * 128; w0 < end; w0 += DS_THREADS * 4) {  // warp-uniform trip count
+            const int i0 = w0 + 4 * lane;
+            uint32_t k4[4];
+            if (i0 + 3 < end) {
+                const uint4 q = *reinterpret_cast<const uint4 *>(ksrc + i0);
+                k4[0] = q.x; k4[1] = q.y; k4[2] = q.z; k4[3] = q.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) k4[j] = i0 + j < end ? ksrc[i0 + j] : DS_CULLED;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool valid = i0 + j < end && (pass > 0 || k4[j] != DS_CULLED);
+                const int d = valid ? (int)((k4[j] >> shift) & DS_MASK) : DS_BINS;
+                const unsigned peers = __match_any_sync(0xffffffffu, d);
+                if (valid && lane == __ffs(peers) - 1) atomicAdd(&s_cnt[d], __popc(peers));
+            }
         }
         __syncthreads();
         for (int d = tid; d < DS_BINS; d += DS_THREADS) table[(size_t)d * G + b] = s_cnt[d];
         grid.sync();
 
-        // ---- phase 2: per-digit exclusive scan over the CTAs (one warp per digit row), digit totals
-        for (int row = b * DS_WARPS + warp; row < DS_BINS; row += G * DS_WARPS) {
-            int32_t *r = table + (size_t)row * G;
-            int carry = 0;
-            for (int x = 0; x < G; x += 32) {
-                const int v = (x + lane < G) ? r[x + lane] : 0;
-                const int incl = ds_warp_incl_scan(v, lane);
-                if (x + lane < G) r[x + lane] = carry + incl - v;
-                carry += __shfl_sync(0xffffffffu, incl, 31);
-            }
-            if (lane == 0) digit_tot[row] = carry;
-        }
-        grid.sync();
-
-        // ---- phase 3: digit bases (every CTA, redundantly) -> running cursor of this CTA per digit
+        // ---- (b1) global start of this CTA's run of every digit: digit totals + counts of the CTAs before this one
         {
-            int loc[DS_BINS / DS_THREADS];
-            int sum = 0;
+            constexpr int ROWS = DS_BINS / DS_WARPS;  // digit rows per warp
+            for (int r = 0; r < ROWS; ++r) {
+                const int d = warp * ROWS + r;
+                const int32_t *row = table + (size_t)d * G;
+                int tot = 0, pre = 0;
+                for (int c = lane; c < G; c += 32) {
+                    const int v = row[c];
+                    tot += v;
+                    pre += c < b ? v : 0;
+                }
 #pragma unroll
-            for (int k = 0; k < DS_BINS / DS_THREADS; ++k) {
-                loc[k] = digit_tot[tid * (DS_BINS / DS_THREADS) + k];
-                sum += loc[k];
+                for (int o = 16; o > 0; o >>= 1) {
+                    tot += __shfl_xor_sync(0xffffffffu, tot, o);
+                    pre += __shfl_xor_sync(0xffffffffu, pre, o);
+                }
+                if (lane == 0) {
+                    s_tcnt[d] = tot;
+                    s_run[d] = pre;
+                }
             }
-            int tot;
-            int ex = ds_block_excl_scan(sum, &tot, s_w);
-#pragma unroll
-            for (int k = 0; k < DS_BINS / DS_THREADS; ++k) {
-                const int d = tid * (DS_BINS / DS_THREADS) + k;
-                s_run[d] = ex + table[(size_t)d * G + b];
-                ex += loc[k];
-            }
+            __syncthreads();
+            int total;
+            const int ex = ds_bins_excl_scan(tid < DS_BINS ? s_tcnt[tid] : 0, &total, s_w);
+            if (tid < DS_BINS) s_run[tid] += ex;
             if (pass == 0) {
-                if (b == 0 && tid == 0) *nvis_out = tot;
-                n = tot;  // later passes (and their slices) only see the visible Gaussians
+                if (b == 0 && tid == 0) *nvis_out = total;
+                n = total;  // later passes (and their slices) only see the visible Gaussians
             }
+            __syncthreads();
         }
-        __syncthreads();
-        // stable ranking + scatter, sub-tile by sub-tile in slice order
+
+        // ---- (b2) stable ranking + coalesced scatter, sub-tile by sub-tile in slice order
         for (int sub = begin; sub < end; sub += DS_TILE) {
             for (int i = tid; i < DS_WARPS * DS_BINS; i += DS_THREADS) s_cnt[i] = 0;
             __syncthreads();
             int *my_cnt = s_cnt + warp * DS_BINS;
             const int wbase = sub + warp * (32 * DS_ROUNDS);
             uint32_t key[DS_ROUNDS];
-            int wrank[DS_ROUNDS];
+            unsigned wrank2[DS_ROUNDS / 2];  // ranks inside the warp's digit group: < 512, two per register (0xffff = invalid)
 #pragma unroll
             for (int r = 0; r < DS_ROUNDS; ++r) {
                 const int i = wbase + r * 32 + lane;
@@ -162,34 +189,55 @@ k_depth_sort_coop(const uint32_t *__restrict__ keys_in, int N,
                 // so earlier rounds get smaller ranks (stable)
                 if (lane == leader && valid) old = atomicAdd(&my_cnt[d], __popc(peers));
                 old = __shfl_sync(0xffffffffu, old, leader);
-                wrank[r] = valid ? old + __popc(peers & lt) : -1;
+                const unsigned rk = valid ? (unsigned)(old + __popc(peers & lt)) : 0xffffu;
+                if (r & 1) wrank2[r >> 1] |= rk << 16;
+                else wrank2[r >> 1] = rk;
             }
             __syncthreads();
-            for (int d = tid; d < DS_BINS; d += DS_THREADS) {
-                int running = s_run[d];
+            // per digit: exclusive prefix over the warps (in place), items of the digit in this sub-tile
+            if (tid < DS_BINS) {
+                int running = 0;
 #pragma unroll
                 for (int w = 0; w < DS_WARPS; ++w) {
-                    const int c = s_cnt[w * DS_BINS + d];
-                    s_cnt[w * DS_BINS + d] = running;
+                    const int c = s_cnt[w * DS_BINS + tid];
+                    s_cnt[w * DS_BINS + tid] = running;
                     running += c;
                 }
-                s_run[d] = running;
+                s_tcnt[tid] = running;
             }
             __syncthreads();
+            int tile_n;
+            const int toff = ds_bins_excl_scan(tid < DS_BINS ? s_tcnt[tid] : 0, &tile_n, s_w);
+            if (tid < DS_BINS) {
+                s_toff[tid] = toff;
+                s_gdst[tid] = s_run[tid] - toff;
+                s_run[tid] += s_tcnt[tid];
+            }
+            __syncthreads();
+            // digit-major order inside shared memory
 #pragma unroll
             for (int r = 0; r < DS_ROUNDS; ++r) {
-                if (wrank[r] >= 0) {
+                const unsigned rk = (wrank2[r >> 1] >> (16 * (r & 1))) & 0xffffu;
+                if (rk != 0xffffu) {
                     const int i = wbase + r * 32 + lane;
-                    const int pos = my_cnt[(key[r] >> shift) & DS_MASK] + wrank[r];
-                    kdst[pos] = key[r];
-                    vdst[pos] = pass == 0 ? (uint32_t)i : vsrc[i];
+                    const int d = (int)((key[r] >> shift) & DS_MASK);
+                    const int lp = s_toff[d] + my_cnt[d] + (int)rk;
+                    s_k[lp] = key[r];
+                    s_v[lp] = pass == 0 ? (uint32_t)i : vsrc[i];
                 }
+            }
+            __syncthreads();
+            // coalesced runs out
+            for (int i = tid; i < tile_n; i += DS_THREADS) {
+                const uint32_t k = s_k[i];
+                const int pos = s_gdst[(k >> shift) & DS_MASK] + i;
+                kdst[pos] = k;
+                vdst[pos] = s_v[i];
             }
             __syncthreads();
         }
-        grid.sync();
+        if (pass + 1 < DS_PASSES) grid.sync();
     }
-
 }
 
 static inline size_t ds_align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -204,20 +252,22 @@ static int ds_max_grid(int device) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_depth_sort_coop, DS_THREADS, DS_SMEM);
     int g = sms * (per_sm > 0 ? per_sm : 1);
     if (g < 1) g = 1;
+    if (g > DS_MAX_GRID) g = DS_MAX_GRID;
     if (device >= 0 && device < 64) cached[device] = g;
     return g;
 }
 
 extern "C" size_t b2s_bin_depth_workspace_bytes(int N) {
     size_t n = (size_t)(N > 0 ? N : 1);
-    // kA, vA, kB + table [BINS][G<=2048] + digit totals
-    return 3 * ds_align256(n * 4) + ds_align256((size_t)DS_BINS * 2048 * 4) + ds_align256(DS_BINS * 4) + 1024;
+    // kA, vA, kB (+16 bytes each for vector loads at the slice ends) + table [BINS][G <= DS_MAX_GRID]
+    return 3 * ds_align256(n * 4 + 16) + ds_align256((size_t)DS_BINS * DS_MAX_GRID * 4) + 1024;
 }
 
 extern "C" int b2s_bin_sort_depth(const uint32_t *sort_keys, int N, int32_t *order, int32_t *n_vis,
                                   void *workspace, size_t workspace_bytes, b2s_stream_t stream) {
     if (N < 0) return B2S_ERR_ARG;
     if (workspace_bytes < b2s_bin_depth_workspace_bytes(N)) return B2S_ERR_WORKSPACE;
+    if (((uintptr_t)sort_keys & 15) || ((uintptr_t)workspace & 15)) return B2S_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (N == 0) {
         cudaMemsetAsync(n_vis, 0, sizeof(int32_t), st);
@@ -228,17 +278,15 @@ extern "C" int b2s_bin_sort_depth(const uint32_t *sort_keys, int N, int32_t *ord
     int G = ds_max_grid(device);
     const int by_work = b2s_div_up(N, DS_TILE);
     if (G > by_work) G = by_work;
-    if (G > 2048) G = 2048;
     char *w = (char *)workspace;
-    const size_t n4 = ds_align256((size_t)N * 4);
+    const size_t n4 = ds_align256((size_t)N * 4 + 16);
     uint32_t *kA = (uint32_t *)w; w += n4;
     uint32_t *vA = (uint32_t *)w; w += n4;
     uint32_t *kB = (uint32_t *)w; w += n4;
-    int32_t *table = (int32_t *)w; w += ds_align256((size_t)DS_BINS * 2048 * 4);
-    int32_t *digit_tot = (int32_t *)w;
+    int32_t *table = (int32_t *)w;
     uint32_t *vB = (uint32_t *)order;
-    void *args[] = {(void *)&sort_keys, (void *)&N,     (void *)&kA,        (void *)&vA,   (void *)&kB,
-                    (void *)&vB,        (void *)&table, (void *)&digit_tot, (void *)&n_vis};
+    void *args[] = {(void *)&sort_keys, (void *)&N, (void *)&kA, (void *)&vA, (void *)&kB, (void *)&vB, (void *)&table,
+                    (void *)&n_vis};
     cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_depth_sort_coop, dim3(G), dim3(DS_THREADS), args,
                                                 DS_SMEM, st);
     if (e != cudaSuccess) {

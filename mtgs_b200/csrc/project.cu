@@ -88,7 +88,7 @@ __device__ __forceinline__ void covar_cam_rn(const float *R, const float *Rq, fl
 }
 
 template <int CDIM>
-__global__ void __launch_bounds__(256, 5)
+__global__ void __launch_bounds__(256, 4)
 k_project_fwd(const float *__restrict__ means, const float *__restrict__ quats, const float *__restrict__ scales,
               const float *__restrict__ opacities, const float *__restrict__ colors_in,
               const float *__restrict__ viewmat, const float *__restrict__ K, int N, int W, int H, int tile_w,
@@ -118,6 +118,8 @@ k_project_fwd(const float *__restrict__ means, const float *__restrict__ quats, 
     int32_t ntiles = 0;
     int2 rect = make_int2(0, 0);  // (x0 | x1 << 16, y0 | y1 << 16) in tiles, max exclusive
     int rx0 = 0, rx1 = 0, ry0 = 0, ry1 = 0;
+    int tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0;  // tight rectangle
+    float op = 0.f;                          // opacity * compensation
     float mx = 0.f, my = 0.f, ca = 0.f, cb = 0.f, cc = 0.f, comp = 1.f;
     float z = pc[2];
     bool ok = !(z < near_plane || z > far_plane);
@@ -177,41 +179,36 @@ k_project_fwd(const float *__restrict__ means, const float *__restrict__ quats, 
                 ntiles = (y1 - y0) * (x1 - x0);
                 rect = make_int2(x0 | (x1 << 16), y0 | (y1 << 16));
                 rx0 = x0; rx1 = x1; ry0 = y0; ry1 = y1;
+                // ---- tight rectangle for the blend's own tile lists: tiles whose pixel centres the footprint
+                // {alpha >= 1/255} = {sigma <= ln(255 opacity)} can reach, intersected with upstream's 3-sigma
+                // rectangle.  Not an upstream output (info["tiles_per_gauss"] / flatten_ids stay upstream's): it only
+                // removes (Gaussian, tile) pairs that contribute to no pixel.  Extents: |dx| <= sqrt(2 t c00), |dy| <=
+                // sqrt(2 t c11) with c00, c11 the blurred 2-D covariance.  The blend evaluates the STORED conic, whose
+                // ellipse differs from the ideal one by a relative ~2^-24 kappa in its extents (kappa = c00 c11 / det,
+                // the cancellation in the inverse), and it evaluates sigma with an fp32 error ~2^-22 (|A|+|B|+|C|) R^2:
+                // both are covered by the slack.  The exact per-tile test follows while the blend stages a batch.
+                op = opacities[g];
+                if (calc_comp) op = MUL(op, comp);
+                if (op >= 0.0039f) {  // below 1/255 the Gaussian reaches no pixel (same gate as tile_keep)
+                    const float Rb = radius + 16.0f;
+                    const float t2 = __log2f(op * 255.0f) + 0.02f +
+                                     4e-7f * B2S_LOG2E * (0.5f * ca + fabsf(cb) + 0.5f * cc) * Rb * Rb;  // log2 units
+                    const float kappa = fminf(c00 * c11 * inv_det, 1e12f);
+                    const float infl = (1.0f + 2.5e-7f * kappa) * (2.0f * B2S_LN2) * t2;  // 2 t (ln units), inflated
+                    const float hx = fminf(sqrtf(infl * c00) * 1.0001f + 0.01f, 1e6f);
+                    const float hy = fminf(sqrtf(infl * c11) * 1.0001f + 0.01f, 1e6f);
+                    // tile k holds the pixel centres 16 k + 0.5 .. 16 k + 15.5
+                    const float mxc = fminf(fmaxf(mx, -1e6f), 1e6f), myc = fminf(fmaxf(my, -1e6f), 1e6f);
+                    tx0 = max(x0, (int)ceilf((mxc - hx - 15.5f) * 0.0625f));
+                    tx1 = min(x1, (int)floorf((mxc + hx - 0.5f) * 0.0625f) + 1);
+                    ty0 = max(y0, (int)ceilf((myc - hy - 15.5f) * 0.0625f));
+                    ty1 = min(y1, (int)floorf((myc + hy - 0.5f) * 0.0625f) + 1);
+                    if (tx1 <= tx0 || ty1 <= ty0) tx0 = tx1 = ty0 = ty1 = 0;
+                }
             }
         }
     }
-    // ---- tight rectangle for the blend's own tile lists: tiles whose pixel centres the footprint
-    // {alpha >= 1/255} = {sigma <= ln(255 opacity)} can reach, intersected with upstream's 3-sigma rectangle.  Not
-    // part of upstream's outputs (info["tiles_per_gauss"] / flatten_ids stay upstream's): it only removes
-    // (Gaussian, tile) pairs that contribute to no pixel.  Extents of the ellipse defined by the STORED conic (what
-    // the blend evaluates), discriminant in double (4AC - B^2 cancels for thin splats), plus slack for the blend's
-    // fp32 evaluation error; the exact per-tile test follows in the last level of the tile lists.
-    float op = 0.f;
-    int2 trect = make_int2(0, 0);
-    int tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0;
-    if (radius_i > 0) {
-        op = opacities[g];
-        if (calc_comp) op = MUL(op, comp);
-        if (op >= 0.0039f) {
-            tx0 = rx0; tx1 = rx1; ty0 = ry0; ty1 = ry1;
-            const float A2 = (0.5f * B2S_LOG2E) * ca, B2 = B2S_LOG2E * cb, C2 = (0.5f * B2S_LOG2E) * cc;
-            const double disc = 4.0 * (double)A2 * (double)C2 - (double)B2 * (double)B2;
-            if (disc > 0.0 && A2 > 0.f && C2 > 0.f) {
-                const float Rb = (float)radius_i + 16.0f;
-                const float tau = __log2f(op * 255.0f) + 0.02f + 4e-7f * (A2 + fabsf(B2) + C2) * Rb * Rb;
-                const float hx = fminf((float)sqrt(4.0 * (double)C2 * (double)tau / disc) * 1.0001f + 0.01f, 1e6f);
-                const float hy = fminf((float)sqrt(4.0 * (double)A2 * (double)tau / disc) * 1.0001f + 0.01f, 1e6f);
-                // tile k holds the pixel centres 16 k + 0.5 .. 16 k + 15.5
-                const float mxc = fminf(fmaxf(mx, -1e6f), 1e6f), myc = fminf(fmaxf(my, -1e6f), 1e6f);
-                tx0 = max(tx0, (int)ceilf((mxc - hx - 15.5f) * 0.0625f));
-                tx1 = min(tx1, (int)floorf((mxc + hx - 0.5f) * 0.0625f) + 1);
-                ty0 = max(ty0, (int)ceilf((myc - hy - 15.5f) * 0.0625f));
-                ty1 = min(ty1, (int)floorf((myc + hy - 0.5f) * 0.0625f) + 1);
-            }
-            if (tx1 <= tx0 || ty1 <= ty0) tx0 = tx1 = ty0 = ty1 = 0;
-            trect = make_int2(tx0 | (tx1 << 16), ty0 | (ty1 << 16));
-        }
-    }
+    const int2 trect = make_int2(tx0 | (tx1 << 16), ty0 | (ty1 << 16));
     // ---- list sizes of both tile-list builds (tilelists.cu): upstream's rectangles [0..3], tight rectangles [4..7],
     // visible Gaussians [8]; one integer warp reduction (redux.sync) per value, 9 atomics per CTA
     {
@@ -566,7 +563,8 @@ extern "C" int b2s_project_fwd(const float *means, const float *quats, const flo
                                float *geo, float *comps, float *colpack, int32_t *tiles_per_gauss,
                                uint32_t *sort_keys, int32_t *tile_rects, int32_t *tight_rects, int64_t *totals,
                                float *bwd_arena, b2s_stream_t stream) {
-    if (N < 0 || W <= 0 || H <= 0 || totals == nullptr || tight_rects == nullptr) return B2S_ERR_ARG;
+    if (N < 0 || W <= 0 || H <= 0 || totals == nullptr) return B2S_ERR_ARG;
+    if (N > 0 && tight_rects == nullptr) return B2S_ERR_ARG;
     int rg_shift = 0, cg_shift = 0;
     if (b2s_tl_shifts(tile_w, tile_h, &rg_shift, &cg_shift) != B2S_OK) return B2S_ERR_UNSUPPORTED;
     if (tile_size != 16 || tile_w > 32767 || tile_h > 32767) return B2S_ERR_UNSUPPORTED;

@@ -275,25 +275,24 @@ def _sort_and_read_totals(keys: Tensor, totals: Tensor):
 
 
 def _tile_lists(rects: Tensor, order: Tensor, n_vis: Tensor, sizes, tile_w: int, tile_h: int, W: int, H: int,
-                means2d: Optional[Tensor], geo: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
-    """Per-tile depth-ordered lists.  ``means2d`` / ``geo`` given: the blend's own lists (tight rectangles + exact
-    per-tile test), offsets with a trailing total; otherwise upstream's lists.  ``sizes`` = (list length, S, E1, E3,
-    n_vis) as summed by the projection kernel for ``rects``."""
+                walk: bool) -> Tuple[Tensor, Tensor]:
+    """Per-tile depth-ordered lists over ``rects``.  ``walk``: the blend's own lists (tight rectangles; offsets carry a
+    trailing total so that no host-side count is needed); otherwise upstream's lists over the 3-sigma rectangles.
+    ``sizes`` = (list length, S, E1, E3, n_vis) as summed by the projection kernel for ``rects``."""
     lib = _lib.load()
     dev = rects.device
     N = rects.shape[0]
-    exact = means2d is not None
     tot = (C.c_longlong * 5)(*sizes)
     ids = torch.empty(sizes[0], dtype=torch.int32, device=dev)
-    offsets = torch.empty(tile_h * tile_w + (1 if exact else 0), dtype=torch.int32, device=dev)
+    offsets = torch.empty(tile_h * tile_w + (1 if walk else 0), dtype=torch.int32, device=dev)
     wsb = int(lib.b2s_bin_tiles_workspace_bytes(tot, tile_w, tile_h))
     if wsb == 0:
         raise NotImplementedError(f"tile grid {tile_w}x{tile_h} not supported")
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-    with _timed("bin_tiles" if exact else "bin_tiles_upstream_lists"):
+    with _timed("bin_tiles" if walk else "bin_tiles_upstream_lists"):
         _lib.check(lib.b2s_bin_tiles(_ptr(rects), _ptr(order), _ptr(n_vis), tot, N, 16, tile_w, tile_h, W, H,
-                                     _ptr(means2d), _ptr(geo), int(exact), _ptr(ids), _ptr(offsets), _ptr(ws), wsb,
-                                     _stream()), "b2s_bin_tiles")
+                                     None, None, int(walk), _ptr(ids), _ptr(offsets), _ptr(ws), wsb, _stream()),
+                   "b2s_bin_tiles")
     return ids, offsets
 
 
@@ -325,9 +324,9 @@ def _rasterize_one(means, quats, scales, opacities, colors, viewmat, K, width, h
         means, quats, scales, opacities, cols, viewmat, K, width, height, tile_w, tile_h, float(eps2d),
         float(near_plane), float(far_plane), float(radius_clip), calc_comp, with_depth, cdim, want_grad)
     order, n_vis, tot = _sort_and_read_totals(keys, totals)
-    # the lists the blend walks: tight rectangles + exact per-tile test (never more than tot[4] entries)
+    # the lists the blend walks: tight rectangles (the exact per-tile test runs lazily while the blend stages a batch)
     walk_ids, walk_offsets = _tile_lists(tight, order, n_vis, (tot[4], tot[5], tot[6], tot[7], tot[8]), tile_w, tile_h,
-                                         width, height, means2d.detach(), geo.detach())
+                                         width, height, True)
     render, alpha, last_ids = _Blend.apply(means2d, geo, colpack, walk_offsets, walk_ids, arena, width, height,
                                            tile_w, tile_h, cdim, d_out, ed, bool(absgrad))
     # keys with a leading underscore are not part of upstream's info dict (bench.py reads them for K_pairs)
@@ -339,7 +338,7 @@ def _rasterize_one(means, quats, scales, opacities, colors, viewmat, K, width, h
         """upstream's flatten_ids / isect_offsets / isect_ids, on demand (bit-identical to the 64-bit sort)."""
         with torch.cuda.device(rects.device):
             flat, offs = _tile_lists(rects, order, n_vis, (tot[0], tot[1], tot[2], tot[3], tot[8]), tile_w, tile_h, width,
-                                     height, None, None)
+                                     height, False)
             return dict(flatten_ids=flat, isect_offsets=offs.view(1, tile_h, tile_w),
                         isect_ids=_isect_ids(offs, flat, depths))
 
