@@ -200,6 +200,31 @@ int b2s_ssim_bwd(const float *self, const float *other, const float *map_a, cons
                  const float *map_c, const float *plane_scale, int N, int C, int H, int W, const float *win,
                  int win_size, float *grad, b2s_stream_t stream);
 
+/* ---- other image-space losses of the training step ----
+ * Reference op sequences: masked L1 on RGB / normals mtgs_scene_graph.py:825-828, 929; LiDAR depth loss (L1 /
+ * InverseL1) :875-884; TVLoss mtgs/utils/geometric_loss.py:287-303; calculate_depth_ncc_loss :322-348;
+ * pcd_to_normal / normal_from_depth_image :350-388 (+ camera_utils.py:74-148).  Every forward accumulates (sum, count)
+ * -- or the two directional sums for TV -- into acc (device double[2], zero-filled by the caller); the mean is formed
+ * on the device by the caller, nothing synchronises.  Backward passes take the upstream gradient as a DEVICE scalar.
+ * masked L1: pred, gt [P, C]; mask uint8 [P] or NULL; mode 0 = |gt - pred|, mode 1 = |1/(gt+eps) - 1/(pred+eps)|.
+ * TV: pred [B, H, W, C].  NCC: depth maps [H, W], mask uint8 [H, W]; patches patch x patch at `stride`, zero padding
+ * patch / 2 as F.unfold; stats [npy * npx, 6] (b2s_ncc_patch_grid gives npy, npx) is written by the forward and read
+ * by the backward.  normal_from_depth: A_t = 12 device floats, inv(c2w[:3,:3]) row-major then c2w[:3,3]. */
+int b2s_masked_l1_fwd(const float *pred, const float *gt, const uint8_t *mask, long long P, int C, int mode,
+                      float eps, double *acc, b2s_stream_t stream);
+int b2s_masked_l1_bwd(const float *pred, const float *gt, const uint8_t *mask, long long P, int C, int mode,
+                      float eps, const double *acc, const float *grad_out, float *grad_pred, b2s_stream_t stream);
+int b2s_tv_fwd(const float *pred, int B, int H, int W, int C, double *acc, b2s_stream_t stream);
+int b2s_tv_bwd(const float *pred, int B, int H, int W, int C, const float *grad_out, float *grad_pred,
+               b2s_stream_t stream);
+int b2s_ncc_patch_grid(int H, int W, int patch, int stride, int *npy, int *npx);
+int b2s_ncc_fwd(const float *pred, const float *gt, const uint8_t *mask, int H, int W, int patch, int stride,
+                float *stats, double *acc, b2s_stream_t stream);
+int b2s_ncc_bwd(const float *pred, const float *gt, int H, int W, int patch, int stride, const float *stats,
+                const double *acc, const float *grad_out, float *grad_pred, b2s_stream_t stream);
+int b2s_normal_from_depth(const float *depth, int H, int W, float fx, float fy, float cx, float cy,
+                          const float *A_t, float *normals, b2s_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,6 +39,14 @@ SIGNATURES = {
     "b2s_blend_bwd": (_i, [_vp] * 2 + [_i] * 7 + [_vp] * 8 + [_vp]),
     "b2s_ssim_fwd": (_i, [_vp] * 3 + [_ll, _ll] + [_i] * 4 + [_vp, _i, _f, _f] + [_vp] * 5 + [_vp]),
     "b2s_ssim_bwd": (_i, [_vp] * 6 + [_i] * 4 + [_vp, _i, _vp] + [_vp]),
+    "b2s_masked_l1_fwd": (_i, [_vp] * 3 + [_ll, _i, _i, _f, _vp, _vp]),
+    "b2s_masked_l1_bwd": (_i, [_vp] * 3 + [_ll, _i, _i, _f, _vp, _vp, _vp, _vp]),
+    "b2s_tv_fwd": (_i, [_vp] + [_i] * 4 + [_vp, _vp]),
+    "b2s_tv_bwd": (_i, [_vp] + [_i] * 4 + [_vp, _vp, _vp]),
+    "b2s_ncc_patch_grid": (_i, [_i] * 4 + [C.POINTER(_i), C.POINTER(_i)]),
+    "b2s_ncc_fwd": (_i, [_vp] * 3 + [_i] * 4 + [_vp, _vp, _vp]),
+    "b2s_ncc_bwd": (_i, [_vp] * 2 + [_i] * 4 + [_vp] * 4 + [_vp]),
+    "b2s_normal_from_depth": (_i, [_vp, _i, _i] + [_f] * 4 + [_vp, _vp, _vp]),
     "b2s_sh_fwd": (_i, [_i] + [_vp] * 3 + [_i, _i] + [_vp, _vp]),
     "b2s_sh_bwd": (_i, [_i] + [_vp] * 3 + [_i, _i] + [_vp] * 3 + [_vp]),
 }

