@@ -225,6 +225,37 @@ int b2s_ncc_bwd(const float *pred, const float *gt, int H, int W, int patch, int
 int b2s_normal_from_depth(const float *depth, int H, int W, float fx, float fy, float cx, float cy,
                           const float *A_t, float *normals, b2s_stream_t stream);
 
+/* ---- fused multi-tensor Adam + densification primitives ----
+ * Reference: one torch.optim.Adam per (node, attribute) group (mtgs/scene_model/custom_trainer.py:115-136), the
+ * after_train statistics and optimizer-state surgery of gaussian_model/vanilla_gaussian_splatting.py:392-474 and the
+ * cull / split / duplicate steps of :476-699.
+ * b2s_adam_multi: ONE launch steps every tensor: tensors_dev = device array of descriptors, chunk c of
+ *   b2s_adam_chunk() elements belongs to tensor chunk_tensor_dev[c] and starts at element chunk_start_dev[c].
+ *   Arithmetic = torch.optim.Adam (no amsgrad): bias_correction{1,2} = 1 - beta^step, computed by the host.
+ * b2s_densify_stats: for radii > 0: xys_grad_norm += ||grad2d * (W, H) / 2||, vis_counts += 1, max_2dsize =
+ *   max(max_2dsize, radii)   (grad2d rows have grad_stride floats: 2, or 4 for the blend's (xy, |xy|) arena).
+ * b2s_mask_scan + b2s_mask_gather_rows: order-preserving compaction of [N, row_floats] rows by a uint8 keep mask;
+ *   scan once (workspace = b2s_mask_workspace_bytes(N); *total = rows kept, device int32), then gather every tensor
+ *   that shares the mask (parameters and their Adam moments). */
+typedef struct B2sAdamTensor {
+    float *p;
+    const float *g;
+    float *m;
+    float *v;
+    long long n;
+    float lr, beta1, beta2, eps, weight_decay, bias_correction1, bias_correction2, _pad;
+} B2sAdamTensor;
+int b2s_adam_chunk(void);
+int b2s_adam_multi(const B2sAdamTensor *tensors_dev, const int32_t *chunk_tensor_dev,
+                   const long long *chunk_start_dev, int n_chunks, b2s_stream_t stream);
+int b2s_densify_stats(const float *grad2d, int grad_stride, const int32_t *radii, int N, int W, int H,
+                      float *xys_grad_norm, float *vis_counts, float *max_2dsize, b2s_stream_t stream);
+size_t b2s_mask_workspace_bytes(long long N);
+int b2s_mask_scan(const uint8_t *keep, long long N, void *workspace, size_t workspace_bytes, int32_t *total,
+                  b2s_stream_t stream);
+int b2s_mask_gather_rows(const uint8_t *keep, long long N, const void *workspace, const float *src, float *dst,
+                         int row_floats, b2s_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
