@@ -51,12 +51,12 @@ long long b2s_launch_count(void);
  *   colpack[g] = (colors_in[0..d_in), depth if with_depth, zero pad) , cdim floats
  * and tight_rects: tile_rects intersected with the tiles whose pixel centres the footprint {alpha >= 1/255} of the
  * Gaussian can reach -- the rectangles the blend's own tile lists are built from (not an upstream output).
- * totals (int64[9], zero-filled by the caller) receives the list sizes of both tile-list builds:
- *   [0..3] = M, S, E1, E3 over tile_rects   (M = upstream's number of intersections = sum of tiles_per_gauss)
- *   [4..7] = the same over tight_rects      (upper bounds of the blend's own lists)
- *   [8]    = number of visible Gaussians (radii > 0)
+ * totals (int64[5], zero-filled by the caller) receives the list sizes of the tile-list build over tight_rects:
+ *   [0] = list length, [1] = S (tile-row hits), [2] = E1 (row-group hits), [3] = E3 ((row, column-group) hits),
+ *   [4] = number of visible Gaussians (radii > 0).
  * The caller reads them back ONCE (the one device->host read of the path, overlapped with the depth sort) to size
- * the lists and the workspace of b2s_bin_tiles.  bwd_arena (may be NULL) = the N * (8 + cdim) floats of the blend
+ * the lists and the workspace of b2s_bin_tiles.  (b2s_bin_rect_totals computes the same five numbers for any other
+ * rectangle array, e.g. tile_rects when upstream's lists are wanted.)  bwd_arena (may be NULL) = the N * (8 + cdim) floats of the blend
  * backward's accumulation buffers (v_xyabs | v_geo | v_colpack), zero-filled here so that no memset pass is needed.
  * comps may be NULL when calc_comp == 0.  colors_in is [N, d_in]. */
 int b2s_project_fwd(const float *means, const float *quats, const float *scales,
@@ -67,7 +67,7 @@ int b2s_project_fwd(const float *means, const float *quats, const float *scales,
                     float *means2d, float *depths, float *geo, float *comps, float *colpack,
                     int32_t *tiles_per_gauss, uint32_t *sort_keys,
                     int32_t *tile_rects /* [N,2]: x0 | x1 << 16, y0 | y1 << 16 */,
-                    int32_t *tight_rects /* [N,2], same packing */, int64_t *totals /* [9] */,
+                    int32_t *tight_rects /* [N,2], same packing */, int64_t *totals /* [5] */,
                     float *bwd_arena, b2s_stream_t stream);
 
 /* upstream fully_fused_projection bwd fused with the opacity*compensation and
@@ -130,8 +130,8 @@ int b2s_project_bwd_exchange(const float *means, const float *quats, const float
  *       order[0..n_vis), *n_vis (device int32).  Entries of order beyond n_vis are undefined.
  *   (2) b2s_bin_tiles      : hierarchy of order-preserving filters (Gaussians -> row groups -> tile rows ->
  *       column groups -> tiles) walking the Gaussians in depth order -> flatten_ids, isect_offsets (no sort of the
- *       intersections).  totals_host = {list length, S, E1, E3, n_vis} for the rectangles passed in (b2s_project_fwd
- *       totals [0..3] + [8] for tile_rects, [4..7] + [8] for tight_rects); they size flatten_ids (list length
+ *       intersections).  totals_host = {list length, S, E1, E3, n_vis} for the rectangles passed in (b2s_project_fwd's
+ *       totals for tight_rects, b2s_bin_rect_totals for any other array); they size flatten_ids (list length
  *       entries) and the workspace.
  *       means2d == geo == NULL: upstream's lists (every tile of the rectangle), bit-identical flatten_ids /
  *       isect_offsets.  means2d, geo given ("exact" mode, with tight_rects): the last level keeps only the (Gaussian,
@@ -139,6 +139,8 @@ int b2s_project_bwd_exchange(const float *means, const float *quats, const float
  *       the list is then at most `list length` long.  offsets_with_total != 0: isect_offsets has tile_w * tile_h + 1
  *       entries, the last one = the final list length (so the blend needs no host-side count).
  *   (3) b2s_bin_isect_ids  : optional, rebuilds upstream's int64 isect_ids for inspection. */
+int b2s_bin_rect_totals(const int32_t *rects, int N, int tile_w, int tile_h, int64_t *totals /* [5] */,
+                        b2s_stream_t stream);
 size_t b2s_bin_depth_workspace_bytes(int N);
 int b2s_bin_sort_depth(const uint32_t *sort_keys, int N, int32_t *order, int32_t *n_vis, void *workspace,
                        size_t workspace_bytes, b2s_stream_t stream);

@@ -29,6 +29,7 @@ SIGNATURES = {
     "b2s_ipc_close": (_i, [_vp]),
     "b2s_project_bwd_exchange": (_i, [_vp] * 6 + [_i] * 3 + [_f] + [_i] * 4 + [_vp] * 4 + [_i] + [_vp] * 3 +
                                  [_i, _i, _i, _i, _ll, _f, C.c_uint, _i, _f] + [_vp] * 4 + [_vp]),
+    "b2s_bin_rect_totals": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "b2s_bin_depth_workspace_bytes": (_sz, [_i]),
     "b2s_bin_sort_depth": (_i, [_vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "b2s_bin_tiles_workspace_bytes": (_sz, [C.POINTER(_ll), _i, _i]),

@@ -10,7 +10,7 @@
 #define B2S_T_EPS 1e-4f
 #define B2S_LOG2E 1.4426950408889634f
 #define B2S_LN2 0.6931471805599453f
-#define B2S_N_TOTALS 9  // list sizes written by the projection: see b2s_project_fwd in include/b200splat.h
+#define B2S_N_TOTALS 5  // list sizes written by the projection: see b2s_project_fwd in include/b200splat.h
 
 // Diagnostic launch counter (api.cu): the library's only mutable global; atomic, never read by a kernel launch path.
 void b2s_count_launch(int n);

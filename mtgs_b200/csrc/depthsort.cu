@@ -15,8 +15,9 @@
 // stable LSD radix sort; the whole working set (keys + ids of the visible Gaussians, ~10 MB) lives in the 126 MB L2.
 // Per pass and CTA (a CTA owns a contiguous slice of the input):
 //     (a) digit histogram of the slice (warp-aggregated shared-memory atomics) -> table[digit][cta]   -> grid barrier
-//     (b) every CTA derives the global start of ITS run of every digit from the table (one warp per 16 digit rows,
-//         coalesced row reads), then sub-tile by sub-tile (4096 items): stable ranks from match.any groups and
+//     (a2) exclusive scan of every digit row over the CTAs (one warp per row, rows spread over the grid) -> grid barrier
+//     (b) every CTA reads the global start of ITS run of every digit (256 loads + one block scan over the digit
+//         totals), then sub-tile by sub-tile (4096 items): stable ranks from match.any groups and
 //         per-warp digit counters, a pass through shared memory that makes each digit's items contiguous, and a
 //         scatter whose stores are coalesced runs (average run = 16 items at 8 bits per digit)        -> grid barrier
 // The round-1 version used 11-bit digits (3 passes): 2048 counters per 4096-item sub-tile made the cross-warp prefix
@@ -79,7 +80,8 @@ __device__ __forceinline__ int ds_bins_excl_scan(int v, int *total, int *s_w) {
 
 __global__ void __launch_bounds__(DS_THREADS, 2)
 k_depth_sort_coop(const uint32_t *__restrict__ keys_in, int N, uint32_t *kA, uint32_t *vA, uint32_t *kB,
-                  uint32_t *vB /* == order */, int32_t *table /* [BINS][G] */, int32_t *nvis_out) {
+                  uint32_t *vB /* == order */, int32_t *table /* [BINS][G] */, int32_t *digit_tot /* [BINS] */,
+                  int32_t *nvis_out) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned char ds_smem_raw[];
     uint32_t *s_k = reinterpret_cast<uint32_t *>(ds_smem_raw);    // [DS_TILE] keys in digit-major order
@@ -131,32 +133,27 @@ k_depth_sort_coop(const uint32_t *__restrict__ keys_in, int N, uint32_t *kA, uin
         for (int d = tid; d < DS_BINS; d += DS_THREADS) table[(size_t)d * G + b] = s_cnt[d];
         grid.sync();
 
-        // ---- (b1) global start of this CTA's run of every digit: digit totals + counts of the CTAs before this one
-        {
-            constexpr int ROWS = DS_BINS / DS_WARPS;  // digit rows per warp
-            for (int r = 0; r < ROWS; ++r) {
-                const int d = warp * ROWS + r;
-                const int32_t *row = table + (size_t)d * G;
-                int tot = 0, pre = 0;
-                for (int c = lane; c < G; c += 32) {
-                    const int v = row[c];
-                    tot += v;
-                    pre += c < b ? v : 0;
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    tot += __shfl_xor_sync(0xffffffffu, tot, o);
-                    pre += __shfl_xor_sync(0xffffffffu, pre, o);
-                }
-                if (lane == 0) {
-                    s_tcnt[d] = tot;
-                    s_run[d] = pre;
-                }
+        // ---- (a2) exclusive scan of every digit row over the CTAs, in place (one warp per row, rows spread over the
+        // grid: every table entry is touched once -- letting each CTA sum the rows itself costs O(G^2) loads and was
+        // measured to be more than half of all instructions of the kernel), digit totals
+        for (int row = b * DS_WARPS + warp; row < DS_BINS; row += G * DS_WARPS) {
+            int32_t *r = table + (size_t)row * G;
+            int carry = 0;
+            for (int x = 0; x < G; x += 32) {
+                const int v = (x + lane < G) ? r[x + lane] : 0;
+                const int incl = ds_warp_incl_scan(v, lane);
+                if (x + lane < G) r[x + lane] = carry + incl - v;
+                carry += __shfl_sync(0xffffffffu, incl, 31);
             }
-            __syncthreads();
+            if (lane == 0) digit_tot[row] = carry;
+        }
+        grid.sync();
+
+        // ---- (b1) global start of this CTA's run of every digit = digits before it + this digit in the CTAs before it
+        {
             int total;
-            const int ex = ds_bins_excl_scan(tid < DS_BINS ? s_tcnt[tid] : 0, &total, s_w);
-            if (tid < DS_BINS) s_run[tid] += ex;
+            const int ex = ds_bins_excl_scan(tid < DS_BINS ? digit_tot[tid] : 0, &total, s_w);
+            if (tid < DS_BINS) s_run[tid] = ex + table[(size_t)tid * G + b];
             if (pass == 0) {
                 if (b == 0 && tid == 0) *nvis_out = total;
                 n = total;  // later passes (and their slices) only see the visible Gaussians
@@ -259,8 +256,8 @@ static int ds_max_grid(int device) {
 
 extern "C" size_t b2s_bin_depth_workspace_bytes(int N) {
     size_t n = (size_t)(N > 0 ? N : 1);
-    // kA, vA, kB (+16 bytes each for vector loads at the slice ends) + table [BINS][G <= DS_MAX_GRID]
-    return 3 * ds_align256(n * 4 + 16) + ds_align256((size_t)DS_BINS * DS_MAX_GRID * 4) + 1024;
+    // kA, vA, kB (+16 bytes each for vector loads at the slice ends) + table [BINS][G <= DS_MAX_GRID] + digit totals
+    return 3 * ds_align256(n * 4 + 16) + ds_align256((size_t)DS_BINS * DS_MAX_GRID * 4) + ds_align256(DS_BINS * 4) + 1024;
 }
 
 extern "C" int b2s_bin_sort_depth(const uint32_t *sort_keys, int N, int32_t *order, int32_t *n_vis,
@@ -283,10 +280,11 @@ extern "C" int b2s_bin_sort_depth(const uint32_t *sort_keys, int N, int32_t *ord
     uint32_t *kA = (uint32_t *)w; w += n4;
     uint32_t *vA = (uint32_t *)w; w += n4;
     uint32_t *kB = (uint32_t *)w; w += n4;
-    int32_t *table = (int32_t *)w;
+    int32_t *table = (int32_t *)w; w += ds_align256((size_t)DS_BINS * DS_MAX_GRID * 4);
+    int32_t *digit_tot = (int32_t *)w;
     uint32_t *vB = (uint32_t *)order;
     void *args[] = {(void *)&sort_keys, (void *)&N, (void *)&kA, (void *)&vA, (void *)&kB, (void *)&vB, (void *)&table,
-                    (void *)&n_vis};
+                    (void *)&digit_tot, (void *)&n_vis};
     cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_depth_sort_coop, dim3(G), dim3(DS_THREADS), args,
                                                 DS_SMEM, st);
     if (e != cudaSuccess) {

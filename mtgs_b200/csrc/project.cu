@@ -117,7 +117,6 @@ k_project_fwd(const float *__restrict__ means, const float *__restrict__ quats, 
     int32_t radius_i = 0;
     int32_t ntiles = 0;
     int2 rect = make_int2(0, 0);  // (x0 | x1 << 16, y0 | y1 << 16) in tiles, max exclusive
-    int rx0 = 0, rx1 = 0, ry0 = 0, ry1 = 0;
     int tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0;  // tight rectangle
     float op = 0.f;                          // opacity * compensation
     float mx = 0.f, my = 0.f, ca = 0.f, cb = 0.f, cc = 0.f, comp = 1.f;
@@ -178,7 +177,6 @@ k_project_fwd(const float *__restrict__ means, const float *__restrict__ quats, 
                 int y1 = fy1 <= 0.f ? 0 : (fy1 >= (float)tile_h ? tile_h : (int)fy1);
                 ntiles = (y1 - y0) * (x1 - x0);
                 rect = make_int2(x0 | (x1 << 16), y0 | (y1 << 16));
-                rx0 = x0; rx1 = x1; ry0 = y0; ry1 = y1;
                 // ---- tight rectangle for the blend's own tile lists: tiles whose pixel centres the footprint
                 // {alpha >= 1/255} = {sigma <= ln(255 opacity)} can reach, intersected with upstream's 3-sigma
                 // rectangle.  Not an upstream output (info["tiles_per_gauss"] / flatten_ids stay upstream's): it only
@@ -209,20 +207,16 @@ k_project_fwd(const float *__restrict__ means, const float *__restrict__ quats, 
         }
     }
     const int2 trect = make_int2(tx0 | (tx1 << 16), ty0 | (ty1 << 16));
-    // ---- list sizes of both tile-list builds (tilelists.cu): upstream's rectangles [0..3], tight rectangles [4..7],
-    // visible Gaussians [8]; one integer warp reduction (redux.sync) per value, 9 atomics per CTA
+    // ---- list sizes of the blend's tile lists (tilelists.cu) over the tight rectangles + the number of visible
+    // Gaussians: one integer warp reduction (redux.sync) per value, at most 5 atomics per CTA
     {
         int v[B2S_N_TOTALS];
-        const int h = ry1 - ry0, w = rx1 - rx0, th_ = ty1 - ty0, tw_ = tx1 - tx0;
-        v[0] = valid ? ntiles : 0;
-        v[1] = valid ? h : 0;
-        v[2] = (valid && h > 0) ? ((ry1 - 1) >> rg_shift) - (ry0 >> rg_shift) + 1 : 0;
-        v[3] = (valid && w > 0) ? h * (((rx1 - 1) >> cg_shift) - (rx0 >> cg_shift) + 1) : 0;
-        v[4] = valid ? th_ * tw_ : 0;
-        v[5] = valid ? th_ : 0;
-        v[6] = (valid && th_ > 0) ? ((ty1 - 1) >> rg_shift) - (ty0 >> rg_shift) + 1 : 0;
-        v[7] = (valid && tw_ > 0) ? th_ * (((tx1 - 1) >> cg_shift) - (tx0 >> cg_shift) + 1) : 0;
-        v[8] = (valid && radius_i > 0) ? 1 : 0;
+        const int th_ = ty1 - ty0, tw_ = tx1 - tx0;
+        v[0] = valid ? th_ * tw_ : 0;
+        v[1] = valid ? th_ : 0;
+        v[2] = (valid && th_ > 0) ? ((ty1 - 1) >> rg_shift) - (ty0 >> rg_shift) + 1 : 0;
+        v[3] = (valid && tw_ > 0) ? th_ * (((tx1 - 1) >> cg_shift) - (tx0 >> cg_shift) + 1) : 0;
+        v[4] = (valid && radius_i > 0) ? 1 : 0;
 #pragma unroll
         for (int k = 0; k < B2S_N_TOTALS; ++k) {
             const int sum = __reduce_add_sync(0xffffffffu, v[k]);
@@ -274,6 +268,44 @@ k_project_fwd(const float *__restrict__ means, const float *__restrict__ quats, 
 #pragma unroll
         for (int k = 0; k < CDIM / 4; ++k) dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+}
+
+// List sizes of a tile-list build over arbitrary rectangles (used for upstream's lists, which are only built when a
+// caller reads info["flatten_ids"] / ["isect_offsets"] / ["isect_ids"]): totals = {M, S, E1, E3, n with tiles}.
+__global__ void __launch_bounds__(256)
+k_rect_totals(const int2 *__restrict__ rects, int N, int rg_shift, int cg_shift, unsigned long long *__restrict__ totals) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    long long v[5] = {0, 0, 0, 0, 0};
+    if (g < N) {
+        const int2 rc = rects[g];
+        const int x0 = rc.x & 0xffff, x1 = (rc.x >> 16) & 0xffff, y0 = rc.y & 0xffff, y1 = (rc.y >> 16) & 0xffff;
+        const int h = max(0, y1 - y0), w = max(0, x1 - x0);
+        v[0] = (long long)h * w;
+        v[1] = h;
+        v[2] = h > 0 ? ((y1 - 1) >> rg_shift) - (y0 >> rg_shift) + 1 : 0;
+        v[3] = w > 0 ? (long long)h * (((x1 - 1) >> cg_shift) - (x0 >> cg_shift) + 1) : 0;
+        v[4] = (h > 0 && w > 0) ? 1 : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        if ((threadIdx.x & 31) == 0 && v[k] != 0) atomicAdd(totals + k, (unsigned long long)v[k]);
+    }
+}
+
+extern "C" int b2s_bin_rect_totals(const int32_t *rects, int N, int tile_w, int tile_h, int64_t *totals,
+                                   b2s_stream_t stream) {
+    if (N < 0 || totals == nullptr) return B2S_ERR_ARG;
+    int rg_shift = 0, cg_shift = 0;
+    if (b2s_tl_shifts(tile_w, tile_h, &rg_shift, &cg_shift) != B2S_OK) return B2S_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(totals, 0, 5 * sizeof(int64_t), st);
+    if (N == 0) return B2S_OK;
+    k_rect_totals<<<b2s_div_up(N, 256), 256, 0, st>>>((const int2 *)rects, N, rg_shift, cg_shift,
+                                                     (unsigned long long *)totals);
+    B2S_LAUNCH_CHECK();
+    return B2S_OK;
 }
 
 // --------------------------------------------------------------------------------------------

@@ -115,7 +115,7 @@ class _Project(torch.autograd.Function):
         keys = torch.empty(N, dtype=torch.int32, device=dev)
         rects = torch.empty(N, 2, dtype=torch.int32, device=dev)
         tight = torch.empty(N, 2, dtype=torch.int32, device=dev)
-        totals = torch.zeros(9, dtype=torch.int64, device=dev)
+        totals = torch.zeros(5, dtype=torch.int64, device=dev)
         # accumulation buffers of the blend backward (v_xyabs | v_geo | v_colpack), zero-filled by the kernel
         arena = torch.empty(N * (8 + cdim) if want_arena else 0, dtype=torch.float32, device=dev)
         with _timed("project_fwd"):
@@ -256,7 +256,7 @@ def _sort_and_read_totals(keys: Tensor, totals: Tensor):
     N = keys.shape[0]
     host = _PINNED_TOTALS.get(dev.index)
     if host is None:
-        host = _PINNED_TOTALS[dev.index] = torch.zeros(9, dtype=torch.int64).pin_memory()
+        host = _PINNED_TOTALS[dev.index] = torch.zeros(5, dtype=torch.int64).pin_memory()
     host.copy_(totals, non_blocking=True)
     ev = torch.cuda.Event()
     ev.record()
@@ -269,8 +269,6 @@ def _sort_and_read_totals(keys: Tensor, totals: Tensor):
                    "b2s_bin_sort_depth")
     ev.synchronize()
     tot = [int(v) for v in host.tolist()]
-    if tot[0] >= 2 ** 31:
-        raise RuntimeError(f"{tot[0]} tile intersections exceed the int32 offset range (same limit as upstream)")
     return order, n_vis, tot
 
 
@@ -325,8 +323,7 @@ def _rasterize_one(means, quats, scales, opacities, colors, viewmat, K, width, h
         float(near_plane), float(far_plane), float(radius_clip), calc_comp, with_depth, cdim, want_grad)
     order, n_vis, tot = _sort_and_read_totals(keys, totals)
     # the lists the blend walks: tight rectangles (the exact per-tile test runs lazily while the blend stages a batch)
-    walk_ids, walk_offsets = _tile_lists(tight, order, n_vis, (tot[4], tot[5], tot[6], tot[7], tot[8]), tile_w, tile_h,
-                                         width, height, True)
+    walk_ids, walk_offsets = _tile_lists(tight, order, n_vis, tuple(tot), tile_w, tile_h, width, height, True)
     render, alpha, last_ids = _Blend.apply(means2d, geo, colpack, walk_offsets, walk_ids, arena, width, height,
                                            tile_w, tile_h, cdim, d_out, ed, bool(absgrad))
     # keys with a leading underscore are not part of upstream's info dict (bench.py reads them for K_pairs)
@@ -337,8 +334,14 @@ def _rasterize_one(means, quats, scales, opacities, colors, viewmat, K, width, h
     def upstream_lists(_key):
         """upstream's flatten_ids / isect_offsets / isect_ids, on demand (bit-identical to the 64-bit sort)."""
         with torch.cuda.device(rects.device):
-            flat, offs = _tile_lists(rects, order, n_vis, (tot[0], tot[1], tot[2], tot[3], tot[8]), tile_w, tile_h, width,
-                                     height, False)
+            lib = _lib.load()
+            up = torch.empty(5, dtype=torch.int64, device=rects.device)
+            _lib.check(lib.b2s_bin_rect_totals(_ptr(rects), N, tile_w, tile_h, _ptr(up), _stream()), "b2s_bin_rect_totals")
+            sizes = [int(v) for v in up.tolist()]
+            if sizes[0] >= 2 ** 31:
+                raise RuntimeError(f"{sizes[0]} tile intersections exceed the int32 offset range (same limit as upstream)")
+            sizes[4] = tot[4]  # the depth order holds every visible Gaussian
+            flat, offs = _tile_lists(rects, order, n_vis, tuple(sizes), tile_w, tile_h, width, height, False)
             return dict(flatten_ids=flat, isect_offsets=offs.view(1, tile_h, tile_w),
                         isect_ids=_isect_ids(offs, flat, depths))
 
