@@ -264,6 +264,8 @@ def main():
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="multi-GPU gradient exchange: fused into the projection backward over peer memory "
                          "(default) or an NCCL all-reduce after the backward (the baseline it replaces)")
+    ap.add_argument("--bwd-px", type=int, default=0, choices=[0, 4, 8],
+                    help="pixels per thread of the blend backward (0 = library default; tuning only)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -313,6 +315,7 @@ def main():
     from mtgs_b200.parallel import GradExchange, SharedGradArena
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback in the product path)"
+    rendering.BWD_PX = args.bwd_px
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
@@ -455,10 +458,25 @@ def main():
     dbuf = [{k: torch.empty_like(params[k].detach()) for k in names} for _ in range(2)]
     copied = [torch.cuda.Event(), torch.cuda.Event()]
 
+    # N > 1: the Gaussians are replicated, so every rank uploads only ITS 1/world slice of the host buffers and the
+    # ranks all-gather the slices over NVLink (NCCL) -- one host does not push world x 112 MB per step over its PCIe
+    # links any more (round 1: e2e efficiency 0.42 at 8 GPUs).  Rows are padded to a multiple of world.
+    if world > 1:
+        rows = (N + world - 1) // world
+        lo, hi = rank * rows, min(N, (rank + 1) * rows)
+        shard = [{k: torch.empty((rows,) + tuple(params[k].shape[1:]), device=dev) for k in names} for _ in range(2)]
+        gath = [{k: torch.empty((rows * world,) + tuple(params[k].shape[1:]), device=dev) for k in names} for _ in range(2)]
+
     def issue_copy(j):
         with torch.cuda.stream(copy_stream):
-            for k in names:
-                dbuf[j][k].copy_(host[k], non_blocking=True)
+            if world > 1:
+                for k in names:
+                    shard[j][k][: hi - lo].copy_(host[k][lo:hi], non_blocking=True)
+                    dist.all_gather_into_tensor(gath[j][k], shard[j][k])
+                    dbuf[j][k] = gath[j][k][:N]
+            else:
+                for k in names:
+                    dbuf[j][k].copy_(host[k], non_blocking=True)
             copied[j].record(copy_stream)
 
     def e2e_step(i):
@@ -496,10 +514,11 @@ def main():
     if dist is not None:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_ms = float(t2.item()) / e2e_steps
-    h2d = sum(host[k].numel() * 4 for k in names)
+    h2d = sum(host[k].numel() * 4 for k in names) // world
     e2e = {"value": N * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
-           "overlap": "H2D of step i+1 runs on a copy stream during step i (double buffer); one 112 MB copy is "
-                      "issued and completed per timed step",
+           "overlap": "H2D of step i+1 runs on a copy stream during step i (double buffer); one copy is issued and "
+                      "completed per timed step" + ("" if world == 1 else f"; every rank uploads 1/{world} of the "
+                      "replicated inputs and the ranks all-gather the slices over NVLink (bytes are per rank)"),
            "ms_per_step": e2e_ms, "steps": e2e_steps}
 
     if rank != 0:

@@ -144,6 +144,9 @@ int b2s_bin_rect_totals(const int32_t *rects, int N, int tile_w, int tile_h, int
 size_t b2s_bin_depth_workspace_bytes(int N);
 int b2s_bin_sort_depth(const uint32_t *sort_keys, int N, int32_t *order, int32_t *n_vis, void *workspace,
                        size_t workspace_bytes, b2s_stream_t stream);
+/* diagnostic: as b2s_bin_sort_depth, plus 13 %globaltimer stamps of the kernel's phases (device uint64[13]) */
+int b2s_debug_sort_depth_phases(const uint32_t *sort_keys, int N, int32_t *order, int32_t *n_vis, void *workspace,
+                                size_t workspace_bytes, unsigned long long *phase_ns, b2s_stream_t stream);
 size_t b2s_bin_tiles_workspace_bytes(const long long *totals_host, int tile_w, int tile_h);
 int b2s_bin_tiles(const int32_t *rects, const int32_t *order, const int32_t *n_vis,
                   const long long *totals_host, int N, int tile_size, int tile_w, int tile_h, int W, int H,
@@ -173,7 +176,8 @@ int b2s_blend_fwd(const float *means2d, const float *geo, const float *colpack,
 int b2s_blend_bwd(const int32_t *tile_offsets, const float *records, int W, int H, int tile_w, int tile_h,
                   int cdim, int d_out, int expected_depth, const float *render, const float *alpha,
                   const int32_t *last_ids, const float *v_render, const float *v_alpha, float *v_xyabs,
-                  float *v_geo, float *v_colpack, b2s_stream_t stream);
+                  float *v_geo, float *v_colpack, int px_per_thread /* 0 = default; 4 or 8 (tuning / tests) */,
+                  b2s_stream_t stream);
 
 /* ---- spherical harmonics (upstream compute_sh fwd / bwd; A.6) ----
  * dirs [N,3], coeffs [N,K,3], masks (uint8, may be NULL), degree in 0..4 with (degree+1)^2 <= K. */

@@ -32,12 +32,13 @@ SIGNATURES = {
     "b2s_bin_rect_totals": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "b2s_bin_depth_workspace_bytes": (_sz, [_i]),
     "b2s_bin_sort_depth": (_i, [_vp, _i, _vp, _vp, _vp, _sz, _vp]),
+    "b2s_debug_sort_depth_phases": (_i, [_vp, _i, _vp, _vp, _vp, _sz, _vp, _vp]),
     "b2s_bin_tiles_workspace_bytes": (_sz, [C.POINTER(_ll), _i, _i]),
     "b2s_bin_tiles": (_i, [_vp] * 3 + [C.POINTER(_ll)] + [_i] * 6 + [_vp, _vp, _i] + [_vp] * 3 + [_sz, _vp]),
     "b2s_bin_isect_ids": (_i, [_vp, _i, _vp, _vp, _ll, _vp, _vp]),
     "b2s_blend_record_bytes": (_sz, [_ll, _i, _i]),
     "b2s_blend_fwd": (_i, [_vp] * 5 + [_i] * 7 + [_vp] * 4 + [_vp]),
-    "b2s_blend_bwd": (_i, [_vp] * 2 + [_i] * 7 + [_vp] * 8 + [_vp]),
+    "b2s_blend_bwd": (_i, [_vp] * 2 + [_i] * 7 + [_vp] * 8 + [_i, _vp]),
     "b2s_ssim_fwd": (_i, [_vp] * 3 + [_ll, _ll] + [_i] * 4 + [_vp, _i, _f, _f] + [_vp] * 5 + [_vp]),
     "b2s_ssim_bwd": (_i, [_vp] * 6 + [_i] * 4 + [_vp, _i, _vp] + [_vp]),
     "b2s_masked_l1_fwd": (_i, [_vp] * 3 + [_ll, _i, _i, _f, _vp, _vp]),

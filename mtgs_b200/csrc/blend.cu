@@ -32,6 +32,9 @@
 
 constexpr int BL_THREADS = 128;
 constexpr int BL_BATCH = 128;  // list entries per walk-record block
+#ifndef B2S_BWD_PX
+#define B2S_BWD_PX 8  // default pixels per thread of the backward (both variants are built)
+#endif
 
 // float4s per walk-record block: q[128] = (mx, my, A, B), c[128] = (C, opacity, Gaussian id bits, 0), col[128][CDIM/4],
 // then one header float4 whose .x holds the number of entries of the block (as int bits)
@@ -242,7 +245,7 @@ k_blend_fwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
 //   v[8..] = v_colour.  (signs and the factors 1/2 are applied once per Gaussian in the flush)
 //   al = alpha (0 if masked), g = e^-sigma where the alpha clamp is inactive (else 0), ca/cb/cc = raw conic.
 template <int CDIM>
-__device__ __forceinline__ void pair_grad(float2 (&v)[16], float2 &T, float2 (&buf)[CDIM], const float2 (&vrc)[CDIM],
+__device__ __forceinline__ void pair_grad(float2 (&v)[16], float2 &T, float2 &Bv, const float2 (&vrc)[CDIM],
                                           const float2 Tfvra, const float (&col)[CDIM], const float ca, const float cb,
                                           const float cc, const float opac, const float dx, const float2 dy,
                                           const float2 al, const float2 g) {
@@ -250,17 +253,19 @@ __device__ __forceinline__ void pair_grad(float2 (&v)[16], float2 &T, float2 (&b
     const float2 ra = make_float2(rcp_approx(om.x), rcp_approx(om.y));  // alpha <= 0.999: well conditioned
     T = mul2(T, ra);                                                     // transmittance in front of this Gaussian
     const float2 fac = mul2(al, T);
-    // buf[] holds R = (colour accumulated behind this Gaussian) / (transmittance behind it).  Upstream's
-    // (c T - S ra) with S the un-normalised sum equals T (c - R); R is updated as a convex combination
-    // R <- R + alpha (c - R), which needs no division and one multiply less per channel.
-    float2 acc = make_float2(0.f, 0.f);
+    // Upstream's sum_k (c_k T - S_k ra) v_out_k, with S the un-normalised colour accumulated behind this Gaussian,
+    // equals T sum_k (c_k - R_k) v_out_k where R = S / (transmittance behind).  R follows the convex update
+    // R <- R + alpha (c - R), and only its projection Bv = <R, v_out> is ever needed, which follows the SAME update:
+    // Bv <- Bv + alpha (<c, v_out> - Bv).  One scalar per pixel instead of CDIM, 2 + CDIM ops instead of 3 CDIM.
+    float2 cv = mul2(bc2(col[0]), vrc[0]);
+    v[8] = fma2(fac, vrc[0], v[8]);
 #pragma unroll
-    for (int k = 0; k < CDIM; ++k) {
-        const float2 d = add2(bc2(col[k]), neg2(buf[k]));
+    for (int k = 1; k < CDIM; ++k) {
+        cv = fma2(bc2(col[k]), vrc[k], cv);
         v[8 + k] = fma2(fac, vrc[k], v[8 + k]);
-        acc = fma2(d, vrc[k], acc);
-        buf[k] = fma2(al, d, buf[k]);
     }
+    const float2 acc = add2(cv, neg2(Bv));
+    Bv = fma2(al, acc, Bv);
     const float2 va = fma2(T, acc, mul2(Tfvra, ra));  // v_alpha
     v[7] = fma2(g, va, v[7]);
     const float2 vs = mul2(mul2(bc2(opac), g), va);   // -v_sigma
@@ -339,15 +344,16 @@ __device__ __forceinline__ void load_pixel_cotangent(size_t pid, const float *__
     }
 }
 
-// 64 threads per tile, 4 pixels per thread (same column, 4 adjacent rows) = 2 packed pixel pairs.
-template <int CDIM, int DOUT, bool ED>
-__global__ void __launch_bounds__(64, CDIM == 4 ? 9 : 7)
+// PX pixels per thread (same column, PX adjacent rows) = PX / 2 packed pixel pairs; 256 / PX threads per tile.
+// PX = 8: ONE warp per tile -- one butterfly and no cross-warp sum per (tile, Gaussian); PX = 4: two warps.
+template <int CDIM, int DOUT, bool ED, int PX>
+__global__ void __launch_bounds__(256 / PX, PX == 8 ? (CDIM == 4 ? 14 : 10) : (CDIM == 4 ? 10 : 7))
 k_blend_bwd(const int32_t *__restrict__ offsets /* [tiles + 1] */, const float4 *__restrict__ records, int W, int H,
             int tile_w, const float *__restrict__ render, const float *__restrict__ alpha_in,
             const int32_t *__restrict__ last_ids, const float *__restrict__ v_render,
             const float *__restrict__ v_alpha, float *__restrict__ v_xyabs, float *__restrict__ v_geo,
             float *__restrict__ v_colpack) {
-    constexpr int PX = 4, THREADS = 64, WARPS = 2, NP = PX / 2;
+    constexpr int THREADS = 256 / PX, WARPS = THREADS / 32, NP = PX / 2;
     constexpr int CQ = CDIM / 4;
     constexpr int NV = 8 + CDIM;   // partial sums per Gaussian
     constexpr int NQUAD = 2 + CQ;  // float4 groups flushed per Gaussian
@@ -357,6 +363,7 @@ k_blend_bwd(const int32_t *__restrict__ offsets /* [tiles + 1] */, const float4 
     __shared__ __align__(16) float s_acc[WARPS][FL][NV];
     __shared__ __align__(8) unsigned long long s_bar[2];
     __shared__ int s_max[WARPS];
+    static_assert(PX == 4 || PX == 8, "pixels travel in pairs; 4 or 8 per thread");
 
     const int tile = blockIdx.x;
     const int ti = tile / tile_w, tj = tile - ti * tile_w;
@@ -367,7 +374,7 @@ k_blend_bwd(const int32_t *__restrict__ offsets /* [tiles + 1] */, const float4 
     const int start = offsets[tile], end = offsets[tile + 1];
 
     float2 T[NP], Tfvra[NP], npy[NP];
-    float2 vrc[NP][CDIM], buf[NP][CDIM];
+    float2 vrc[NP][CDIM], Bv[NP];
     int bin[PX];
     int maxbin = -1;
 #pragma unroll
@@ -386,13 +393,13 @@ k_blend_bwd(const int32_t *__restrict__ offsets /* [tiles + 1] */, const float4 
         maxbin = max(maxbin, bin[j]);
         const float npyj = -((float)(ybase + j) + 0.5f);
         if (j & 1) {
-            T[j / 2].y = Tj; Tfvra[j / 2].y = Tfj * vraj; npy[j / 2].y = npyj;
+            T[j / 2].y = Tj; Tfvra[j / 2].y = Tfj * vraj; npy[j / 2].y = npyj; Bv[j / 2].y = 0.f;
 #pragma unroll
-            for (int k = 0; k < CDIM; ++k) { vrc[j / 2][k].y = vrcj[k]; buf[j / 2][k].y = 0.f; }
+            for (int k = 0; k < CDIM; ++k) vrc[j / 2][k].y = vrcj[k];
         } else {
-            T[j / 2].x = Tj; Tfvra[j / 2].x = Tfj * vraj; npy[j / 2].x = npyj;
+            T[j / 2].x = Tj; Tfvra[j / 2].x = Tfj * vraj; npy[j / 2].x = npyj; Bv[j / 2].x = 0.f;
 #pragma unroll
-            for (int k = 0; k < CDIM; ++k) { vrc[j / 2][k].x = vrcj[k]; buf[j / 2][k].x = 0.f; }
+            for (int k = 0; k < CDIM; ++k) vrc[j / 2][k].x = vrcj[k];
         }
     }
     // last list index any pixel of this tile blended
@@ -403,7 +410,8 @@ k_blend_bwd(const int32_t *__restrict__ offsets /* [tiles + 1] */, const float4 
         b2s_mbar_init(&s_bar[1], 1);
     }
     __syncthreads();
-    maxbin = max(s_max[0], s_max[1]);
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) maxbin = max(maxbin, s_max[w]);
     const int hi0 = min(end - 1, maxbin);
     if (hi0 < start) return;  // nothing was blended in this tile (CTA-uniform)
     const int nblk = ((hi0 - start) >> 7) + 1;
@@ -466,7 +474,7 @@ k_blend_bwd(const int32_t *__restrict__ offsets /* [tiles + 1] */, const float4 
             const float ca = 2.f * B2S_LN2 * sq.z, cb = B2S_LN2 * sq.w, cc = 2.f * B2S_LN2 * sc.x;
 #pragma unroll
             for (int q = 0; q < NP; ++q)
-                pair_grad<CDIM>(v2, T[q], buf[q], vrc[q], Tfvra[q], col, ca, cb, cc, sc.y, dx, dy[q], al[q], g[q]);
+                pair_grad<CDIM>(v2, T[q], Bv[q], vrc[q], Tfvra[q], col, ca, cb, cc, sc.y, dx, dy[q], al[q], g[q]);
             float v[16];
 #pragma unroll
             for (int k2 = 0; k2 < 16; ++k2) v[k2] = k2 < NV ? v2[k2].x + v2[k2].y : 0.f;
@@ -475,14 +483,17 @@ k_blend_bwd(const int32_t *__restrict__ offsets /* [tiles + 1] */, const float4 
         }
         __syncthreads();
 
-        // flush: item = (slot, quad); sum over the two warps, one 16-byte vector reduction per non-zero quad
+        // flush: item = (slot, quad); sum over the warps, one 16-byte vector reduction per non-zero quad
         const int nitem = (t1 - t0 + 1) * 4;
         for (int item = (int)threadIdx.x; item < nitem; item += THREADS) {
             const int slot = item >> 2, quad = item & 3;
             if (quad < NQUAD) {
                 float4 s = *reinterpret_cast<const float4 *>(&s_acc[0][slot][4 * quad]);
-                const float4 o = *reinterpret_cast<const float4 *>(&s_acc[1][slot][4 * quad]);
-                s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+#pragma unroll
+                for (int w = 1; w < WARPS; ++w) {
+                    const float4 o = *reinterpret_cast<const float4 *>(&s_acc[w][slot][4 * quad]);
+                    s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+                }
                 // undo the accumulation convention of pair_grad: quad 0 = (-v_x, -v_y, |v_x|, |v_y|),
                 // quad 1 = (-2 v_conic_a, -v_conic_b, -2 v_conic_c, v_opacity), quads >= 2 = v_colour
                 if (quad == 0) { s.x = -s.x; s.y = -s.y; }
@@ -517,10 +528,15 @@ static int launch_fwd(const float *means2d, const float *geo, const float *colpa
 template <int CDIM, int DOUT, bool ED>
 static int launch_bwd(const int32_t *offsets, const float *records, int W, int H, int tile_w, int tile_h,
                       const float *render, const float *alpha, const int32_t *last_ids, const float *v_render,
-                      const float *v_alpha, float *v_xyabs, float *v_geo, float *v_colpack, cudaStream_t st) {
-    k_blend_bwd<CDIM, DOUT, ED><<<tile_w * tile_h, 64, 0, st>>>(offsets, (const float4 *)records, W, H, tile_w, render,
-                                                                alpha, last_ids, v_render, v_alpha, v_xyabs, v_geo,
-                                                                v_colpack);
+                      const float *v_alpha, float *v_xyabs, float *v_geo, float *v_colpack, int px, cudaStream_t st) {
+    if (px == 4)
+        k_blend_bwd<CDIM, DOUT, ED, 4><<<tile_w * tile_h, 64, 0, st>>>(offsets, (const float4 *)records, W, H, tile_w,
+                                                                       render, alpha, last_ids, v_render, v_alpha,
+                                                                       v_xyabs, v_geo, v_colpack);
+    else
+        k_blend_bwd<CDIM, DOUT, ED, 8><<<tile_w * tile_h, 32, 0, st>>>(offsets, (const float4 *)records, W, H, tile_w,
+                                                                       render, alpha, last_ids, v_render, v_alpha,
+                                                                       v_xyabs, v_geo, v_colpack);
     B2S_LAUNCH_CHECK();
     return B2S_OK;
 }
@@ -568,10 +584,12 @@ extern "C" int b2s_blend_fwd(const float *means2d, const float *geo, const float
 extern "C" int b2s_blend_bwd(const int32_t *tile_offsets, const float *records, int W, int H, int tile_w, int tile_h,
                              int cdim, int d_out, int expected_depth, const float *render, const float *alpha,
                              const int32_t *last_ids, const float *v_render, const float *v_alpha, float *v_xyabs,
-                             float *v_geo, float *v_colpack, b2s_stream_t stream) {
+                             float *v_geo, float *v_colpack, int px_per_thread, b2s_stream_t stream) {
     if (W <= 0 || H <= 0 || tile_w * 16 < W || tile_h * 16 < H || records == nullptr) return B2S_ERR_ARG;
     if ((uintptr_t)records & 127) return B2S_ERR_ARG;
+    if (px_per_thread != 0 && px_per_thread != 4 && px_per_thread != 8) return B2S_ERR_UNSUPPORTED;
+    const int px = px_per_thread == 0 ? B2S_BWD_PX : px_per_thread;
     cudaStream_t st = (cudaStream_t)stream;
     B2S_DISPATCH(launch_bwd, tile_offsets, records, W, H, tile_w, tile_h, render, alpha, last_ids, v_render, v_alpha,
-                 v_xyabs, v_geo, v_colpack, st);
+                 v_xyabs, v_geo, v_colpack, px, st);
 }

@@ -81,7 +81,7 @@ __device__ __forceinline__ int ds_bins_excl_scan(int v, int *total, int *s_w) {
 __global__ void __launch_bounds__(DS_THREADS, 2)
 k_depth_sort_coop(const uint32_t *__restrict__ keys_in, int N, uint32_t *kA, uint32_t *vA, uint32_t *kB,
                   uint32_t *vB /* == order */, int32_t *table /* [BINS][G] */, int32_t *digit_tot /* [BINS] */,
-                  int32_t *nvis_out) {
+                  int32_t *nvis_out, unsigned long long *phase_ns /* optional diagnostic: [1 + 3 * passes] timestamps */) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned char ds_smem_raw[];
     uint32_t *s_k = reinterpret_cast<uint32_t *>(ds_smem_raw);    // [DS_TILE] keys in digit-major order
@@ -96,6 +96,14 @@ k_depth_sort_coop(const uint32_t *__restrict__ keys_in, int N, uint32_t *kA, uin
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = lanemask_lt();
 
+    auto stamp = [&](int slot) {
+        if (phase_ns != nullptr && b == 0 && tid == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            phase_ns[slot] = t;
+        }
+    };
+    stamp(0);
     int n = N;  // items entering the current pass
     for (int pass = 0; pass < DS_PASSES; ++pass) {
         const int shift = DS_BITS * pass;
@@ -132,6 +140,7 @@ k_depth_sort_coop(const uint32_t *__restrict__ keys_in, int N, uint32_t *kA, uin
         __syncthreads();
         for (int d = tid; d < DS_BINS; d += DS_THREADS) table[(size_t)d * G + b] = s_cnt[d];
         grid.sync();
+        stamp(1 + 3 * pass);
 
         // ---- (a2) exclusive scan of every digit row over the CTAs, in place (one warp per row, rows spread over the
         // grid: every table entry is touched once -- letting each CTA sum the rows itself costs O(G^2) loads and was
@@ -148,6 +157,7 @@ k_depth_sort_coop(const uint32_t *__restrict__ keys_in, int N, uint32_t *kA, uin
             if (lane == 0) digit_tot[row] = carry;
         }
         grid.sync();
+        stamp(2 + 3 * pass);
 
         // ---- (b1) global start of this CTA's run of every digit = digits before it + this digit in the CTAs before it
         {
@@ -234,6 +244,7 @@ k_depth_sort_coop(const uint32_t *__restrict__ keys_in, int N, uint32_t *kA, uin
             __syncthreads();
         }
         if (pass + 1 < DS_PASSES) grid.sync();
+        stamp(3 + 3 * pass);
     }
 }
 
@@ -260,8 +271,24 @@ extern "C" size_t b2s_bin_depth_workspace_bytes(int N) {
     return 3 * ds_align256(n * 4 + 16) + ds_align256((size_t)DS_BINS * DS_MAX_GRID * 4) + ds_align256(DS_BINS * 4) + 1024;
 }
 
+static int ds_launch(const uint32_t *sort_keys, int N, int32_t *order, int32_t *n_vis, void *workspace,
+                     size_t workspace_bytes, unsigned long long *phase_ns, b2s_stream_t stream);
+
 extern "C" int b2s_bin_sort_depth(const uint32_t *sort_keys, int N, int32_t *order, int32_t *n_vis,
                                   void *workspace, size_t workspace_bytes, b2s_stream_t stream) {
+    return ds_launch(sort_keys, N, order, n_vis, workspace, workspace_bytes, nullptr, stream);
+}
+
+// Diagnostic variant (tools/sort_phases.py): CTA 0 also writes 13 %globaltimer stamps (kernel start, then after the
+// histogram barrier, the row-scan barrier and the scatter of each of the 4 passes) to phase_ns (device uint64[13]).
+extern "C" int b2s_debug_sort_depth_phases(const uint32_t *sort_keys, int N, int32_t *order, int32_t *n_vis,
+                                           void *workspace, size_t workspace_bytes, unsigned long long *phase_ns,
+                                           b2s_stream_t stream) {
+    return ds_launch(sort_keys, N, order, n_vis, workspace, workspace_bytes, phase_ns, stream);
+}
+
+static int ds_launch(const uint32_t *sort_keys, int N, int32_t *order, int32_t *n_vis, void *workspace,
+                     size_t workspace_bytes, unsigned long long *phase_ns, b2s_stream_t stream) {
     if (N < 0) return B2S_ERR_ARG;
     if (workspace_bytes < b2s_bin_depth_workspace_bytes(N)) return B2S_ERR_WORKSPACE;
     if (((uintptr_t)sort_keys & 15) || ((uintptr_t)workspace & 15)) return B2S_ERR_ARG;
@@ -284,7 +311,7 @@ extern "C" int b2s_bin_sort_depth(const uint32_t *sort_keys, int N, int32_t *ord
     int32_t *digit_tot = (int32_t *)w;
     uint32_t *vB = (uint32_t *)order;
     void *args[] = {(void *)&sort_keys, (void *)&N, (void *)&kA, (void *)&vA, (void *)&kB, (void *)&vB, (void *)&table,
-                    (void *)&digit_tot, (void *)&n_vis};
+                    (void *)&digit_tot, (void *)&n_vis, (void *)&phase_ns};
     cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_depth_sort_coop, dim3(G), dim3(DS_THREADS), args,
                                                 DS_SMEM, st);
     if (e != cudaSuccess) {

@@ -30,6 +30,8 @@ def _stream():
 # Optional per-stage CUDA-event timing (bench.py sets PROFILE = {} to collect (start, end) event pairs per
 # stage on the launching stream; None = zero overhead).
 PROFILE = None
+# pixels per thread of the blend backward: 0 = the library's default; tools / tests may set 4 or 8
+BWD_PX = 0
 
 
 class _timed:
@@ -237,7 +239,8 @@ class _Blend(torch.autograd.Function):
             with _timed("blend_bwd"):
                 _lib.check(lib.b2s_blend_bwd(_ptr(offsets), _ptr(records), W, H, tile_w, tile_h, cdim, d_out, int(ed),
                                              _ptr(render), _ptr(alpha), _ptr(last_ids), _ptr(v_render), _ptr(v_alpha),
-                                             _ptr(v_xyabs), _ptr(v_geo), _ptr(v_colpack), _stream()), "b2s_blend_bwd")
+                                             _ptr(v_xyabs), _ptr(v_geo), _ptr(v_colpack), BWD_PX, _stream()),
+                           "b2s_blend_bwd")
         if absgrad:
             # upstream: `means2d.absgrad = v_means2d_abs` on the tensor object handed in by the caller
             means2d.absgrad = v_xyabs[:, 2:4].unsqueeze(0)

@@ -205,6 +205,20 @@ def test_walk_lists_are_upstream_lists_minus_dead_pairs(cuda_device, scene):
     assert Mw < M
 
 
+@pytest.mark.parametrize("px", [4, 8])
+def test_backward_variants_agree_with_the_oracle(oracle, cuda_device, px):
+    """Both builds of the blend backward (4 and 8 pixels per thread) against the oracle, CDIM 4 and 8."""
+    from mtgs_b200 import rendering
+    old = rendering.BWD_PX
+    rendering.BWD_PX = px
+    try:
+        for d_in in (3, 6):
+            test_backward_parity(oracle, cuda_device, "street20k", "antialiased", "RGB+ED", d_in)
+            test_backward_parity(oracle, cuda_device, "tiny_ragged", "antialiased", "RGB+ED", d_in)
+    finally:
+        rendering.BWD_PX = old
+
+
 def test_golden_fixture_through_c_abi(cuda_device):
     """Committed fixture (tests/golden/oracle_tiny_golden.npz): no oracle code runs in this test."""
     g = np.load(os.path.join(GOLD, "oracle_tiny_golden.npz"))
