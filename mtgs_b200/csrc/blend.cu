@@ -33,7 +33,7 @@
 constexpr int BL_THREADS = 128;
 constexpr int BL_BATCH = 128;  // list entries per walk-record block
 #ifndef B2S_BWD_PX
-#define B2S_BWD_PX 8  // default pixels per thread of the backward (both variants are built)
+#define B2S_BWD_PX 4  // default pixels per thread of the backward (both variants are built)
 #endif
 
 // float4s per walk-record block: q[128] = (mx, my, A, B), c[128] = (C, opacity, Gaussian id bits, 0), col[128][CDIM/4],

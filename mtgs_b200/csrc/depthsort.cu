@@ -26,11 +26,7 @@
 // Pass 0 reads the projection's keys directly and drops the culled ones (key 0xFFFFFFFF), so the later passes and
 // everything downstream only touch n_vis items; the value payload of pass 0 is the index itself.
 // Integer work on L2-resident data; no tensor cores.
-#include <cooperative_groups.h>
-
 #include "common.cuh"
-
-namespace cg = cooperative_groups;
 
 constexpr int DS_THREADS = 512;
 constexpr int DS_WARPS = DS_THREADS / 32;
@@ -40,7 +36,7 @@ constexpr int DS_BITS = 8;
 constexpr int DS_BINS = 1 << DS_BITS;
 constexpr unsigned DS_MASK = DS_BINS - 1;
 constexpr int DS_PASSES = 4;
-constexpr int DS_MAX_GRID = 1024;
+constexpr int DS_MAX_GRID = 512;   // >= 2 x SM count; rows of the digit table are scanned by one warp (16 loads per lane)
 constexpr unsigned DS_CULLED = 0xFFFFFFFFu;
 // shared memory: reordered keys + values of a sub-tile, per-warp digit counters, per-digit bookkeeping, scan scratch
 constexpr size_t DS_SMEM = (size_t)DS_TILE * 8 + (size_t)DS_WARPS * DS_BINS * 4 + (size_t)DS_BINS * 4 * 4 + 256;
@@ -78,11 +74,28 @@ __device__ __forceinline__ int ds_bins_excl_scan(int v, int *total, int *s_w) {
     return res;
 }
 
+// Grid-wide barrier of the co-resident grid: one release-add per CTA on a counter that only grows, then an acquire
+// spin until the counter reaches `target` (= CTAs x barriers passed so far).  cooperative_groups' grid.sync() was
+// measured at ~5-10 us per barrier for 296 CTAs of 512 threads (tools/sort_phases.py: 11 barriers were most of the
+// kernel); this one needs one L2 atomic and one polled line per CTA.
+__device__ __forceinline__ void ds_grid_barrier(unsigned *counter, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned seen;
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        } while (seen < target);
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(DS_THREADS, 2)
 k_depth_sort_coop(const uint32_t *__restrict__ keys_in, int N, uint32_t *kA, uint32_t *vA, uint32_t *kB,
                   uint32_t *vB /* == order */, int32_t *table /* [BINS][G] */, int32_t *digit_tot /* [BINS] */,
-                  int32_t *nvis_out, unsigned long long *phase_ns /* optional diagnostic: [1 + 3 * passes] timestamps */) {
-    cg::grid_group grid = cg::this_grid();
+                  int32_t *nvis_out, unsigned *barrier /* zeroed before the launch */,
+                  unsigned long long *phase_ns /* optional diagnostic: [1 + 3 * passes] timestamps */) {
+    unsigned n_bar = 0;
     extern __shared__ __align__(16) unsigned char ds_smem_raw[];
     uint32_t *s_k = reinterpret_cast<uint32_t *>(ds_smem_raw);    // [DS_TILE] keys in digit-major order
     uint32_t *s_v = s_k + DS_TILE;                                // [DS_TILE] values
@@ -139,24 +152,33 @@ k_depth_sort_coop(const uint32_t *__restrict__ keys_in, int N, uint32_t *kA, uin
         }
         __syncthreads();
         for (int d = tid; d < DS_BINS; d += DS_THREADS) table[(size_t)d * G + b] = s_cnt[d];
-        grid.sync();
+        ds_grid_barrier(barrier, ++n_bar * gridDim.x);
         stamp(1 + 3 * pass);
 
         // ---- (a2) exclusive scan of every digit row over the CTAs, in place (one warp per row, rows spread over the
         // grid: every table entry is touched once -- letting each CTA sum the rows itself costs O(G^2) loads and was
         // measured to be more than half of all instructions of the kernel), digit totals
-        for (int row = b * DS_WARPS + warp; row < DS_BINS; row += G * DS_WARPS) {
-            int32_t *r = table + (size_t)row * G;
-            int carry = 0;
-            for (int x = 0; x < G; x += 32) {
-                const int v = (x + lane < G) ? r[x + lane] : 0;
-                const int incl = ds_warp_incl_scan(v, lane);
-                if (x + lane < G) r[x + lane] = carry + incl - v;
-                carry += __shfl_sync(0xffffffffu, incl, 31);
+        // rows are dealt round-robin to the CTAs (row r goes to CTA r % G) so that at full grid size every CTA scans
+        // at most one row; the whole row is loaded before the scan starts (independent loads, G <= DS_MAX_GRID = 32 x 32)
+        for (int row = b + warp * G; row < DS_BINS; row += G * DS_WARPS) {
+            {
+                int32_t *r = table + (size_t)row * G;
+                int v[DS_MAX_GRID / 32];
+#pragma unroll
+                for (int j = 0; j < DS_MAX_GRID / 32; ++j) v[j] = (j * 32 + lane < G) ? r[j * 32 + lane] : 0;
+                int carry = 0;
+#pragma unroll
+                for (int j = 0; j < DS_MAX_GRID / 32; ++j) {
+                    if (j * 32 < G) {
+                        const int incl = ds_warp_incl_scan(v[j], lane);
+                        if (j * 32 + lane < G) r[j * 32 + lane] = carry + incl - v[j];
+                        carry += __shfl_sync(0xffffffffu, incl, 31);
+                    }
+                }
+                if (lane == 0) digit_tot[row] = carry;
             }
-            if (lane == 0) digit_tot[row] = carry;
         }
-        grid.sync();
+        ds_grid_barrier(barrier, ++n_bar * gridDim.x);
         stamp(2 + 3 * pass);
 
         // ---- (b1) global start of this CTA's run of every digit = digits before it + this digit in the CTAs before it
@@ -243,7 +265,7 @@ k_depth_sort_coop(const uint32_t *__restrict__ keys_in, int N, uint32_t *kA, uin
             }
             __syncthreads();
         }
-        if (pass + 1 < DS_PASSES) grid.sync();
+        if (pass + 1 < DS_PASSES) ds_grid_barrier(barrier, ++n_bar * gridDim.x);
         stamp(3 + 3 * pass);
     }
 }
@@ -308,10 +330,12 @@ static int ds_launch(const uint32_t *sort_keys, int N, int32_t *order, int32_t *
     uint32_t *vA = (uint32_t *)w; w += n4;
     uint32_t *kB = (uint32_t *)w; w += n4;
     int32_t *table = (int32_t *)w; w += ds_align256((size_t)DS_BINS * DS_MAX_GRID * 4);
-    int32_t *digit_tot = (int32_t *)w;
+    int32_t *digit_tot = (int32_t *)w; w += ds_align256(DS_BINS * 4);
+    unsigned *barrier = (unsigned *)w;
+    cudaMemsetAsync(barrier, 0, sizeof(unsigned), st);
     uint32_t *vB = (uint32_t *)order;
     void *args[] = {(void *)&sort_keys, (void *)&N, (void *)&kA, (void *)&vA, (void *)&kB, (void *)&vB, (void *)&table,
-                    (void *)&digit_tot, (void *)&n_vis, (void *)&phase_ns};
+                    (void *)&digit_tot, (void *)&n_vis, (void *)&barrier, (void *)&phase_ns};
     cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_depth_sort_coop, dim3(G), dim3(DS_THREADS), args,
                                                 DS_SMEM, st);
     if (e != cudaSuccess) {

@@ -88,7 +88,7 @@ __device__ __forceinline__ void covar_cam_rn(const float *R, const float *Rq, fl
 }
 
 template <int CDIM>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 6)
 k_project_fwd(const float *__restrict__ means, const float *__restrict__ quats, const float *__restrict__ scales,
               const float *__restrict__ opacities, const float *__restrict__ colors_in,
               const float *__restrict__ viewmat, const float *__restrict__ K, int N, int W, int H, int tile_w,
@@ -98,17 +98,42 @@ k_project_fwd(const float *__restrict__ means, const float *__restrict__ quats, 
               float *__restrict__ colpack, int32_t *__restrict__ tiles_per_gauss,
               uint32_t *__restrict__ sort_keys, int2 *__restrict__ tile_rects, int2 *__restrict__ tight_rects,
               int rg_shift, int cg_shift, unsigned long long *__restrict__ totals /* [B2S_N_TOTALS], pre-zeroed */,
-              float4 *__restrict__ bwd_arena /* [N * (2 + CDIM / 4)] or null: zero-filled for the blend backward */) {
+              float4 *__restrict__ bwd_arena /* [N * (2 + CDIM / 4)] or null: zero-filled for the blend backward */,
+              int use_tma /* all input arrays 16-byte aligned */) {
+    // The CTA's 256 input rows (means | quats | scales | opacities | colours: contiguous runs of the SoA arrays) are
+    // staged by TMA bulk copies issued by ONE thread onto an mbarrier (cp.async.bulk, SASS UBLKCP): every byte of
+    // the tile is in flight before any thread needs it, instead of each thread waiting for its own strided loads
+    // (long-scoreboard stalls were ~30 % of this kernel's samples).  The camera constants (six divisions) are
+    // computed once per CTA by another warp meanwhile.
     __shared__ int s_tot[B2S_N_TOTALS];
+    __shared__ CamParams s_cam;
+    __shared__ __align__(8) unsigned long long s_bar;
+    extern __shared__ __align__(128) float s_in[];  // [768 means | 1024 quats | 768 scales | 256 opac | 256 d_in colours]
+    float *s_means = s_in, *s_quats = s_in + 768, *s_scales = s_in + 1792, *s_opac = s_in + 2560, *s_cols = s_in + 2816;
+    const int g0 = blockIdx.x * 256;
+    const bool staged = use_tma && g0 + 256 <= N;  // CTA-uniform; the last, partial CTA loads directly
     if (threadIdx.x < B2S_N_TOTALS) s_tot[threadIdx.x] = 0;
+    if (threadIdx.x == 0 && staged) {
+        b2s_mbar_init(&s_bar, 1);
+        b2s_mbar_expect_tx(&s_bar, (unsigned)((11 + d_in) * 1024));
+        b2s_bulk_g2s(s_means, means + (size_t)g0 * 3, 3072, &s_bar);
+        b2s_bulk_g2s(s_quats, quats + (size_t)g0 * 4, 4096, &s_bar);
+        b2s_bulk_g2s(s_scales, scales + (size_t)g0 * 3, 3072, &s_bar);
+        b2s_bulk_g2s(s_opac, opacities + g0, 1024, &s_bar);
+        if (d_in > 0) b2s_bulk_g2s(s_cols, colors_in + (size_t)g0 * d_in, (unsigned)(d_in * 1024), &s_bar);
+    }
+    if (threadIdx.x == 32) load_camera(viewmat, K, W, H, s_cam);
     __syncthreads();
-    const int g_raw = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g_raw = g0 + threadIdx.x;
     const bool valid = g_raw < N;
     const int g = valid ? g_raw : N - 1;  // out-of-range threads recompute the last Gaussian and write nothing
-    CamParams cam;
-    load_camera(viewmat, K, W, H, cam);
+    const CamParams &cam = s_cam;
+    if (staged) b2s_mbar_wait(&s_bar, 0);
+    const int t3 = 3 * threadIdx.x;
 
-    float p0 = means[3 * g], p1 = means[3 * g + 1], p2 = means[3 * g + 2];
+    float p0, p1, p2;
+    if (staged) { p0 = s_means[t3]; p1 = s_means[t3 + 1]; p2 = s_means[t3 + 2]; }
+    else { p0 = means[3 * g]; p1 = means[3 * g + 1]; p2 = means[3 * g + 2]; }
     float pc[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -123,8 +148,11 @@ k_project_fwd(const float *__restrict__ means, const float *__restrict__ quats, 
     float z = pc[2];
     bool ok = !(z < near_plane || z > far_plane);
     if (ok) {
-        const float4 q = reinterpret_cast<const float4 *>(quats)[g];
-        float s0 = scales[3 * g], s1 = scales[3 * g + 1], s2 = scales[3 * g + 2];
+        const float4 q = staged ? reinterpret_cast<const float4 *>(s_quats)[threadIdx.x]
+                                : reinterpret_cast<const float4 *>(quats)[g];
+        float s0, s1, s2;
+        if (staged) { s0 = s_scales[t3]; s1 = s_scales[t3 + 1]; s2 = s_scales[t3 + 2]; }
+        else { s0 = scales[3 * g]; s1 = scales[3 * g + 1]; s2 = scales[3 * g + 2]; }
         float Rq[9], Sigma[9], Sc[9];
         quat_to_rotmat_rn(q.x, q.y, q.z, q.w, Rq);
         covar_cam_rn(cam.R, Rq, s0, s1, s2, Sigma, Sc);
@@ -185,7 +213,7 @@ k_project_fwd(const float *__restrict__ means, const float *__restrict__ quats, 
                 // ellipse differs from the ideal one by a relative ~2^-24 kappa in its extents (kappa = c00 c11 / det,
                 // the cancellation in the inverse), and it evaluates sigma with an fp32 error ~2^-22 (|A|+|B|+|C|) R^2:
                 // both are covered by the slack.  The exact per-tile test follows while the blend stages a batch.
-                op = opacities[g];
+                op = staged ? s_opac[threadIdx.x] : opacities[g];
                 if (calc_comp) op = MUL(op, comp);
                 if (op >= 0.0039f) {  // below 1/255 the Gaussian reaches no pixel (same gate as tile_keep)
                     const float Rb = radius + 16.0f;
@@ -249,7 +277,7 @@ k_project_fwd(const float *__restrict__ means, const float *__restrict__ quats, 
         for (int k = 0; k < CDIM; ++k) cp[k] = 0.f;
 #pragma unroll
         for (int k = 0; k < CDIM; ++k)
-            if (k < d_in) cp[k] = colors_in[(size_t)g * d_in + k];
+            if (k < d_in) cp[k] = staged ? s_cols[threadIdx.x * d_in + k] : colors_in[(size_t)g * d_in + k];
         if (with_depth) {
 #pragma unroll
             for (int k = 0; k < CDIM; ++k)
@@ -343,7 +371,7 @@ __device__ __forceinline__ void mat3_mul_at(const float *A, const float *B, floa
 // one-warp kernel then raises this rank's flag at every peer (exchange.cu, which also holds the reduce +
 // all-gather half).
 template <int CDIM, bool EXCH>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 3)
 k_project_bwd(const float *__restrict__ means, const float *__restrict__ quats, const float *__restrict__ scales,
               const float *__restrict__ opacities, const float *__restrict__ viewmat, const float *__restrict__ K,
               int N, int W, int H, float eps2d, int calc_comp, int d_in, int with_depth,
@@ -351,23 +379,49 @@ k_project_bwd(const float *__restrict__ means, const float *__restrict__ quats, 
               const float *__restrict__ v_means2d, int v_m2d_stride, const float4 *__restrict__ v_geo,
               const float *__restrict__ v_colpack, float *__restrict__ v_means, float4 *__restrict__ v_quats,
               float *__restrict__ v_scales, float *__restrict__ v_opacities, float *__restrict__ v_viewmat,
-              const B2sExchange ex) {
-    int g = blockIdx.x * blockDim.x + threadIdx.x;
+              const B2sExchange ex, int use_tma /* every staged array 16-byte aligned */) {
+    // Inputs of the CTA's 256 rows staged by TMA bulk copies on an mbarrier, camera constants once per CTA (see
+    // k_project_fwd).  Staged: means, quats, scales, geo, the blend's three gradient rows; the 4-byte-per-row arrays
+    // (radii, opacities, compensations) are read directly (one coalesced 128-byte line per warp).
+    __shared__ CamParams s_cam;
+    __shared__ __align__(8) unsigned long long s_bar;
+    extern __shared__ __align__(128) float s_dyn[];
+    // layout (floats): means 768 | quats 1024 | scales 768 | geo 1024 | v_geo 1024 | v_m2d 256 * stride | v_colpack 256 * CDIM
+    float *s_means = s_dyn, *s_quats = s_dyn + 768, *s_scales = s_dyn + 1792, *s_geo = s_dyn + 2560, *s_vgeo = s_dyn + 3584,
+          *s_vm2d = s_dyn + 4608, *s_vcol = s_dyn + 4608 + 256 * v_m2d_stride;
+    const int g0 = blockIdx.x * 256;
+    const bool staged = use_tma && g0 + 256 <= N;  // CTA-uniform
+    if (threadIdx.x == 0 && staged) {
+        b2s_mbar_init(&s_bar, 1);
+        b2s_mbar_expect_tx(&s_bar, (unsigned)((18 + v_m2d_stride + CDIM) * 1024));
+        b2s_bulk_g2s(s_means, means + (size_t)g0 * 3, 3072, &s_bar);
+        b2s_bulk_g2s(s_quats, quats + (size_t)g0 * 4, 4096, &s_bar);
+        b2s_bulk_g2s(s_scales, scales + (size_t)g0 * 3, 3072, &s_bar);
+        b2s_bulk_g2s(s_geo, geo + g0, 4096, &s_bar);
+        b2s_bulk_g2s(s_vgeo, v_geo + g0, 4096, &s_bar);
+        b2s_bulk_g2s(s_vm2d, v_means2d + (size_t)g0 * v_m2d_stride, (unsigned)(v_m2d_stride * 1024), &s_bar);
+        b2s_bulk_g2s(s_vcol, v_colpack + (size_t)g0 * CDIM, CDIM * 1024, &s_bar);
+    }
+    if (threadIdx.x == 32) load_camera(viewmat, K, W, H, s_cam);
+    __syncthreads();
+    int g = g0 + threadIdx.x;
     float vR[9], vt[3];
 #pragma unroll
     for (int k = 0; k < 9; ++k) vR[k] = 0.f;
     vt[0] = vt[1] = vt[2] = 0.f;
     const bool live = g < N && radii[g] > 0;
+    if (staged) b2s_mbar_wait(&s_bar, 0);
+    const int t3 = 3 * threadIdx.x;
     // this Gaussian's gradient row (zeros when it is culled)
     float o_means[3] = {0.f, 0.f, 0.f}, o_scales[3] = {0.f, 0.f, 0.f}, o_opac = 0.f;
     float4 o_quat = make_float4(0.f, 0.f, 0.f, 0.f);
     if (live) {
-        CamParams cam;
-        load_camera(viewmat, K, W, H, cam);
+        const CamParams &cam = s_cam;
         const float *R = cam.R;
-        const float4 cg = geo[g];
-        const float2 gxy = *reinterpret_cast<const float2 *>(v_means2d + (size_t)g * v_m2d_stride);
-        const float4 gge = v_geo[g];
+        const float4 cg = staged ? reinterpret_cast<const float4 *>(s_geo)[threadIdx.x] : geo[g];
+        const float2 gxy = staged ? *reinterpret_cast<const float2 *>(s_vm2d + threadIdx.x * v_m2d_stride)
+                                  : *reinterpret_cast<const float2 *>(v_means2d + (size_t)g * v_m2d_stride);
+        const float4 gge = staged ? reinterpret_cast<const float4 *>(s_vgeo)[threadIdx.x] : v_geo[g];
         float ia = cg.x, ib = cg.y, ic = cg.z;
         // inverse VJP: v_cov2d = -Minv * G * Minv with G = [[ga, gb/2],[gb/2, gc]]
         float ga = gge.x, gb = 0.5f * gge.y, gc = gge.z;
@@ -395,14 +449,19 @@ k_project_bwd(const float *__restrict__ means, const float *__restrict__ quats, 
             o_opac = v_op_eff;
             if (!EXCH) v_opacities[g] = o_opac;
         }
-        float v_depth = with_depth ? v_colpack[(size_t)g * CDIM + d_in] : 0.f;
+        float v_depth = with_depth ? (staged ? s_vcol[threadIdx.x * CDIM + d_in] : v_colpack[(size_t)g * CDIM + d_in]) : 0.f;
 
-        float p[3] = {means[3 * g], means[3 * g + 1], means[3 * g + 2]};
+        float p[3];
+        if (staged) { p[0] = s_means[t3]; p[1] = s_means[t3 + 1]; p[2] = s_means[t3 + 2]; }
+        else { p[0] = means[3 * g]; p[1] = means[3 * g + 1]; p[2] = means[3 * g + 2]; }
         float pc[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) pc[i] = R[i * 3 + 0] * p[0] + R[i * 3 + 1] * p[1] + R[i * 3 + 2] * p[2] + cam.t[i];
-        const float4 q = reinterpret_cast<const float4 *>(quats)[g];
-        float s[3] = {scales[3 * g], scales[3 * g + 1], scales[3 * g + 2]};
+        const float4 q = staged ? reinterpret_cast<const float4 *>(s_quats)[threadIdx.x]
+                                : reinterpret_cast<const float4 *>(quats)[g];
+        float s[3];
+        if (staged) { s[0] = s_scales[t3]; s[1] = s_scales[t3 + 1]; s[2] = s_scales[t3 + 2]; }
+        else { s[0] = scales[3 * g]; s[1] = scales[3 * g + 1]; s[2] = scales[3 * g + 2]; }
         float inv_norm = rsqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
         float qw = q.x * inv_norm, qx = q.y * inv_norm, qy = q.z * inv_norm, qz = q.w * inv_norm;
         float Rq[9];
@@ -526,7 +585,8 @@ k_project_bwd(const float *__restrict__ means, const float *__restrict__ quats, 
         }
     } else {
         // ---- transpose the CTA's rows through shared memory, then 16-byte coalesced stores into the owner's slot
-        extern __shared__ __align__(16) float s_ex[];  // [768 means | 1024 quats | 768 scales | 256 opac | d_col * 256 colours]
+        float *s_ex = s_dyn;  // [768 means | 1024 quats | 768 scales | 256 opac | d_col * 256 colours]
+        __syncthreads();      // every thread has read its staged inputs: the buffer is reused for the output rows
         const int d_col = ex.d_col;
         const int t = threadIdx.x;
         s_ex[3 * t] = o_means[0]; s_ex[3 * t + 1] = o_means[1]; s_ex[3 * t + 2] = o_means[2];
@@ -606,13 +666,16 @@ extern "C" int b2s_project_fwd(const float *means, const float *quats, const flo
     if (N == 0) return B2S_OK;
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(b2s_div_up(N, 256)), block(256);
+    const int use_tma = ((((uintptr_t)means | (uintptr_t)quats | (uintptr_t)scales | (uintptr_t)opacities |
+                           (uintptr_t)colors_in) & 15) == 0) ? 1 : 0;
+    const size_t smem = (size_t)(11 + d_in) * 256 * sizeof(float);
 #define LAUNCH(CD)                                                                                           \
-    k_project_fwd<CD><<<grid, block, 0, st>>>(means, quats, scales, opacities, colors_in, viewmat, K, N, W, H, \
+    k_project_fwd<CD><<<grid, block, smem, st>>>(means, quats, scales, opacities, colors_in, viewmat, K, N, W, H, \
                                               tile_w, tile_h, eps2d, near_plane, far_plane, radius_clip,     \
                                               calc_comp, d_in, with_depth, radii, (float2 *)means2d, depths, \
                                               (float4 *)geo, comps, colpack, tiles_per_gauss, sort_keys, \
                                               (int2 *)tile_rects, (int2 *)tight_rects, rg_shift, cg_shift,  \
-                                              (unsigned long long *)totals, (float4 *)bwd_arena)
+                                              (unsigned long long *)totals, (float4 *)bwd_arena, use_tma)
     if (cdim == 4) LAUNCH(4);
     else LAUNCH(8);
 #undef LAUNCH
@@ -635,12 +698,16 @@ extern "C" int b2s_project_bwd(const float *means, const float *quats, const flo
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(b2s_div_up(N, 256)), block(256);
     B2sExchange none = {};
+    const int use_tma = ((((uintptr_t)means | (uintptr_t)quats | (uintptr_t)scales | (uintptr_t)geo | (uintptr_t)v_geo |
+                           (uintptr_t)v_means2d | (uintptr_t)v_colpack) & 15) == 0) ? 1 : 0;
+    const size_t smem = (size_t)(18 + v_means2d_stride + cdim) * 256 * sizeof(float);
+    if (v_means2d_stride > 8) return B2S_ERR_ARG;
 #define LAUNCH(CD)                                                                                                \
-    k_project_bwd<CD, false><<<grid, block, 0, st>>>(means, quats, scales, opacities, viewmat, K, N, W, H, eps2d,  \
+    k_project_bwd<CD, false><<<grid, block, smem, st>>>(means, quats, scales, opacities, viewmat, K, N, W, H, eps2d,  \
                                                      calc_comp, d_in, with_depth, radii, (const float4 *)geo,     \
                                                      comps, v_means2d, v_means2d_stride, (const float4 *)v_geo,   \
                                                      v_colpack, v_means, (float4 *)v_quats, v_scales, v_opacities, \
-                                                     v_viewmat, none)
+                                                     v_viewmat, none, use_tma)
     if (cdim == 4) LAUNCH(4);
     else LAUNCH(8);
 #undef LAUNCH
@@ -656,13 +723,18 @@ int b2s_launch_project_bwd_exchange(const float *means, const float *quats, cons
                                     const float *v_geo, const float *v_colpack, float *v_viewmat, const B2sExchange &ex,
                                     cudaStream_t st) {
     dim3 grid(b2s_div_up(n_rows, 256)), block(256);
-    const size_t smem = (size_t)(11 + ex.d_col) * 256 * sizeof(float);
+    const int use_tma = ((((uintptr_t)means | (uintptr_t)quats | (uintptr_t)scales | (uintptr_t)geo | (uintptr_t)v_geo |
+                           (uintptr_t)v_means2d | (uintptr_t)v_colpack) & 15) == 0) ? 1 : 0;
+    if (v_means2d_stride > 8) return B2S_ERR_ARG;
+    const size_t smem_in = (size_t)(18 + v_means2d_stride + cdim) * 256 * sizeof(float);
+    const size_t smem_out = (size_t)(11 + ex.d_col) * 256 * sizeof(float);
+    const size_t smem = smem_in > smem_out ? smem_in : smem_out;
 #define LAUNCH(CD)                                                                                               \
     k_project_bwd<CD, true><<<grid, block, smem, st>>>(means, quats, scales, opacities, viewmat, K, n_rows, W, H, \
                                                        eps2d, calc_comp, d_in, with_depth, radii,                \
                                                        (const float4 *)geo, comps, v_means2d, v_means2d_stride,  \
                                                        (const float4 *)v_geo, v_colpack, nullptr, nullptr,       \
-                                                       nullptr, nullptr, v_viewmat, ex)
+                                                       nullptr, nullptr, v_viewmat, ex, use_tma)
     if (cdim == 4) LAUNCH(4);
     else LAUNCH(8);
 #undef LAUNCH
