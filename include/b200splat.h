@@ -73,6 +73,7 @@ int b2s_project_fwd(const float *means, const float *quats, const float *scales,
 /* upstream fully_fused_projection bwd fused with the opacity*compensation and
  * colour/depth un-packing VJPs.  v_means2d[g * v_means2d_stride + {0,1}] (stride 2, or 4 when it aliases
  * the blend's (xy, |xy|) arena), v_geo[g] = (v_conic a,b,c, v_opacity_eff), v_colpack[g][cdim].
+ * v_colors (may be NULL): contiguous [N, d_in] copy of the colour part of v_colpack (zeros for culled rows).
  * v_viewmat (16 floats, pre-zeroed) may be NULL. */
 int b2s_project_bwd(const float *means, const float *quats, const float *scales,
                     const float *opacities, const float *viewmat, const float *K, int N, int W,
@@ -80,7 +81,7 @@ int b2s_project_bwd(const float *means, const float *quats, const float *scales,
                     const int32_t *radii, const float *geo, const float *comps,
                     const float *v_means2d, int v_means2d_stride, const float *v_geo,
                     const float *v_colpack,
-                    float *v_means, float *v_quats, float *v_scales, float *v_opacities,
+                    float *v_means, float *v_quats, float *v_scales, float *v_opacities, float *v_colors,
                     float *v_viewmat, b2s_stream_t stream);
 
 /* ---- multi-GPU: projection backward fused with the exchange of the shared-node gradients ----
@@ -138,6 +139,12 @@ int b2s_project_bwd_exchange(const float *means, const float *quats, const float
  *       tile) pairs that can reach alpha >= 1/255 at a pixel centre of the tile -- the lists the blend kernels walk;
  *       the list is then at most `list length` long.  offsets_with_total != 0: isect_offsets has tile_w * tile_h + 1
  *       entries, the last one = the final list length (so the blend needs no host-side count).
+ *       overflow (device int32, zero-filled by the caller; may be NULL): CAPACITY MODE -- totals_host are then not the
+ *       exact sizes but capacities chosen by the caller (e.g. the previous frame's sizes plus headroom), so that the
+ *       build can be enqueued without waiting for this frame's sizes.  If a level needs more room than provided, the
+ *       word becomes non-zero, every later kernel of the build returns at once (nothing is written out of bounds)
+ *       and the lists are invalid: the caller must rebuild with exact sizes (b2s_blend_fwd takes the same word as
+ *       skip_flag and does nothing when it is set).
  *   (3) b2s_bin_isect_ids  : optional, rebuilds upstream's int64 isect_ids for inspection. */
 int b2s_bin_rect_totals(const int32_t *rects, int N, int tile_w, int tile_h, int64_t *totals /* [5] */,
                         b2s_stream_t stream);
@@ -150,7 +157,7 @@ int b2s_debug_sort_depth_phases(const uint32_t *sort_keys, int N, int32_t *order
 size_t b2s_bin_tiles_workspace_bytes(const long long *totals_host, int tile_w, int tile_h);
 int b2s_bin_tiles(const int32_t *rects, const int32_t *order, const int32_t *n_vis,
                   const long long *totals_host, int N, int tile_size, int tile_w, int tile_h, int W, int H,
-                  const float *means2d, const float *geo, int offsets_with_total,
+                  const float *means2d, const float *geo, int offsets_with_total, int32_t *overflow,
                   int32_t *flatten_ids, int32_t *isect_offsets, void *workspace,
                   size_t workspace_bytes, b2s_stream_t stream);
 int b2s_bin_isect_ids(const int32_t *isect_offsets, int n_tiles, const int32_t *flatten_ids,
@@ -172,7 +179,7 @@ size_t b2s_blend_record_bytes(long long list_capacity, int n_tiles, int cdim);
 int b2s_blend_fwd(const float *means2d, const float *geo, const float *colpack,
                   const int32_t *tile_offsets, const int32_t *tile_ids, int W, int H, int tile_w, int tile_h,
                   int cdim, int d_out, int expected_depth, float *render, float *alpha, int32_t *last_ids,
-                  float *records, b2s_stream_t stream);
+                  float *records, const int32_t *skip_flag /* may be NULL */, b2s_stream_t stream);
 int b2s_blend_bwd(const int32_t *tile_offsets, const float *records, int W, int H, int tile_w, int tile_h,
                   int cdim, int d_out, int expected_depth, const float *render, const float *alpha,
                   const int32_t *last_ids, const float *v_render, const float *v_alpha, float *v_xyabs,

@@ -20,7 +20,7 @@ SIGNATURES = {
     "b2s_error_string": (C.c_char_p, [_i]),
     "b2s_launch_count": (_ll, []),
     "b2s_project_fwd": (_i, [_vp] * 7 + [_i] * 6 + [_f] * 4 + [_i] * 4 + [_vp] * 12 + [_vp]),
-    "b2s_project_bwd": (_i, [_vp] * 6 + [_i] * 3 + [_f] + [_i] * 4 + [_vp] * 4 + [_i] + [_vp] * 7 + [_vp]),
+    "b2s_project_bwd": (_i, [_vp] * 6 + [_i] * 3 + [_f] + [_i] * 4 + [_vp] * 4 + [_i] + [_vp] * 8 + [_vp]),
     "b2s_exchange_shard_rows": (_i, [_i, _i]),
     "b2s_peer_alloc": (_i, [_sz, C.POINTER(C.c_void_p)]),
     "b2s_peer_free": (_i, [_vp]),
@@ -34,10 +34,10 @@ SIGNATURES = {
     "b2s_bin_sort_depth": (_i, [_vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "b2s_debug_sort_depth_phases": (_i, [_vp, _i, _vp, _vp, _vp, _sz, _vp, _vp]),
     "b2s_bin_tiles_workspace_bytes": (_sz, [C.POINTER(_ll), _i, _i]),
-    "b2s_bin_tiles": (_i, [_vp] * 3 + [C.POINTER(_ll)] + [_i] * 6 + [_vp, _vp, _i] + [_vp] * 3 + [_sz, _vp]),
+    "b2s_bin_tiles": (_i, [_vp] * 3 + [C.POINTER(_ll)] + [_i] * 6 + [_vp, _vp, _i, _vp] + [_vp] * 3 + [_sz, _vp]),
     "b2s_bin_isect_ids": (_i, [_vp, _i, _vp, _vp, _ll, _vp, _vp]),
     "b2s_blend_record_bytes": (_sz, [_ll, _i, _i]),
-    "b2s_blend_fwd": (_i, [_vp] * 5 + [_i] * 7 + [_vp] * 4 + [_vp]),
+    "b2s_blend_fwd": (_i, [_vp] * 5 + [_i] * 7 + [_vp] * 5 + [_vp]),
     "b2s_blend_bwd": (_i, [_vp] * 2 + [_i] * 7 + [_vp] * 8 + [_i, _vp]),
     "b2s_ssim_fwd": (_i, [_vp] * 3 + [_ll, _ll] + [_i] * 4 + [_vp, _i, _f, _f] + [_vp] * 5 + [_vp]),
     "b2s_ssim_bwd": (_i, [_vp] * 6 + [_i] * 4 + [_vp, _i, _vp] + [_vp]),

@@ -97,7 +97,9 @@ __global__ void __launch_bounds__(BL_THREADS)
 k_blend_fwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, const float4 *__restrict__ colpack,
             const int32_t *__restrict__ offsets /* [tiles + 1] */, const int32_t *__restrict__ ids, int W, int H,
             int tile_w, float *__restrict__ render, float *__restrict__ alpha_out, int32_t *__restrict__ last_ids,
-            float4 *__restrict__ records /* walk-record blocks for the backward, or null */) {
+            float4 *__restrict__ records /* walk-record blocks for the backward, or null */,
+            const int32_t *__restrict__ skip /* or null: non-zero = the lists are invalid (capacity overflow), do nothing */) {
+    if (skip != nullptr && *skip != 0) return;
     constexpr int CQ = CDIM / 4;
     using BL = BlkLayout<CDIM>;
     __shared__ __align__(128) float4 s_blk[BL::F4];
@@ -518,10 +520,10 @@ k_blend_bwd(const int32_t *__restrict__ offsets /* [tiles + 1] */, const float4 
 template <int CDIM, int DOUT, bool ED>
 static int launch_fwd(const float *means2d, const float *geo, const float *colpack, const int32_t *offsets,
                       const int32_t *ids, int W, int H, int tile_w, int tile_h, float *render, float *alpha,
-                      int32_t *last_ids, float *records, cudaStream_t st) {
+                      int32_t *last_ids, float *records, const int32_t *skip, cudaStream_t st) {
     k_blend_fwd<CDIM, DOUT, ED><<<tile_w * tile_h, BL_THREADS, 0, st>>>(
         (const float2 *)means2d, (const float4 *)geo, (const float4 *)colpack, offsets, ids, W, H, tile_w, render, alpha,
-        last_ids, (float4 *)records);
+        last_ids, (float4 *)records, skip);
     B2S_LAUNCH_CHECK();
     return B2S_OK;
 }
@@ -573,12 +575,12 @@ extern "C" size_t b2s_blend_record_bytes(long long list_capacity, int n_tiles, i
 extern "C" int b2s_blend_fwd(const float *means2d, const float *geo, const float *colpack,
                              const int32_t *tile_offsets, const int32_t *tile_ids, int W, int H, int tile_w, int tile_h,
                              int cdim, int d_out, int expected_depth, float *render, float *alpha, int32_t *last_ids,
-                             float *records, b2s_stream_t stream) {
+                             float *records, const int32_t *skip_flag, b2s_stream_t stream) {
     if (W <= 0 || H <= 0 || tile_w * 16 < W || tile_h * 16 < H) return B2S_ERR_ARG;
     if (records != nullptr && ((uintptr_t)records & 127)) return B2S_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     B2S_DISPATCH(launch_fwd, means2d, geo, colpack, tile_offsets, tile_ids, W, H, tile_w, tile_h, render, alpha, last_ids,
-                 records, st);
+                 records, skip_flag, st);
 }
 
 extern "C" int b2s_blend_bwd(const int32_t *tile_offsets, const float *records, int W, int H, int tile_w, int tile_h,

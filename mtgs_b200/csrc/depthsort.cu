@@ -130,7 +130,7 @@ k_depth_sort_coop(const uint32_t *__restrict__ keys_in, int N, uint32_t *kA, uin
         const int begin = min(n, b * per), end = min(n, begin + per);
 
         // ---- (a) histogram of this CTA's slice
-        for (int d = tid; d < DS_BINS; d += DS_THREADS) s_cnt[d] = 0;
+        for (int d = tid; d < DS_WARPS * DS_BINS; d += DS_THREADS) s_cnt[d] = 0;
         __syncthreads();
         for (int w0 = begin + warp * 128; w0 < end; w0 += DS_THREADS * 4) {  // warp-uniform trip count
             const int i0 = w0 + 4 * lane;
@@ -145,13 +145,20 @@ k_depth_sort_coop(const uint32_t *__restrict__ keys_in, int N, uint32_t *kA, uin
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const bool valid = i0 + j < end && (pass > 0 || k4[j] != DS_CULLED);
-                const int d = valid ? (int)((k4[j] >> shift) & DS_MASK) : DS_BINS;
-                const unsigned peers = __match_any_sync(0xffffffffu, d);
-                if (valid && lane == __ffs(peers) - 1) atomicAdd(&s_cnt[d], __popc(peers));
+                // plain shared atomics on the warp's private counters: a full same-address conflict costs ~32 cycles
+                // per warp instruction, less than grouping the lanes first
+                if (valid) atomicAdd(&s_cnt[warp * DS_BINS + ((k4[j] >> shift) & DS_MASK)], 1);
             }
         }
         __syncthreads();
-        for (int d = tid; d < DS_BINS; d += DS_THREADS) table[(size_t)d * G + b] = s_cnt[d];
+        for (int d = tid; d < DS_BINS; d += DS_THREADS) {
+            int c = 0;
+#pragma unroll
+            for (int w = 0; w < DS_WARPS; ++w) c += s_cnt[w * DS_BINS + d];
+            s_tcnt[d] = c;
+        }
+        __syncthreads();
+        for (int d = tid; d < DS_BINS; d += DS_THREADS) table[(size_t)d * G + b] = s_tcnt[d];
         ds_grid_barrier(barrier, ++n_bar * gridDim.x);
         stamp(1 + 3 * pass);
 
@@ -211,7 +218,16 @@ k_depth_sort_coop(const uint32_t *__restrict__ keys_in, int N, uint32_t *kA, uin
                 const int i = wbase + r * 32 + lane;
                 const bool valid = i < end && (pass > 0 || key[r] != DS_CULLED);
                 const int d = valid ? (int)((key[r] >> shift) & DS_MASK) : DS_BINS;  // invalid lanes: dummy digit
-                const unsigned peers = __match_any_sync(0xffffffffu, d);
+                // lanes holding the same digit: one ballot per digit bit (+1 for validity); match.any takes one
+                // iteration per distinct value, i.e. up to 32 for the random low digits
+                unsigned peers = __ballot_sync(0xffffffffu, valid);
+                if (!valid) peers = ~peers;
+#pragma unroll
+                for (int bit = 0; bit < DS_BITS; ++bit) {
+                    const bool one = (d >> bit) & 1;
+                    const unsigned bal = __ballot_sync(0xffffffffu, one);
+                    peers &= one ? bal : ~bal;
+                }
                 const int leader = __ffs(peers) - 1;
                 int old = 0;
                 // one atomic per (round, digit group); the shuffle below makes the next round wait for it,

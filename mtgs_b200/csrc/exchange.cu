@@ -225,7 +225,7 @@ extern "C" int b2s_project_bwd_exchange(
                              eps2d, calc_comp, d_in, with_depth, cdim, radii + o, geo + 4 * o,
                              comps ? comps + o : nullptr, v_means2d + (size_t)v_means2d_stride * o, v_means2d_stride,
                              v_geo + 4 * o, v_colpack + (size_t)cdim * o, arena + 3 * o, arena + 3 * rows_cap + 4 * o,
-                             arena + 7 * rows_cap + 3 * o, arena + 10 * rows_cap + o, v_viewmat, stream);
+                             arena + 7 * rows_cap + 3 * o, arena + 10 * rows_cap + o, nullptr, v_viewmat, stream);
         if (rc != B2S_OK) return rc;
     }
     if (n_shared > 0 && (phases & 1)) {

@@ -378,8 +378,8 @@ k_project_bwd(const float *__restrict__ means, const float *__restrict__ quats, 
               const int32_t *__restrict__ radii, const float4 *__restrict__ geo, const float *__restrict__ comps,
               const float *__restrict__ v_means2d, int v_m2d_stride, const float4 *__restrict__ v_geo,
               const float *__restrict__ v_colpack, float *__restrict__ v_means, float4 *__restrict__ v_quats,
-              float *__restrict__ v_scales, float *__restrict__ v_opacities, float *__restrict__ v_viewmat,
-              const B2sExchange ex, int use_tma /* every staged array 16-byte aligned */) {
+              float *__restrict__ v_scales, float *__restrict__ v_opacities, float *__restrict__ v_colors_out,
+              float *__restrict__ v_viewmat, const B2sExchange ex, int use_tma /* every staged array 16-byte aligned */) {
     // Inputs of the CTA's 256 rows staged by TMA bulk copies on an mbarrier, camera constants once per CTA (see
     // k_project_fwd).  Staged: means, quats, scales, geo, the blend's three gradient rows; the 4-byte-per-row arrays
     // (radii, opacities, compensations) are read directly (one coalesced 128-byte line per warp).
@@ -575,6 +575,11 @@ k_project_bwd(const float *__restrict__ means, const float *__restrict__ quats, 
                              (vqn[2] - dotp * qy) * inv_norm, (vqn[3] - dotp * qz) * inv_norm);
     }
     if (!EXCH) {
+        if (v_colors_out != nullptr && g < N) {  // contiguous [N, d_in] colour gradient (zeros for culled rows)
+            for (int k = 0; k < d_in; ++k)
+                v_colors_out[(size_t)g * d_in + k] =
+                    live ? (staged ? s_vcol[threadIdx.x * CDIM + k] : v_colpack[(size_t)g * CDIM + k]) : 0.f;
+        }
         if (live) {
             v_quats[g] = o_quat;
         } else if (g < N) {  // culled: define the row (zeros) so callers need no memset pass
@@ -688,8 +693,8 @@ extern "C" int b2s_project_bwd(const float *means, const float *quats, const flo
                                float eps2d, int calc_comp, int d_in, int with_depth, int cdim,
                                const int32_t *radii, const float *geo, const float *comps, const float *v_means2d,
                                int v_means2d_stride, const float *v_geo, const float *v_colpack, float *v_means,
-                               float *v_quats,
-                               float *v_scales, float *v_opacities, float *v_viewmat, b2s_stream_t stream) {
+                               float *v_quats, float *v_scales, float *v_opacities, float *v_colors,
+                               float *v_viewmat, b2s_stream_t stream) {
     if (N < 0) return B2S_ERR_ARG;
     if (cdim != 4 && cdim != 8) return B2S_ERR_UNSUPPORTED;
     if (calc_comp && comps == nullptr) return B2S_ERR_ARG;
@@ -707,7 +712,7 @@ extern "C" int b2s_project_bwd(const float *means, const float *quats, const flo
                                                      calc_comp, d_in, with_depth, radii, (const float4 *)geo,     \
                                                      comps, v_means2d, v_means2d_stride, (const float4 *)v_geo,   \
                                                      v_colpack, v_means, (float4 *)v_quats, v_scales, v_opacities, \
-                                                     v_viewmat, none, use_tma)
+                                                     v_colors, v_viewmat, none, use_tma)
     if (cdim == 4) LAUNCH(4);
     else LAUNCH(8);
 #undef LAUNCH
@@ -734,7 +739,7 @@ int b2s_launch_project_bwd_exchange(const float *means, const float *quats, cons
                                                        eps2d, calc_comp, d_in, with_depth, radii,                \
                                                        (const float4 *)geo, comps, v_means2d, v_means2d_stride,  \
                                                        (const float4 *)v_geo, v_colpack, nullptr, nullptr,       \
-                                                       nullptr, nullptr, v_viewmat, ex, use_tma)
+                                                       nullptr, nullptr, nullptr, v_viewmat, ex, use_tma)
     if (cdim == 4) LAUNCH(4);
     else LAUNCH(8);
 #undef LAUNCH

@@ -40,6 +40,8 @@ struct TlGeom {
     int W, H;                // image size in pixels (exact mode: pixel-centre boxes of the tiles)
     int exact;               // level 4 keeps only (Gaussian, tile) pairs that can reach alpha >= 1/255 (tile_keep)
     int offs_total;          // isect_offsets has tile_w * tile_h + 1 entries; the last one receives the list length
+    int *overflow;           // capacity mode (or null): set when a level needs more room than the caller provided;
+                             // every later kernel of the build then returns at once (no out-of-bounds write)
     int rg_shift, cg_shift;  // tile rows per row group = 1 << rg_shift, tile columns per column group = 1 << cg_shift
     int nrg, ncg;            // number of row groups / column groups (<= 32)
 };
@@ -192,6 +194,7 @@ k_level_count(const TlGeom g, int2 *__restrict__ in, const int32_t *__restrict__
     __shared__ int s_diff[TL_WARPS][33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (blockIdx.x == 0 && threadIdx.x == 0) *ticket = 0u;  // armed for this level's prefix kernel
+    if (g.overflow != nullptr && *g.overflow != 0) return;
     const int c = blockIdx.x;
     int L, begin, end;
     if (!tl_chunk<K>(c, nlists, list_off, chunk_off, n_vis, L, begin, end)) return;  // CTA-uniform
@@ -256,10 +259,11 @@ __global__ void __launch_bounds__(TL_PT)
 k_level_prefix(const TlGeom g, const int32_t *__restrict__ n_vis, int nlists, const int32_t *__restrict__ chunk_off,
                int nch, int32_t *__restrict__ table, int32_t *__restrict__ out_len, int32_t *__restrict__ out_off,
                int32_t *__restrict__ out_chunk_off, int32_t *__restrict__ isect_offsets,
-               unsigned *__restrict__ ticket) {
+               unsigned *__restrict__ ticket, long long cap_out /* entries the output list of this level can hold */) {
     __shared__ int s_w[TL_PT / 32];
     __shared__ unsigned s_last;
     const int tid = threadIdx.x;
+    if (g.overflow != nullptr && *g.overflow != 0) return;
     const int NB = tl_nb<K>(g);
     const int nout = nlists * NB;
     if (K >= 3) {  // short chunk tables: one warp per child list
@@ -347,6 +351,7 @@ k_level_prefix(const TlGeom g, const int32_t *__restrict__ n_vis, int nlists, co
         out_off[nout] = carry_e;
         if (K < 4) out_chunk_off[nout] = carry_c;
         if (K == 4 && g.offs_total) isect_offsets[g.tile_w * g.tile_h] = carry_e;
+        if (g.overflow != nullptr && (long long)carry_e > cap_out) *g.overflow = K;  // the fill of this level has not run yet
     }
 }
 
@@ -360,6 +365,7 @@ k_level_fill(const TlGeom g, const int2 *__restrict__ in, const int32_t *__restr
              const int32_t *__restrict__ out_off, int2 *__restrict__ out2, int32_t *__restrict__ out1) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = lanemask_lt();
+    if (g.overflow != nullptr && *g.overflow != 0) return;
     const int c = blockIdx.x;
     int L, begin, end;
     if (!tl_chunk<K>(c, nlists, list_off, chunk_off, n_vis, L, begin, end)) return;  // CTA-uniform
@@ -406,6 +412,7 @@ struct TlLayout {
     int nb[5];         // children per list at level k
     long long nch[5];  // chunks at level k (upper bound)
     size_t table[5], slice[5], out_len[5], out_off[5], chunk_off[5], out[4], ticket, total;
+    long long cap_out[5];  // entries the output list of level k can hold
 };
 
 // totals = {M, S, E1, E3, n_vis} as written by b2s_bin_sort_depth
@@ -421,6 +428,7 @@ static bool tl_layout(const long long *t, int tile_w, int tile_h, TlGeom &g, TlL
     for (int k = 1; k <= 4; ++k) {
         L.nch[k] = in_items[k] / tl_ch(k) + L.nl[k];
         const size_t nout = (size_t)L.nl[k] * L.nb[k];
+        L.cap_out[k] = out_items[k];
         L.table[k] = o; o += tl_align256((size_t)L.nch[k] * L.nb[k] * 4);
         L.slice[k] = o; o += tl_align256((size_t)L.nch[k] * TL_WARPS * 32 * 4);
         L.out_len[k] = o; o += tl_align256(nout * 4);
@@ -464,7 +472,7 @@ static int tl_run_level(const TlGeom &g, const TlLayout &L, char *w, const int32
     B2S_LAUNCH_CHECK();
     const int nout = nlists * L.nb[K];
     k_level_prefix<K><<<K >= 3 ? b2s_div_up(nout, TL_PT / 32) : nout, TL_PT, 0, st>>>(g, n_vis, nlists, chunk_off, nch, table, out_len, out_off,
-                                                          out_chunk_off, isect_offsets, ticket);
+                                                          out_chunk_off, isect_offsets, ticket, L.cap_out[K]);
     B2S_LAUNCH_CHECK();
     k_level_fill<K><<<nch, 32 * TL_WARPS, 0, st>>>(g, in, order, rects, n_vis, nlists, list_off, chunk_off, nch, table,
                                                    slice_cnt, out_off, out2, flatten_ids);
@@ -474,7 +482,7 @@ static int tl_run_level(const TlGeom &g, const TlLayout &L, char *w, const int32
 
 extern "C" int b2s_bin_tiles(const int32_t *tile_rects, const int32_t *order, const int32_t *n_vis,
                              const long long *totals_host, int N, int tile_size, int tile_w, int tile_h, int W, int H,
-                             const float *means2d, const float *geo, int offsets_with_total,
+                             const float *means2d, const float *geo, int offsets_with_total, int32_t *overflow,
                              int32_t *flatten_ids, int32_t *isect_offsets, void *workspace, size_t workspace_bytes,
                              b2s_stream_t stream) {
     if (N < 0 || !totals_host || tile_w <= 0 || tile_h <= 0) return B2S_ERR_ARG;
@@ -492,6 +500,7 @@ extern "C" int b2s_bin_tiles(const int32_t *tile_rects, const int32_t *order, co
     g.H = H;
     g.exact = means2d != nullptr;
     g.offs_total = offsets_with_total != 0;
+    g.overflow = overflow;
     cudaStream_t st = (cudaStream_t)stream;
     const int T = tile_w * tile_h;
     if (M == 0 || N == 0) {

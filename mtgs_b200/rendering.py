@@ -117,7 +117,7 @@ class _Project(torch.autograd.Function):
         keys = torch.empty(N, dtype=torch.int32, device=dev)
         rects = torch.empty(N, 2, dtype=torch.int32, device=dev)
         tight = torch.empty(N, 2, dtype=torch.int32, device=dev)
-        totals = torch.zeros(5, dtype=torch.int64, device=dev)
+        totals = torch.zeros(6, dtype=torch.int64, device=dev)  # 5 list sizes + the capacity-overflow word
         # accumulation buffers of the blend backward (v_xyabs | v_geo | v_colpack), zero-filled by the kernel
         arena = torch.empty(N * (8 + cdim) if want_arena else 0, dtype=torch.float32, device=dev)
         with _timed("project_fwd"):
@@ -129,6 +129,7 @@ class _Project(torch.autograd.Function):
                                            _ptr(arena) if want_arena and N > 0 else None, _stream()),
                        "b2s_project_fwd")
         ctx.save_for_backward(means, quats, scales, opacities, viewmat, K, radii, geo, comps)
+        ctx.set_materialize_grads(False)  # no zero tensors for the gradients of the integer / scratch outputs
         ctx.cfg = (W, H, eps2d, calc_comp, d_in, with_depth, cdim)
         ctx.has_colors = colors is not None
         ctx.mark_non_differentiable(radii, depths, tiles, keys, rects, tight, totals, arena)
@@ -183,14 +184,16 @@ class _Project(torch.autograd.Function):
         v_quats = torch.empty_like(quats)
         v_scales = torch.empty_like(scales)
         v_opac = torch.empty_like(opacities)
+        want_colors = ctx.has_colors and ctx.needs_input_grad[4]
+        v_colors = torch.empty(N, d_in, dtype=torch.float32, device=dev) if want_colors else None
         with _timed("project_bwd"):
             _lib.check(lib.b2s_project_bwd(_ptr(means), _ptr(quats), _ptr(scales), _ptr(opacities), _ptr(viewmat),
                                            _ptr(K), N, W, H, eps2d, int(calc_comp), d_in, int(with_depth), cdim,
                                            _ptr(radii), _ptr(geo), _ptr(comps), _ptr(v_means2d),
                                            int(v_means2d.stride(0)), _ptr(v_geo), _ptr(v_colpack), _ptr(v_means),
-                                           _ptr(v_quats), _ptr(v_scales), _ptr(v_opac), _ptr(v_view), _stream()),
+                                           _ptr(v_quats), _ptr(v_scales), _ptr(v_opac), _ptr(v_colors), _ptr(v_view),
+                                           _stream()),
                        "b2s_project_bwd")
-        v_colors = v_colpack[:, :d_in] if (ctx.has_colors and ctx.needs_input_grad[4]) else None
         return (v_means, v_quats, v_scales, v_opac, v_colors, v_view) + (None,) * 13
 
 
@@ -199,7 +202,8 @@ class _Blend(torch.autograd.Function):
     exactly as with upstream (mtgs_scene_graph.py:666-667, 1171-1174)."""
 
     @staticmethod
-    def forward(ctx, means2d, geo, colpack, offsets, ids, arena, W, H, tile_w, tile_h, cdim, d_out, ed, absgrad):
+    def forward(ctx, means2d, geo, colpack, offsets, ids, arena, W, H, tile_w, tile_h, cdim, d_out, ed, absgrad,
+                skip_ptr=None):
         lib = _lib.load()
         dev = means2d.device
         render = torch.empty(1, H, W, d_out, dtype=torch.float32, device=dev)
@@ -212,9 +216,10 @@ class _Blend(torch.autograd.Function):
         with _timed("blend_fwd"):
             _lib.check(lib.b2s_blend_fwd(_ptr(means2d), _ptr(geo), _ptr(colpack), _ptr(offsets), _ptr(ids), W, H,
                                          tile_w, tile_h, cdim, d_out, int(ed), _ptr(render), _ptr(alpha),
-                                         _ptr(last_ids), _ptr(records), _stream()), "b2s_blend_fwd")
+                                         _ptr(last_ids), _ptr(records), skip_ptr, _stream()), "b2s_blend_fwd")
         ctx.save_for_backward(means2d, offsets, render, alpha, last_ids, records, arena)
         ctx.cfg = (W, H, tile_w, tile_h, cdim, d_out, ed, absgrad, geo.shape[0])
+        ctx.set_materialize_grads(False)
         ctx.arena_clean = True
         ctx.mark_non_differentiable(last_ids)
         return render, alpha, last_ids
@@ -244,25 +249,37 @@ class _Blend(torch.autograd.Function):
         if absgrad:
             # upstream: `means2d.absgrad = v_means2d_abs` on the tensor object handed in by the caller
             means2d.absgrad = v_xyabs[:, 2:4].unsqueeze(0)
-        return (v_xyabs[:, 0:2].unsqueeze(0), v_geo, v_colpack) + (None,) * 11
+        return (v_xyabs[:, 0:2].unsqueeze(0), v_geo, v_colpack) + (None,) * 12
 
 
 # ------------------------------------------------------------------------------------------------
-_PINNED_TOTALS: Dict[int, Tensor] = {}
+_PINNED_TOTALS: Dict[int, tuple] = {}
+# Capacities of the tile-list build per (device, tile grid): the largest list sizes seen so far plus headroom.  With
+# them the whole forward is enqueued WITHOUT waiting for this frame's sizes (they are read back, asynchronously, and
+# checked once everything is queued); a frame that needs more room is rebuilt with its exact sizes.
+_CAPACITY: Dict[tuple, list] = {}
+CAPACITY_HEADROOM = 1.25
+SYNC_SIZES = False  # True: always wait for the exact sizes before building the lists (debugging / tests)
 
 
-def _sort_and_read_totals(keys: Tensor, totals: Tensor):
-    """Depth order of the visible Gaussians; the list sizes summed by the projection kernel travel to the host
-    WHILE the sort runs (the one device->host read of the path; it sizes the tile lists)."""
+def _start_totals_readback(totals: Tensor):
+    """Asynchronous device->host copy of the list sizes summed by the projection kernel (the one device->host read
+    of the path) into a pinned buffer; returns (host tensor, event)."""
+    dev = totals.device
+    slot = _PINNED_TOTALS.get(dev.index)
+    if slot is None:
+        slot = _PINNED_TOTALS[dev.index] = (torch.zeros(6, dtype=torch.int64).pin_memory(), torch.cuda.Event())
+    host, ev = slot
+    host.copy_(totals, non_blocking=True)
+    ev.record()
+    return host, ev
+
+
+def _sort_depth(keys: Tensor):
+    """Depth order of the visible Gaussians (runs while the list sizes travel to the host)."""
     lib = _lib.load()
     dev = keys.device
     N = keys.shape[0]
-    host = _PINNED_TOTALS.get(dev.index)
-    if host is None:
-        host = _PINNED_TOTALS[dev.index] = torch.zeros(5, dtype=torch.int64).pin_memory()
-    host.copy_(totals, non_blocking=True)
-    ev = torch.cuda.Event()
-    ev.record()
     order = torch.empty(N, dtype=torch.int32, device=dev)
     n_vis = torch.empty(1, dtype=torch.int32, device=dev)
     wsb = int(lib.b2s_bin_depth_workspace_bytes(N))
@@ -270,16 +287,15 @@ def _sort_and_read_totals(keys: Tensor, totals: Tensor):
     with _timed("bin_sort_depth"):
         _lib.check(lib.b2s_bin_sort_depth(_ptr(keys), N, _ptr(order), _ptr(n_vis), _ptr(ws), wsb, _stream()),
                    "b2s_bin_sort_depth")
-    ev.synchronize()
-    tot = [int(v) for v in host.tolist()]
-    return order, n_vis, tot
+    return order, n_vis
 
 
 def _tile_lists(rects: Tensor, order: Tensor, n_vis: Tensor, sizes, tile_w: int, tile_h: int, W: int, H: int,
-                walk: bool) -> Tuple[Tensor, Tensor]:
+                walk: bool, overflow_ptr=None) -> Tuple[Tensor, Tensor]:
     """Per-tile depth-ordered lists over ``rects``.  ``walk``: the blend's own lists (tight rectangles; offsets carry a
     trailing total so that no host-side count is needed); otherwise upstream's lists over the 3-sigma rectangles.
-    ``sizes`` = (list length, S, E1, E3, n_vis) as summed by the projection kernel for ``rects``."""
+    ``sizes`` = (list length, S, E1, E3, n_vis): the exact sizes summed by the projection kernel for ``rects``, or --
+    with ``overflow_ptr`` (capacity mode) -- capacities."""
     lib = _lib.load()
     dev = rects.device
     N = rects.shape[0]
@@ -292,8 +308,8 @@ def _tile_lists(rects: Tensor, order: Tensor, n_vis: Tensor, sizes, tile_w: int,
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     with _timed("bin_tiles" if walk else "bin_tiles_upstream_lists"):
         _lib.check(lib.b2s_bin_tiles(_ptr(rects), _ptr(order), _ptr(n_vis), tot, N, 16, tile_w, tile_h, W, H,
-                                     None, None, int(walk), _ptr(ids), _ptr(offsets), _ptr(ws), wsb, _stream()),
-                   "b2s_bin_tiles")
+                                     None, None, int(walk), overflow_ptr, _ptr(ids), _ptr(offsets), _ptr(ws), wsb,
+                                     _stream()), "b2s_bin_tiles")
     return ids, offsets
 
 
@@ -324,11 +340,33 @@ def _rasterize_one(means, quats, scales, opacities, colors, viewmat, K, width, h
     means2d, geo, colpack, radii, depths, tiles, keys, rects, tight, totals, arena = _Project.apply(
         means, quats, scales, opacities, cols, viewmat, K, width, height, tile_w, tile_h, float(eps2d),
         float(near_plane), float(far_plane), float(radius_clip), calc_comp, with_depth, cdim, want_grad)
-    order, n_vis, tot = _sort_and_read_totals(keys, totals)
-    # the lists the blend walks: tight rectangles (the exact per-tile test runs lazily while the blend stages a batch)
-    walk_ids, walk_offsets = _tile_lists(tight, order, n_vis, tuple(tot), tile_w, tile_h, width, height, True)
-    render, alpha, last_ids = _Blend.apply(means2d, geo, colpack, walk_offsets, walk_ids, arena, width, height,
-                                           tile_w, tile_h, cdim, d_out, ed, bool(absgrad))
+    host, ev = _start_totals_readback(totals)
+    order, n_vis = _sort_depth(keys)
+    key = (means.device.index, tile_w, tile_h)
+    caps = _CAPACITY.get(key)
+
+    def build(sizes, overflow_ptr):
+        # the lists the blend walks: tight rectangles (the exact per-tile test runs lazily while the blend stages a batch)
+        ids, offs = _tile_lists(tight, order, n_vis, sizes, tile_w, tile_h, width, height, True, overflow_ptr)
+        return (ids, offs) + tuple(_Blend.apply(means2d, geo, colpack, offs, ids, arena, width, height, tile_w, tile_h,
+                                                cdim, d_out, ed, bool(absgrad), overflow_ptr))
+
+    if caps is None or SYNC_SIZES or N == 0:
+        ev.synchronize()
+        tot = [int(v) for v in host.tolist()[:5]]
+        walk_ids, walk_offsets, render, alpha, last_ids = build(tuple(tot), None)
+    else:
+        # capacity mode: everything is enqueued before this frame's sizes are known; they are checked afterwards
+        flag = C.c_void_p(totals.data_ptr() + 40)
+        walk_ids, walk_offsets, render, alpha, last_ids = build((caps[0], caps[1], caps[2], caps[3], N), flag)
+        ev.synchronize()
+        tot = [int(v) for v in host.tolist()[:5]]
+        if any(tot[i] > caps[i] for i in range(4)):  # rare: rebuild with the exact sizes
+            walk_ids, walk_offsets, render, alpha, last_ids = build(tuple(tot), None)
+    if caps is None:
+        caps = _CAPACITY[key] = [0, 0, 0, 0]
+    for i in range(4):
+        caps[i] = max(caps[i], int(tot[i] * CAPACITY_HEADROOM) + 4096)
     # keys with a leading underscore are not part of upstream's info dict (bench.py reads them for K_pairs)
     meta = dict(radii=radii.unsqueeze(0), means2d=means2d, depths=depths.unsqueeze(0),
                 conics=geo.detach()[:, :3].unsqueeze(0), opacities=geo.detach()[:, 3].unsqueeze(0),

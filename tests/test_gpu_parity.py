@@ -219,6 +219,43 @@ def test_backward_variants_agree_with_the_oracle(oracle, cuda_device, px):
         rendering.BWD_PX = old
 
 
+def test_capacity_mode_equals_exact_sizes_and_survives_overflow(cuda_device):
+    """The forward is enqueued with list capacities from earlier frames (no wait for this frame's sizes).  It must give
+    the same bits as the build with exact sizes, and a frame that outgrows the capacities (here: forced) must be rebuilt,
+    not corrupted."""
+    from mtgs_b200 import rendering
+    s = scenes.street(n=20_000, seed=7, width=960, height=540)
+    t = _to_dev(s, cuda_device)
+    kw = dict(render_mode="RGB+ED", rasterize_mode="antialiased")
+    rendering._CAPACITY.clear()
+    old = rendering.SYNC_SIZES
+    try:
+        rendering.SYNC_SIZES = True
+        with torch.no_grad():
+            r0, a0, m0 = _gpu_raster(t, s, **kw)
+        rendering.SYNC_SIZES = False
+        key = (cuda_device.index or 0, m0["tile_width"], m0["tile_height"])
+        assert key in rendering._CAPACITY
+        with torch.no_grad():
+            r1, a1, m1 = _gpu_raster(t, s, **kw)          # capacity mode, capacities sufficient
+        assert torch.equal(r0, r1) and torch.equal(a0, a1)
+        n_walk = int(m1["_walk_offsets"][-1])
+        assert m1["_walk_ids"].numel() >= n_walk and torch.equal(m1["_walk_ids"][:n_walk], m0["_walk_ids"][:n_walk])
+        for lvl in range(4):                              # every level's capacity too small in turn
+            caps = list(rendering._CAPACITY[key])
+            small = list(caps)
+            small[lvl] = 64
+            rendering._CAPACITY[key] = small
+            t2 = _to_dev(s, cuda_device, grad=True)
+            r2, a2, m2 = _gpu_raster(t2, s, absgrad=True, **kw)
+            assert torch.equal(r0, r2.detach()) and torch.equal(a0, a2.detach()), f"level {lvl}"
+            (r2.sum() + a2.sum()).backward()
+            assert torch.isfinite(t2["means"].grad).all() and float(t2["means"].grad.abs().sum()) > 0
+            assert rendering._CAPACITY[key][lvl] >= caps[lvl] - 1   # grown back
+    finally:
+        rendering.SYNC_SIZES = old
+
+
 def test_golden_fixture_through_c_abi(cuda_device):
     """Committed fixture (tests/golden/oracle_tiny_golden.npz): no oracle code runs in this test."""
     g = np.load(os.path.join(GOLD, "oracle_tiny_golden.npz"))
