@@ -238,6 +238,26 @@ int b2s_ncc_bwd(const float *pred, const float *gt, int H, int W, int patch, int
 int b2s_normal_from_depth(const float *depth, int H, int W, float fx, float fy, float cx, float cy,
                           const float *A_t, float *normals, b2s_stream_t stream);
 
+/* ---- Gaussian arena: node gather + activations + SH colour in one kernel each way ----
+ * Reference: per-node chains of torch ops (gaussian_model/vanilla_gaussian_splatting.py:299-322, rigid_node.py:206-215,
+ * 243-252) followed by a per-attribute torch.cat over the nodes (mtgs_scene_graph.py:408-461).  All nodes live in one
+ * structure-of-arrays arena: means [N,3], scales_raw [N,3] (log), quats_raw [N,4] (wxyz, any norm), opac_raw [N]
+ * (logit), sh [N,K,3] (features_dc then features_rest); node_of [N] (int32, may be NULL = one node) indexes poses
+ * [n_nodes,16] = R (9, row-major) | t (3) | q (4, wxyz) of each node for this frame; campos [3] = camera centre.
+ * fwd: means_w = means R^T + t, quats_w = q_node (x) quats / ||quats||, scales = exp, opac = sigmoid, colors [N,3] =
+ *   clamp(SH_degree(normalise(means_w - campos), sh) + 0.5, 0, 1) (degree 0: sigmoid(sh[:,0])); clamp_mask [N] (uint8)
+ *   records which channels lie strictly inside the clamp.  bwd: gradients of the raw arrays from those of the five
+ *   outputs (view directions are detached, as in the reference; no gradient to the node poses). */
+int b2s_arena_fwd(const float *means, const float *scales_raw, const float *quats_raw, const float *opac_raw,
+                  const float *sh, const int32_t *node_of, const float *poses, const float *campos, int N, int K,
+                  int degree, float *means_w, float *quats_w, float *scales, float *opac, float *colors,
+                  uint8_t *clamp_mask, b2s_stream_t stream);
+int b2s_arena_bwd(const float *means, const float *scales_raw, const float *quats_raw, const float *opac_raw,
+                  const float *sh, const int32_t *node_of, const float *poses, const float *campos, int N, int K,
+                  int degree, const uint8_t *clamp_mask, const float *v_means_w, const float *v_quats_w,
+                  const float *v_scales, const float *v_opac, const float *v_colors, float *g_means, float *g_quats,
+                  float *g_scales, float *g_opac, float *g_sh, b2s_stream_t stream);
+
 /* ---- fused multi-tensor Adam + densification primitives ----
  * Reference: one torch.optim.Adam per (node, attribute) group (mtgs/scene_model/custom_trainer.py:115-136), the
  * after_train statistics and optimizer-state surgery of gaussian_model/vanilla_gaussian_splatting.py:392-474 and the

@@ -49,6 +49,8 @@ SIGNATURES = {
     "b2s_ncc_fwd": (_i, [_vp] * 3 + [_i] * 4 + [_vp, _vp, _vp]),
     "b2s_ncc_bwd": (_i, [_vp] * 2 + [_i] * 4 + [_vp] * 4 + [_vp]),
     "b2s_normal_from_depth": (_i, [_vp, _i, _i] + [_f] * 4 + [_vp, _vp, _vp]),
+    "b2s_arena_fwd": (_i, [_vp] * 8 + [_i] * 3 + [_vp] * 6 + [_vp]),
+    "b2s_arena_bwd": (_i, [_vp] * 8 + [_i] * 3 + [_vp] * 11 + [_vp]),
     "b2s_adam_chunk": (_i, []),
     "b2s_adam_multi": (_i, [_vp, _vp, _vp, _i, _vp]),
     "b2s_densify_stats": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
