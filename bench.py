@@ -448,6 +448,10 @@ def main():
     ms_per_step = float(t_ms.item()) / args.steps
     value = N * world / (ms_per_step * 1e-3)
 
+    # one extra step under the torch profiler (EVERY rank: the step contains the collective exchange)
+    launches_per_step = count_step_launches(lambda: step(params))
+    barrier()
+
     # ---- timed region 2: end to end from pinned host buffers through the public API
     e2e_steps = max(3, args.steps // 2)
 
@@ -592,8 +596,6 @@ def main():
     except Exception as e:  # pragma: no cover
         blend_fp32 = {"error": f"{type(e).__name__}: {e}"}
         r_chk = a_chk = None
-
-    launches_per_step = count_step_launches(lambda: step(params))
 
     # ---- CPU baseline (oracle port, full workload, one timed step) + PSNR delta of the CUDA render against it
     cpu_baseline = psnr = None
