@@ -145,7 +145,7 @@ def run_cpu_port(args, scene, vcfg, sample_n, steps, warmup):
                                                   render_mode=vcfg["render_mode"], rasterize_mode=vcfg["rasterize_mode"])
         ctx["meta_offs"], ctx["meta_flat"] = meta["isect_offsets"], meta["flatten_ids"]
         cpu_ref.rasterization_bwd(ctx, v_r, v_a, absgrad=vcfg["absgrad"])
-        out["render"], out["alpha"] = rc, ra
+        out["render"], out["alpha"], out["last"], out["meta"] = rc, ra, ctx["last"], meta
         return meta
 
     for _ in range(warmup):
@@ -157,29 +157,24 @@ def run_cpu_port(args, scene, vcfg, sample_n, steps, warmup):
     return sample_n / dt, dt, cpu_ref.num_threads(), out
 
 
-def k_pairs_stats(meta, alpha, N, tile_w):
-    """K_pairs of SURVEY 8d: sum over pixels of the sorted entries walked before termination, i.e.
-    last_id - tile_start + 1 in upstream's (tile, depth)-sorted intersection list.  `walked` is the same sum over
-    the list the blend kernels actually walk (identical to upstream's list unless binning culls dead pairs)."""
-    import torch
+def k_pairs_walked(meta, alpha):
+    """Pairs the blend kernels actually evaluate up to each pixel's last contribution: sum over hit pixels of the
+    tile-local dense index of the last blended entry + 1 (entries that cannot reach alpha >= 1/255 in the tile are
+    dropped before they are counted)."""
     last = meta["_last_ids"].reshape(-1).long()
-    H, W = meta["_last_ids"].shape[-2:]
-    dev = last.device
-    ys, xs = torch.meshgrid(torch.arange(H, device=dev), torch.arange(W, device=dev), indexing="ij")
-    tile = ((ys // 16) * tile_w + xs // 16).reshape(-1)
     hit = alpha.reshape(-1) > 0
-    w_off = meta["_walk_offsets"].reshape(-1).long()
-    walked = int(((last - w_off[tile] + 1) * hit).sum())
-    flat, offs = meta["flatten_ids"].long(), meta["isect_offsets"].reshape(-1).long()
-    if flat.data_ptr() == meta["_walk_ids"].data_ptr():
-        return walked, walked
-    M = flat.numel()
-    tile_e = torch.searchsorted(offs, torch.arange(M, device=dev), right=True) - 1
-    key_full, perm = torch.sort(tile_e * N + flat)
-    g_last = meta["_walk_ids"].long()[last.clamp(0, max(0, meta["_walk_ids"].numel() - 1))]
-    pos = perm[torch.searchsorted(key_full, tile * N + g_last).clamp(0, M - 1)]
-    upstream = int(((pos - offs[tile] + 1) * hit).sum())
-    return upstream, walked
+    return int(((last + 1) * hit).sum())
+
+
+def k_pairs_reference(ref_meta, ref_last, ref_alpha, tile_w):
+    """K_pairs of SURVEY 8d on the reference algorithm's own lists: sum over pixels of the sorted entries walked before
+    termination = last_id - tile_start + 1 (from the CPU oracle's forward of the same inputs)."""
+    H, W = ref_last.shape
+    offs = np.asarray(ref_meta["isect_offsets"]).reshape(-1).astype(np.int64)
+    ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    tile = (ys // 16) * tile_w + xs // 16
+    hit = np.asarray(ref_alpha).reshape(H, W) > 0
+    return int(((ref_last.astype(np.int64) - offs[tile] + 1) * hit).sum())
 
 
 def probe_gsplat():
@@ -566,36 +561,14 @@ def main():
                             "construction; their fp32 roofline is in blend_fp32, whole-step HBM fraction in roofline_step"}
     step_frac = ab["total"] / (ms_per_step * 1e-3) / 1e9 / peak
 
-    # ---- secondary roofline of the blend kernels (SURVEY 8d "Algorithmic flops", BASELINE.md section 3), live:
-    # K_pairs from this run's last_ids, flop model fwd (16 + 2 CDIM), bwd (35 + 6 CDIM) per pair, fp32 peak =
-    # SMs x 128 lanes x 2 flop x the SM clock sampled during the timed region
-    blend_fp32 = None
-    try:
-        with torch.no_grad():
-            r_chk, a_chk, meta_chk = rasterization(params["means"], params["quats"], params["scales"],
-                                                   params["opacities"], params["colors"], viewmat, Ks, W, H,
-                                                   packed=False, render_mode=vcfg["render_mode"],
-                                                   rasterize_mode=vcfg["rasterize_mode"], absgrad=vcfg["absgrad"])
-        kp_up, kp_walk = k_pairs_stats(meta_chk, a_chk, N, int(meta_chk["tile_width"]))
-        sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        clk = (clocks or {}).get("sm_mhz") or 1965.0
-        fp32_peak = sms * 128 * 2 * clk * 1e6 / 1e12
-        f_fwd, f_bwd = kp_up * (16 + 2 * cdim), kp_up * (35 + 6 * cdim)
-        blend_fp32 = {"K_pairs": kp_up, "K_pairs_walked_by_kernels": kp_walk, "pairs_upper_bound_256M": 256 * M,
-                      "fp32_peak_tflops": fp32_peak, "sm_mhz_used": clk,
-                      "fwd": {"flop": f_fwd, "ms": stage_ms.get("blend_fwd"),
-                              "tflops": f_fwd / (stage_ms["blend_fwd"] * 1e-3) / 1e12,
-                              "frac_of_fp32_peak": f_fwd / (stage_ms["blend_fwd"] * 1e-3) / 1e12 / fp32_peak,
-                              "ex2_per_s": kp_up / (stage_ms["blend_fwd"] * 1e-3),
-                              "frac_of_sfu_peak": kp_up / (stage_ms["blend_fwd"] * 1e-3) / (sms * 16 * clk * 1e6)},
-                      "bwd": {"flop": f_bwd, "ms": stage_ms.get("blend_bwd"),
-                              "tflops": f_bwd / (stage_ms["blend_bwd"] * 1e-3) / 1e12,
-                              "frac_of_fp32_peak": f_bwd / (stage_ms["blend_bwd"] * 1e-3) / 1e12 / fp32_peak,
-                              "sfu_ops_per_s": 2 * kp_up / (stage_ms["blend_bwd"] * 1e-3),
-                              "frac_of_sfu_peak": 2 * kp_up / (stage_ms["blend_bwd"] * 1e-3) / (sms * 16 * clk * 1e6)}}
-    except Exception as e:  # pragma: no cover
-        blend_fp32 = {"error": f"{type(e).__name__}: {e}"}
-        r_chk = a_chk = None
+    # one forward of the timed configuration for the checks below (PSNR delta, K_pairs, gsplat A/B)
+    with torch.no_grad():
+        r_chk, a_chk, meta_chk = rasterization(params["means"], params["quats"], params["scales"], params["opacities"],
+                                               params["colors"], viewmat, Ks, W, H, packed=False,
+                                               render_mode=vcfg["render_mode"], rasterize_mode=vcfg["rasterize_mode"],
+                                               absgrad=vcfg["absgrad"])
+    kp_walk = k_pairs_walked(meta_chk, a_chk)
+    kp_ref = None
 
     # ---- CPU baseline (oracle port, full workload, one timed step) + PSNR delta of the CUDA render against it
     cpu_baseline = psnr = None
@@ -618,12 +591,39 @@ def main():
                     m = float(np.mean((x - y) ** 2))
                     return float("inf") if m == 0 else 10 * math.log10(1.0 / m)
                 p_o, p_r = _psnr(ours, gt), _psnr(ref, gt)
+                kp_ref = k_pairs_reference(ref_out["meta"], ref_out["last"], ref_out["alpha"], int(meta_chk["tile_width"]))
                 psnr = {"delta_db": p_o - p_r, "ours_vs_gt_db": p_o, "reference_vs_gt_db": p_r,
                         "ours_vs_reference_db": _psnr(ours, ref),
                         "reference": "CPU oracle render of the same inputs (gsplat unavailable on this box)",
                         "gt": "reference render + N(0, 0.05) noise (seed 5), clipped to [0, 1]"}
         except Exception as e:  # pragma: no cover
             cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+
+    # ---- secondary roofline of the blend kernels (SURVEY 8d "Algorithmic flops", BASELINE.md section 3), live:
+    # K_pairs = entries walked before termination on the reference algorithm's lists (oracle forward of the same
+    # inputs; falls back to the pairs the kernels evaluate when the CPU leg is skipped), flop model fwd (16 + 2 CDIM),
+    # bwd (35 + 6 CDIM) per pair, fp32 peak = SMs x 128 lanes x 2 flop x the SM clock sampled during the timed region
+    try:
+        kp = kp_ref if kp_ref is not None else kp_walk
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        clk = (clocks or {}).get("sm_mhz") or 1965.0
+        fp32_peak = sms * 128 * 2 * clk * 1e6 / 1e12
+        f_fwd, f_bwd = kp * (16 + 2 * cdim), kp * (35 + 6 * cdim)
+        t_f, t_b = stage_ms["blend_fwd"] * 1e-3, stage_ms["blend_bwd"] * 1e-3
+        blend_fp32 = {"K_pairs": kp, "K_pairs_source": "reference lists (CPU oracle forward)" if kp_ref is not None
+                      else "pairs evaluated by the kernels (CPU leg skipped)",
+                      "pairs_evaluated_by_kernels": kp_walk, "pairs_upper_bound_256M": 256 * M,
+                      "fp32_peak_tflops": fp32_peak, "sm_mhz_used": clk,
+                      "note": "fractions above 1 are possible: the flop count is the reference algorithm's, and the "
+                              "kernels drop (Gaussian, tile) pairs that cannot reach alpha >= 1/255 before evaluating them",
+                      "fwd": {"flop": f_fwd, "ms": stage_ms["blend_fwd"], "tflops": f_fwd / t_f / 1e12,
+                              "frac_of_fp32_peak": f_fwd / t_f / 1e12 / fp32_peak,
+                              "frac_of_sfu_peak": kp / t_f / (sms * 16 * clk * 1e6)},
+                      "bwd": {"flop": f_bwd, "ms": stage_ms["blend_bwd"], "tflops": f_bwd / t_b / 1e12,
+                              "frac_of_fp32_peak": f_bwd / t_b / 1e12 / fp32_peak,
+                              "frac_of_sfu_peak": 2 * kp / t_b / (sms * 16 * clk * 1e6)}}
+    except Exception as e:  # pragma: no cover
+        blend_fp32 = {"error": f"{type(e).__name__}: {e}"}
 
     # ---- A/B against the reference's own implementation if it exists on this box
     gs_mod, gs_reason = probe_gsplat()

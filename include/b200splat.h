@@ -158,29 +158,41 @@ size_t b2s_bin_tiles_workspace_bytes(const long long *totals_host, int tile_w, i
 int b2s_bin_tiles(const int32_t *rects, const int32_t *order, const int32_t *n_vis,
                   const long long *totals_host, int N, int tile_size, int tile_w, int tile_h, int W, int H,
                   const float *means2d, const float *geo, int offsets_with_total, int32_t *overflow,
+                  int levels /* 4: per-tile lists; 3: stop at the (tile row, column group) lists */,
                   int32_t *flatten_ids, int32_t *isect_offsets, void *workspace,
                   size_t workspace_bytes, b2s_stream_t stream);
+/* levels == 3: where the (tile row y, column group c) lists live inside `workspace` (same totals): items = int2
+ * (Gaussian id, tile-column range x0 | x1 << 16), list index y * ncg + c, offsets = int32 [nlists + 1].  Tile (y, x)
+ * belongs to list y * ncg + (x >> cg_shift) and is covered by an item iff x0 <= x < x1 -- the last filter level, which
+ * b2s_blend_fwd applies lazily while it walks (only ~16 % of every list is read before a tile saturates). */
+int b2s_bin_tiles_l3_view(const long long *totals_host, int tile_w, int tile_h, size_t *items_byte_offset,
+                          size_t *offsets_byte_offset, int *nlists, int *ncg, int *cg_shift);
 int b2s_bin_isect_ids(const int32_t *isect_offsets, int n_tiles, const int32_t *flatten_ids,
                       const float *depths, long long M, int64_t *isect_ids, b2s_stream_t stream);
 
 /* ---- alpha blending (upstream rasterize_to_pixels fwd / bwd; A.3, A.4) ----
  * cdim in {4, 8}; d_out = channels written per pixel (<= cdim); expected_depth != 0 divides channel
  * d_out-1 by max(alpha, 1e-10) in the epilogue (upstream does that in torch).  16x16 tiles only.
- * tile_offsets [tile_w * tile_h + 1] / tile_ids: depth-ordered list per tile (b2s_bin_tiles, either mode; the exact
- * mode's lists give the same image with ~3x fewer entries).  last_ids [H, W]: index into tile_ids of the last entry
- * each pixel blended.  records (may be NULL for a forward without backward; 128-byte aligned,
- * b2s_blend_record_bytes(capacity of tile_ids, tiles, cdim) bytes): the forward stores every list block it walks as
- * a "walk record" (projected mean, log2-domain conic, opacity, Gaussian id, colours of 128 entries, SoA) through TMA
- * bulk stores; the backward replays those blocks back to front through double-buffered TMA bulk loads and never
- * touches the lists or the per-Gaussian arrays.  v_xyabs [N,4] = (v_mean2d xy, |v_mean2d| xy), v_geo [N,4] =
- * (v_conic abc, v_opacity_eff), v_colpack [N,cdim]: accumulated with 16-byte vector reductions, zero-filled by the
- * caller (b2s_project_fwd does it). */
-size_t b2s_blend_record_bytes(long long list_capacity, int n_tiles, int cdim);
-int b2s_blend_fwd(const float *means2d, const float *geo, const float *colpack,
-                  const int32_t *tile_offsets, const int32_t *tile_ids, int W, int H, int tile_w, int tile_h,
+ * The forward walks the depth-ordered (tile row, column group) lists of b2s_bin_tiles(levels = 3) /
+ * b2s_bin_tiles_l3_view: per tile it keeps the items that cover the tile's column AND can reach alpha >= 1/255 at a
+ * pixel centre of the tile (exact test; dropping the others changes no output bit), packs them densely into blocks of
+ * 128 and blends block by block.  last_ids [H, W]: tile-local dense index of the last entry each pixel blended.
+ * records (may be NULL for a forward without backward; 128-byte aligned, b2s_blend_record_bytes(pairs, tiles, cdim)
+ * bytes with pairs = the tight list length of b2s_project_fwd's totals): every blended block is stored as a "walk
+ * record" (projected mean, log2-domain conic, opacity, Gaussian id, colours of its entries, SoA; header: entries,
+ * previous block of the tile) through one TMA bulk store at an index drawn from *block_counter (device uint32, zeroed
+ * by the caller); tile_blocks [tiles, 2] receives (last block, number of blocks) of every tile.  The backward replays
+ * each tile's chain back to front through double-buffered TMA bulk loads and never touches the lists or the
+ * per-Gaussian arrays.  v_xyabs [N,4] = (v_mean2d xy, |v_mean2d| xy), v_geo [N,4] = (v_conic abc, v_opacity_eff),
+ * v_colpack [N,cdim]: accumulated with 16-byte vector reductions, zero-filled by the caller (b2s_project_fwd does it).
+ * skip_flag: the overflow word of a capacity-mode b2s_bin_tiles (may be NULL). */
+size_t b2s_blend_record_bytes(long long pair_capacity, int n_tiles, int cdim);
+int b2s_blend_fwd(const float *means2d, const float *geo, const float *colpack, const int32_t *list_offsets,
+                  const int32_t *list_items, int ncg, int cg_shift, int W, int H, int tile_w, int tile_h,
                   int cdim, int d_out, int expected_depth, float *render, float *alpha, int32_t *last_ids,
-                  float *records, const int32_t *skip_flag /* may be NULL */, b2s_stream_t stream);
-int b2s_blend_bwd(const int32_t *tile_offsets, const float *records, int W, int H, int tile_w, int tile_h,
+                  float *records, uint32_t *block_counter, int32_t *tile_blocks, const int32_t *skip_flag,
+                  b2s_stream_t stream);
+int b2s_blend_bwd(const int32_t *tile_blocks, const float *records, int W, int H, int tile_w, int tile_h,
                   int cdim, int d_out, int expected_depth, const float *render, const float *alpha,
                   const int32_t *last_ids, const float *v_render, const float *v_alpha, float *v_xyabs,
                   float *v_geo, float *v_colpack, int px_per_thread /* 0 = default; 4 or 8 (tuning / tests) */,

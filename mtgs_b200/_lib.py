@@ -34,10 +34,12 @@ SIGNATURES = {
     "b2s_bin_sort_depth": (_i, [_vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "b2s_debug_sort_depth_phases": (_i, [_vp, _i, _vp, _vp, _vp, _sz, _vp, _vp]),
     "b2s_bin_tiles_workspace_bytes": (_sz, [C.POINTER(_ll), _i, _i]),
-    "b2s_bin_tiles": (_i, [_vp] * 3 + [C.POINTER(_ll)] + [_i] * 6 + [_vp, _vp, _i, _vp] + [_vp] * 3 + [_sz, _vp]),
+    "b2s_bin_tiles": (_i, [_vp] * 3 + [C.POINTER(_ll)] + [_i] * 6 + [_vp, _vp, _i, _vp, _i] + [_vp] * 3 + [_sz, _vp]),
+    "b2s_bin_tiles_l3_view": (_i, [C.POINTER(_ll), _i, _i, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_i), C.POINTER(_i),
+                                   C.POINTER(_i)]),
     "b2s_bin_isect_ids": (_i, [_vp, _i, _vp, _vp, _ll, _vp, _vp]),
     "b2s_blend_record_bytes": (_sz, [_ll, _i, _i]),
-    "b2s_blend_fwd": (_i, [_vp] * 5 + [_i] * 7 + [_vp] * 5 + [_vp]),
+    "b2s_blend_fwd": (_i, [_vp] * 5 + [_i] * 9 + [_vp] * 7 + [_vp]),
     "b2s_blend_bwd": (_i, [_vp] * 2 + [_i] * 7 + [_vp] * 8 + [_i, _vp]),
     "b2s_ssim_fwd": (_i, [_vp] * 3 + [_ll, _ll] + [_i] * 4 + [_vp, _i, _f, _f] + [_vp] * 5 + [_vp]),
     "b2s_ssim_bwd": (_i, [_vp] * 6 + [_i] * 4 + [_vp, _i, _vp] + [_vp]),

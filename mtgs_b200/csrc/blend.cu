@@ -44,8 +44,6 @@ template <int CDIM> struct BlkLayout {
     static constexpr int F4 = HDR + 1;
     static constexpr unsigned BYTES = F4 * 16;
 };
-// walk-record block index of batch k of a tile whose list starts at `start`: strictly increasing over (tile, k)
-__device__ __forceinline__ size_t blk_index(int start, int tile, int k) { return (size_t)(start >> 7) + tile + k; }
 
 // exponent in log2 units: s = A dx^2 + B dx dy + C dy^2 with A = a/2*log2e, B = b*log2e, C = c/2*log2e.
 // Written with explicit roundings so that forward and backward evaluate identical bits.
@@ -70,24 +68,30 @@ struct FwdRec {  // one list entry gathered into registers
     float4 col[2];
     bool keep;
 };
-// id -> projected record, plus the exact per-tile test: a (Gaussian, tile) pair whose minimum exponent over the tile's
-// pixel centres already gives alpha < 1/255 contributes to no pixel and is dropped while staging (tile_keep).
+// List item -> projected record.  The lists walked here are the (tile row, column group) lists of the tile-list
+// hierarchy (level 3): an item = (Gaussian id, tile-column range); the LAST filter level (does the item cover this
+// tile's column?) and the exact per-tile test (tile_keep: can the pair reach alpha >= 1/255 at any pixel centre of the
+// tile?) both run here, lazily, only for the part of the list that is walked before the tile saturates -- the blend
+// reads ~16 % of each list, so building per-tile lists for everything was 90 us of mostly unread output.
 template <int CQ>
-__device__ __forceinline__ void fwd_gather(FwdRec &r, int idx, int end, const int32_t *__restrict__ ids,
+__device__ __forceinline__ void fwd_gather(FwdRec &r, int idx, int end, const int2 *__restrict__ items, int tx,
                                            const float2 *__restrict__ means2d, const float4 *__restrict__ geo,
                                            const float4 *__restrict__ colpack, float rx0, float ry0, float rx1,
                                            float ry1) {
     r.keep = false;
     if (idx < end) {
-        const int g = ids[idx];
-        const float2 m = means2d[g];
-        const float4 ge = geo[g];
-        r.q = make_float4(m.x, m.y, 0.5f * B2S_LOG2E * ge.x, B2S_LOG2E * ge.y);
-        r.c = make_float4(0.5f * B2S_LOG2E * ge.z, ge.w, __int_as_float(g), 0.f);
-        r.keep = tile_keep(m.x, m.y, r.q.z, r.q.w, r.c.x, ge.w, rx0, ry0, rx1, ry1);
-        if (r.keep) {
+        const int2 it = items[idx];
+        if (tx >= (it.y & 0xffff) && tx < ((it.y >> 16) & 0xffff)) {
+            const int g = it.x;
+            const float2 m = means2d[g];
+            const float4 ge = geo[g];
+            r.q = make_float4(m.x, m.y, 0.5f * B2S_LOG2E * ge.x, B2S_LOG2E * ge.y);
+            r.c = make_float4(0.5f * B2S_LOG2E * ge.z, ge.w, __int_as_float(g), 0.f);
+            r.keep = tile_keep(m.x, m.y, r.q.z, r.q.w, r.c.x, ge.w, rx0, ry0, rx1, ry1);
+            if (r.keep) {
 #pragma unroll
-            for (int k = 0; k < CQ; ++k) r.col[k] = colpack[(size_t)g * CQ + k];
+                for (int k = 0; k < CQ; ++k) r.col[k] = colpack[(size_t)g * CQ + k];
+            }
         }
     }
 }
@@ -95,15 +99,19 @@ __device__ __forceinline__ void fwd_gather(FwdRec &r, int idx, int end, const in
 template <int CDIM, int DOUT, bool ED>
 __global__ void __launch_bounds__(BL_THREADS)
 k_blend_fwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, const float4 *__restrict__ colpack,
-            const int32_t *__restrict__ offsets /* [tiles + 1] */, const int32_t *__restrict__ ids, int W, int H,
-            int tile_w, float *__restrict__ render, float *__restrict__ alpha_out, int32_t *__restrict__ last_ids,
-            float4 *__restrict__ records /* walk-record blocks for the backward, or null */,
-            const int32_t *__restrict__ skip /* or null: non-zero = the lists are invalid (capacity overflow), do nothing */) {
+            const int32_t *__restrict__ list_off /* [lists + 1] */, const int2 *__restrict__ items, int ncg, int cg_shift,
+            int W, int H, int tile_w, float *__restrict__ render, float *__restrict__ alpha_out,
+            int32_t *__restrict__ last_ids, float4 *__restrict__ records /* walk-record blocks, or null */,
+            unsigned *__restrict__ blk_counter /* bump allocator of record blocks (zeroed by the caller) */,
+            int2 *__restrict__ tile_blocks /* [tiles]: (last block written, blocks written) */,
+            const int32_t *__restrict__ skip /* or null: non-zero = the lists are invalid (capacity overflow) */) {
     if (skip != nullptr && *skip != 0) return;
     constexpr int CQ = CDIM / 4;
     using BL = BlkLayout<CDIM>;
-    __shared__ __align__(128) float4 s_blk[BL::F4];
-    float4 *s_q = s_blk, *s_c = s_blk + BL_BATCH, *s_col = s_blk + 2 * BL_BATCH;
+    // two block-shaped buffers: kept entries are packed densely (slot s lives in buffer (s >> 7) & 1), a block is
+    // blended -- and handed to the TMA engine as a walk record -- as soon as its 128 slots are full
+    __shared__ __align__(128) float4 s_blk[2][BL::F4];
+    __shared__ int s_wcnt[BL_THREADS / 32];
 
     const int tile = blockIdx.x;
     const int ti = tile / tile_w, tj = tile - ti * tile_w;
@@ -112,7 +120,12 @@ k_blend_fwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
     const int y0 = ti * 16 + 4 * warp + 2 * (lane >> 4);  // the thread's pixels: rows y0 and y0 + 1 of column x
     const bool in0 = x < W && y0 < H, in1 = x < W && (y0 + 1) < H;
     const float px = (float)x + 0.5f;
-    const int start = offsets[tile], end = offsets[tile + 1];
+    const int L = ti * ncg + (tj >> cg_shift);
+    const int start = list_off[L], end = list_off[L + 1];
+    // pixel-centre rectangle of the tile clipped to the image
+    const float rx0 = (float)(tj * 16) + 0.5f, ry0 = (float)(ti * 16) + 0.5f;
+    const float rx1 = (float)min(tj * 16 + 16, W) - 0.5f, ry1 = (float)min(ti * 16 + 16, H) - 0.5f;
+    const unsigned lt = lanemask_lt();
 
     // the thread's two pixels are the halves of every float2 below
     float2 T = make_float2(1.f, 1.f);
@@ -122,49 +135,29 @@ k_blend_fwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
     const float2 npy = make_float2(-((float)y0 + 0.5f), -((float)y0 + 1.5f));
     int cur0 = 0, cur1 = 0;
     bool done0 = !in0, done1 = !in1;
+    int npend = 0;    // kept entries appended so far (CTA-uniform)
+    int nblend = 0;   // entries blended so far = 128 x blocks finished
+    int prev_blk = -1, nblocks = 0;  // chain of this tile's record blocks (meaningful in thread 0)
 
-    // pixel-centre rectangle of the tile clipped to the image
-    const float rx0 = (float)(tj * 16) + 0.5f, ry0 = (float)(ti * 16) + 0.5f;
-    const float rx1 = (float)min(tj * 16 + 16, W) - 0.5f, ry1 = (float)min(ti * 16 + 16, H) - 0.5f;
-    const unsigned lt = lanemask_lt();
-    __shared__ int s_wcnt[BL_THREADS / 32];
-
-    FwdRec nxt;
-    fwd_gather<CQ>(nxt, start + (int)threadIdx.x, end, ids, means2d, geo, colpack, rx0, ry0, rx1, ry1);
-    for (int base = start, k = 0; base < end; base += BL_BATCH, ++k) {
-        // the TMA store of the previous block must have read shared memory before the block is overwritten
-        if (records != nullptr && threadIdx.x == 0) b2s_bulk_wait_read();
-        if (__syncthreads_and(done0 && done1)) break;
-        // ballot compaction of the kept entries: slot order == list order
-        const unsigned bal = __ballot_sync(0xffffffffu, nxt.keep);
-        if (lane == 0) s_wcnt[warp] = __popc(bal);
-        __syncthreads();
-        int off = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < BL_THREADS / 32; ++w) {
-            const int nw = s_wcnt[w];
-            off += (w < warp) ? nw : 0;
-            total += nw;
+    // blend entries [0, cnt) of block buffer `bufi`; they carry the tile-local ids nblend .. nblend + cnt - 1
+    auto process_block = [&](int bufi, int cnt) {
+        float4 *s_q = s_blk[bufi], *s_c = s_blk[bufi] + BL_BATCH, *s_col = s_blk[bufi] + 2 * BL_BATCH;
+        if (records != nullptr) {
+            if (threadIdx.x == 0) {
+                const int blk = (int)atomicAdd(blk_counter, 1u);
+                s_blk[bufi][BL::HDR] = make_float4(__int_as_float(cnt), __int_as_float(prev_blk), 0.f, 0.f);
+                prev_blk = blk;
+                ++nblocks;
+            }
+            b2s_fence_async_smem();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                b2s_bulk_s2g(records + (size_t)prev_blk * BL::F4, s_blk[bufi], BL::BYTES);
+                b2s_bulk_commit();
+            }
         }
-        if (nxt.keep) {
-            const int slot = off + __popc(bal & lt);
-            s_q[slot] = nxt.q;
-            s_c[slot] = nxt.c;
-#pragma unroll
-            for (int j = 0; j < CQ; ++j) s_col[slot * CQ + j] = nxt.col[j];
-        }
-        if (threadIdx.x == 0) s_blk[BL::HDR] = make_float4(__int_as_float(total), 0.f, 0.f, 0.f);
-        if (records != nullptr) b2s_fence_async_smem();
-        __syncthreads();
-        if (records != nullptr && threadIdx.x == 0) {
-            b2s_bulk_s2g(records + blk_index(start, tile, k) * BL::F4, s_blk, BL::BYTES);
-            b2s_bulk_commit();
-        }
-        // gathers of the next batch fly while this one is blended
-        fwd_gather<CQ>(nxt, base + BL_BATCH + (int)threadIdx.x, end, ids, means2d, geo, colpack, rx0, ry0, rx1, ry1);
-
 #pragma unroll 2
-        for (int t = 0; t < total; ++t) {
+        for (int t = 0; t < cnt; ++t) {
             const float4 sq = s_q[t];
             const float4 sc = s_c[t];
             const float dx = sq.x - px;
@@ -184,7 +177,7 @@ k_blend_fwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
                 vis.y = ap1 ? vis.y : 0.f;
                 T.x = ap0 ? nT.x : T.x;
                 T.y = ap1 ? nT.y : T.y;
-                const int id = base + t;
+                const int id = nblend + t;
                 cur0 = ap0 ? id : cur0;
                 cur1 = ap1 ? id : cur1;
 #pragma unroll
@@ -197,8 +190,50 @@ k_blend_fwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
                 }
             }
         }
+        nblend += cnt;
+    };
+
+    bool all_done = false;
+    FwdRec nxt;
+    fwd_gather<CQ>(nxt, start + (int)threadIdx.x, end, items, tj, means2d, geo, colpack, rx0, ry0, rx1, ry1);
+    for (int base = start; base < end; base += BL_BATCH) {
+        // a TMA store still reading a block buffer must finish before new entries are appended to that buffer
+        if (records != nullptr && threadIdx.x == 0) b2s_bulk_wait_read();
+        if (__syncthreads_and(done0 && done1)) { all_done = true; break; }
+        // ballot compaction of the kept entries of this batch: slot order == list order
+        const unsigned bal = __ballot_sync(0xffffffffu, nxt.keep);
+        if (lane == 0) s_wcnt[warp] = __popc(bal);
+        __syncthreads();
+        int off = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < BL_THREADS / 32; ++w) {
+            const int nw = s_wcnt[w];
+            off += (w < warp) ? nw : 0;
+            total += nw;
+        }
+        if (nxt.keep) {
+            const int slot = npend + off + __popc(bal & lt);
+            float4 *bufp = s_blk[(slot >> 7) & 1];
+            const int e = slot & (BL_BATCH - 1);
+            bufp[e] = nxt.q;
+            bufp[BL_BATCH + e] = nxt.c;
+#pragma unroll
+            for (int j = 0; j < CQ; ++j) bufp[2 * BL_BATCH + e * CQ + j] = nxt.col[j];
+        }
+        npend += total;
+        // gathers of the next batch fly while full blocks are blended
+        fwd_gather<CQ>(nxt, base + BL_BATCH + (int)threadIdx.x, end, items, tj, means2d, geo, colpack, rx0, ry0, rx1, ry1);
+        __syncthreads();
+        if (npend - nblend >= BL_BATCH) process_block((nblend >> 7) & 1, BL_BATCH);  // at most one block fills per batch
     }
-    if (records != nullptr && threadIdx.x == 0) b2s_bulk_wait_read();  // shared memory must outlive the last store
+    if (!all_done && npend > nblend) {  // the partial block at the end of the list
+        if (records != nullptr && threadIdx.x == 0) b2s_bulk_wait_read();
+        if (!__syncthreads_and(done0 && done1)) process_block((nblend >> 7) & 1, npend - nblend);
+    }
+    if (threadIdx.x == 0) {
+        if (records != nullptr) b2s_bulk_wait_read();  // shared memory must outlive the last store
+        if (tile_blocks != nullptr) tile_blocks[tile] = make_int2(prev_blk, nblocks);
+    }
 
     const float T0 = T.x, T1 = T.y;
     float acc0[CDIM], acc1[CDIM];
@@ -350,8 +385,8 @@ __device__ __forceinline__ void load_pixel_cotangent(size_t pid, const float *__
 // PX = 8: ONE warp per tile -- one butterfly and no cross-warp sum per (tile, Gaussian); PX = 4: two warps.
 template <int CDIM, int DOUT, bool ED, int PX>
 __global__ void __launch_bounds__(256 / PX, PX == 8 ? (CDIM == 4 ? 14 : 10) : (CDIM == 4 ? 10 : 7))
-k_blend_bwd(const int32_t *__restrict__ offsets /* [tiles + 1] */, const float4 *__restrict__ records, int W, int H,
-            int tile_w, const float *__restrict__ render, const float *__restrict__ alpha_in,
+k_blend_bwd(const int2 *__restrict__ tile_blocks /* [tiles]: (last record block, blocks written) */,
+            const float4 *__restrict__ records, int W, int H, int tile_w, const float *__restrict__ render, const float *__restrict__ alpha_in,
             const int32_t *__restrict__ last_ids, const float *__restrict__ v_render,
             const float *__restrict__ v_alpha, float *__restrict__ v_xyabs, float *__restrict__ v_geo,
             float *__restrict__ v_colpack) {
@@ -373,7 +408,7 @@ k_blend_bwd(const int32_t *__restrict__ offsets /* [tiles + 1] */, const float4 
     const int x = tj * 16 + (lane & 15);
     const int ybase = ti * 16 + 2 * PX * warp + PX * (lane >> 4);
     const float px = (float)x + 0.5f;
-    const int start = offsets[tile], end = offsets[tile + 1];
+    const int2 tb = tile_blocks[tile];
 
     float2 T[NP], Tfvra[NP], npy[NP];
     float2 vrc[NP][CDIM], Bv[NP];
@@ -414,26 +449,34 @@ k_blend_bwd(const int32_t *__restrict__ offsets /* [tiles + 1] */, const float4 
     __syncthreads();
 #pragma unroll
     for (int w = 0; w < WARPS; ++w) maxbin = max(maxbin, s_max[w]);
-    const int hi0 = min(end - 1, maxbin);
-    if (hi0 < start) return;  // nothing was blended in this tile (CTA-uniform)
-    const int nblk = ((hi0 - start) >> 7) + 1;
-    const float4 *blk0 = records + blk_index(start, tile, 0) * BL::F4;
+    // ids are tile-local and dense: entry id lives in the tile's block id >> 7.  The forward chained the tile's blocks
+    // (header: entries, previous block); it may have written blocks behind the last contribution: skip them.
+    const int hi0 = maxbin;
+    if (hi0 < 0 || tb.y <= 0) return;  // nothing was blended in this tile (CTA-uniform)
+    const int nblk = (hi0 >> 7) + 1;
+    __shared__ int s_next;
     if (threadIdx.x == 0) {
+        int blk = tb.x;
+        for (int skip = tb.y - nblk; skip > 0; --skip)
+            blk = __float_as_int(__ldg(&records[(size_t)blk * BL::F4 + BL::HDR]).y);
+        s_next = blk;
         b2s_mbar_expect_tx(&s_bar[0], BL::BYTES);
-        b2s_bulk_g2s(s_blk[0], blk0 + (size_t)(nblk - 1) * BL::F4, BL::BYTES, &s_bar[0]);
+        b2s_bulk_g2s(s_blk[0], records + (size_t)blk * BL::F4, BL::BYTES, &s_bar[0]);
     }
 
     for (int k = nblk - 1, it = 0; k >= 0; --k, ++it) {
         const int st = it & 1;
-        // the other buffer was last read in the previous iteration, which ended with a CTA barrier
-        if (threadIdx.x == 0 && k > 0) {
-            b2s_mbar_expect_tx(&s_bar[st ^ 1], BL::BYTES);
-            b2s_bulk_g2s(s_blk[st ^ 1], blk0 + (size_t)(k - 1) * BL::F4, BL::BYTES, &s_bar[st ^ 1]);
-        }
         b2s_mbar_wait(&s_bar[st], (it >> 1) & 1);
+        // the header of the block that just landed names the previous block of the chain: fetch it into the other
+        // buffer (last read in the previous iteration, which ended with a CTA barrier) while this one is processed
+        if (threadIdx.x == 0 && k > 0) {
+            const int prev = __float_as_int(s_blk[st][BL::HDR].y);
+            b2s_mbar_expect_tx(&s_bar[st ^ 1], BL::BYTES);
+            b2s_bulk_g2s(s_blk[st ^ 1], records + (size_t)prev * BL::F4, BL::BYTES, &s_bar[st ^ 1]);
+        }
         const float4 *s_q = s_blk[st], *s_c = s_blk[st] + BL_BATCH, *s_col = s_blk[st] + 2 * BL_BATCH;
-        const int base = start + (k << 7);
-        const int cnt = __float_as_int(s_blk[st][BL::HDR].x);  // entries the forward kept in this block
+        const int base = k << 7;
+        const int cnt = __float_as_int(s_blk[st][BL::HDR].x);  // entries of this block
         const int tmax = min(cnt - 1, hi0 - base);
 
         for (int t1 = tmax; t1 >= 0; t1 = (t1 & ~(FL - 1)) - 1) {  // flush rounds: entries [t0, t1] share s_acc
@@ -518,27 +561,28 @@ k_blend_bwd(const int32_t *__restrict__ offsets /* [tiles + 1] */, const float4 
 // C ABI
 // ------------------------------------------------------------------------------------------------
 template <int CDIM, int DOUT, bool ED>
-static int launch_fwd(const float *means2d, const float *geo, const float *colpack, const int32_t *offsets,
-                      const int32_t *ids, int W, int H, int tile_w, int tile_h, float *render, float *alpha,
-                      int32_t *last_ids, float *records, const int32_t *skip, cudaStream_t st) {
+static int launch_fwd(const float *means2d, const float *geo, const float *colpack, const int32_t *list_off,
+                      const int32_t *items, int ncg, int cg_shift, int W, int H, int tile_w, int tile_h, float *render,
+                      float *alpha, int32_t *last_ids, float *records, unsigned *blk_counter, int32_t *tile_blocks,
+                      const int32_t *skip, cudaStream_t st) {
     k_blend_fwd<CDIM, DOUT, ED><<<tile_w * tile_h, BL_THREADS, 0, st>>>(
-        (const float2 *)means2d, (const float4 *)geo, (const float4 *)colpack, offsets, ids, W, H, tile_w, render, alpha,
-        last_ids, (float4 *)records, skip);
+        (const float2 *)means2d, (const float4 *)geo, (const float4 *)colpack, list_off, (const int2 *)items, ncg,
+        cg_shift, W, H, tile_w, render, alpha, last_ids, (float4 *)records, blk_counter, (int2 *)tile_blocks, skip);
     B2S_LAUNCH_CHECK();
     return B2S_OK;
 }
 template <int CDIM, int DOUT, bool ED>
-static int launch_bwd(const int32_t *offsets, const float *records, int W, int H, int tile_w, int tile_h,
+static int launch_bwd(const int32_t *tile_blocks, const float *records, int W, int H, int tile_w, int tile_h,
                       const float *render, const float *alpha, const int32_t *last_ids, const float *v_render,
                       const float *v_alpha, float *v_xyabs, float *v_geo, float *v_colpack, int px, cudaStream_t st) {
     if (px == 4)
-        k_blend_bwd<CDIM, DOUT, ED, 4><<<tile_w * tile_h, 64, 0, st>>>(offsets, (const float4 *)records, W, H, tile_w,
-                                                                       render, alpha, last_ids, v_render, v_alpha,
-                                                                       v_xyabs, v_geo, v_colpack);
+        k_blend_bwd<CDIM, DOUT, ED, 4><<<tile_w * tile_h, 64, 0, st>>>((const int2 *)tile_blocks, (const float4 *)records,
+                                                                       W, H, tile_w, render, alpha, last_ids, v_render,
+                                                                       v_alpha, v_xyabs, v_geo, v_colpack);
     else
-        k_blend_bwd<CDIM, DOUT, ED, 8><<<tile_w * tile_h, 32, 0, st>>>(offsets, (const float4 *)records, W, H, tile_w,
-                                                                       render, alpha, last_ids, v_render, v_alpha,
-                                                                       v_xyabs, v_geo, v_colpack);
+        k_blend_bwd<CDIM, DOUT, ED, 8><<<tile_w * tile_h, 32, 0, st>>>((const int2 *)tile_blocks, (const float4 *)records,
+                                                                       W, H, tile_w, render, alpha, last_ids, v_render,
+                                                                       v_alpha, v_xyabs, v_geo, v_colpack);
     B2S_LAUNCH_CHECK();
     return B2S_OK;
 }
@@ -566,32 +610,35 @@ static int launch_bwd(const int32_t *offsets, const float *records, int W, int H
         return B2S_ERR_UNSUPPORTED;                                                                \
     } while (0)
 
-extern "C" size_t b2s_blend_record_bytes(long long list_capacity, int n_tiles, int cdim) {
-    if (list_capacity < 0 || n_tiles < 0 || (cdim != 4 && cdim != 8)) return 0;
-    const size_t blocks = (size_t)(list_capacity >> 7) + (size_t)n_tiles + 1;
+extern "C" size_t b2s_blend_record_bytes(long long pair_capacity, int n_tiles, int cdim) {
+    if (pair_capacity < 0 || n_tiles < 0 || (cdim != 4 && cdim != 8)) return 0;
+    // blocks are packed densely per tile: at most ceil(kept / 128) per tile, kept <= (Gaussian, tile) pairs in total
+    const size_t blocks = (size_t)(pair_capacity >> 7) + (size_t)n_tiles + 1;
     return blocks * ((size_t)BL_BATCH * (size_t)(2 + cdim / 4) + 1) * 16;  // + header
 }
 
-extern "C" int b2s_blend_fwd(const float *means2d, const float *geo, const float *colpack,
-                             const int32_t *tile_offsets, const int32_t *tile_ids, int W, int H, int tile_w, int tile_h,
+extern "C" int b2s_blend_fwd(const float *means2d, const float *geo, const float *colpack, const int32_t *list_offsets,
+                             const int32_t *list_items, int ncg, int cg_shift, int W, int H, int tile_w, int tile_h,
                              int cdim, int d_out, int expected_depth, float *render, float *alpha, int32_t *last_ids,
-                             float *records, const int32_t *skip_flag, b2s_stream_t stream) {
-    if (W <= 0 || H <= 0 || tile_w * 16 < W || tile_h * 16 < H) return B2S_ERR_ARG;
-    if (records != nullptr && ((uintptr_t)records & 127)) return B2S_ERR_ARG;
+                             float *records, uint32_t *block_counter, int32_t *tile_blocks, const int32_t *skip_flag,
+                             b2s_stream_t stream) {
+    if (W <= 0 || H <= 0 || tile_w * 16 < W || tile_h * 16 < H || ncg < 1 || cg_shift < 0) return B2S_ERR_ARG;
+    if (records != nullptr && (((uintptr_t)records & 127) || !block_counter || !tile_blocks)) return B2S_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    B2S_DISPATCH(launch_fwd, means2d, geo, colpack, tile_offsets, tile_ids, W, H, tile_w, tile_h, render, alpha, last_ids,
-                 records, skip_flag, st);
+    B2S_DISPATCH(launch_fwd, means2d, geo, colpack, list_offsets, list_items, ncg, cg_shift, W, H, tile_w, tile_h, render,
+                 alpha, last_ids, records, block_counter, tile_blocks, skip_flag, st);
 }
 
-extern "C" int b2s_blend_bwd(const int32_t *tile_offsets, const float *records, int W, int H, int tile_w, int tile_h,
+extern "C" int b2s_blend_bwd(const int32_t *tile_blocks, const float *records, int W, int H, int tile_w, int tile_h,
                              int cdim, int d_out, int expected_depth, const float *render, const float *alpha,
                              const int32_t *last_ids, const float *v_render, const float *v_alpha, float *v_xyabs,
                              float *v_geo, float *v_colpack, int px_per_thread, b2s_stream_t stream) {
-    if (W <= 0 || H <= 0 || tile_w * 16 < W || tile_h * 16 < H || records == nullptr) return B2S_ERR_ARG;
+    if (W <= 0 || H <= 0 || tile_w * 16 < W || tile_h * 16 < H || records == nullptr || tile_blocks == nullptr)
+        return B2S_ERR_ARG;
     if ((uintptr_t)records & 127) return B2S_ERR_ARG;
     if (px_per_thread != 0 && px_per_thread != 4 && px_per_thread != 8) return B2S_ERR_UNSUPPORTED;
     const int px = px_per_thread == 0 ? B2S_BWD_PX : px_per_thread;
     cudaStream_t st = (cudaStream_t)stream;
-    B2S_DISPATCH(launch_bwd, tile_offsets, records, W, H, tile_w, tile_h, render, alpha, last_ids, v_render, v_alpha,
+    B2S_DISPATCH(launch_bwd, tile_blocks, records, W, H, tile_w, tile_h, render, alpha, last_ids, v_render, v_alpha,
                  v_xyabs, v_geo, v_colpack, px, st);
 }

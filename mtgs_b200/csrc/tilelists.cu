@@ -483,8 +483,9 @@ static int tl_run_level(const TlGeom &g, const TlLayout &L, char *w, const int32
 extern "C" int b2s_bin_tiles(const int32_t *tile_rects, const int32_t *order, const int32_t *n_vis,
                              const long long *totals_host, int N, int tile_size, int tile_w, int tile_h, int W, int H,
                              const float *means2d, const float *geo, int offsets_with_total, int32_t *overflow,
-                             int32_t *flatten_ids, int32_t *isect_offsets, void *workspace, size_t workspace_bytes,
-                             b2s_stream_t stream) {
+                             int levels, int32_t *flatten_ids, int32_t *isect_offsets, void *workspace,
+                             size_t workspace_bytes, b2s_stream_t stream) {
+    if (levels != 3 && levels != 4) return B2S_ERR_ARG;
     if (N < 0 || !totals_host || tile_w <= 0 || tile_h <= 0) return B2S_ERR_ARG;
     if ((means2d == nullptr) != (geo == nullptr)) return B2S_ERR_ARG;
     if (means2d != nullptr && (W <= 0 || H <= 0 || tile_w * 16 < W || tile_h * 16 < H)) return B2S_ERR_ARG;
@@ -504,7 +505,10 @@ extern "C" int b2s_bin_tiles(const int32_t *tile_rects, const int32_t *order, co
     cudaStream_t st = (cudaStream_t)stream;
     const int T = tile_w * tile_h;
     if (M == 0 || N == 0) {
-        cudaMemsetAsync(isect_offsets, 0, sizeof(int32_t) * (size_t)(T + (g.offs_total ? 1 : 0)), st);
+        if (levels == 3)  // every (row, column-group) list is empty
+            cudaMemsetAsync((char *)workspace + L.out_off[3], 0, sizeof(int32_t) * ((size_t)L.nl[3] * L.nb[3] + 1), st);
+        else
+            cudaMemsetAsync(isect_offsets, 0, sizeof(int32_t) * (size_t)(T + (g.offs_total ? 1 : 0)), st);
         return B2S_OK;
     }
     const float2 *m2 = (const float2 *)means2d;
@@ -515,7 +519,25 @@ extern "C" int b2s_bin_tiles(const int32_t *tile_rects, const int32_t *order, co
     if ((rc = tl_run_level<1>(g, L, w, order, rects, n_vis, flatten_ids, isect_offsets, m2, ge, st)) != B2S_OK) return rc;
     if ((rc = tl_run_level<2>(g, L, w, order, rects, n_vis, flatten_ids, isect_offsets, m2, ge, st)) != B2S_OK) return rc;
     if ((rc = tl_run_level<3>(g, L, w, order, rects, n_vis, flatten_ids, isect_offsets, m2, ge, st)) != B2S_OK) return rc;
+    if (levels == 3) return B2S_OK;  // the caller walks the (row, column-group) lists itself (b2s_bin_tiles_l3_view)
     if ((rc = tl_run_level<4>(g, L, w, order, rects, n_vis, flatten_ids, isect_offsets, m2, ge, st)) != B2S_OK) return rc;
+    return B2S_OK;
+}
+
+// Where the output of level 3 lives inside the workspace of a build with the same totals: items = int2 (Gaussian id,
+// tile-column range x0 | x1 << 16) of the (tile row y, column group c) lists, list index y * ncg + c; offsets = int32
+// [nlists + 1].  Tile (y, x) belongs to list y * ncg + (x >> cg_shift) and is covered by an item iff x0 <= x < x1.
+extern "C" int b2s_bin_tiles_l3_view(const long long *totals_host, int tile_w, int tile_h, size_t *items_byte_offset,
+                                     size_t *offsets_byte_offset, int *nlists, int *ncg, int *cg_shift) {
+    TlGeom g = {};
+    TlLayout L;
+    if (!totals_host || !items_byte_offset || !offsets_byte_offset || !nlists || !ncg || !cg_shift) return B2S_ERR_ARG;
+    if (!tl_layout(totals_host, tile_w, tile_h, g, L)) return B2S_ERR_UNSUPPORTED;
+    *items_byte_offset = L.out[3];
+    *offsets_byte_offset = L.out_off[3];
+    *nlists = L.nl[3] * L.nb[3];
+    *ncg = g.ncg;
+    *cg_shift = g.cg_shift;
     return B2S_OK;
 }
 

@@ -117,7 +117,7 @@ class _Project(torch.autograd.Function):
         keys = torch.empty(N, dtype=torch.int32, device=dev)
         rects = torch.empty(N, 2, dtype=torch.int32, device=dev)
         tight = torch.empty(N, 2, dtype=torch.int32, device=dev)
-        totals = torch.zeros(6, dtype=torch.int64, device=dev)  # 5 list sizes + the capacity-overflow word
+        totals = torch.zeros(8, dtype=torch.int64, device=dev)  # 5 list sizes, capacity-overflow word, record-block counter
         # accumulation buffers of the blend backward (v_xyabs | v_geo | v_colpack), zero-filled by the kernel
         arena = torch.empty(N * (8 + cdim) if want_arena else 0, dtype=torch.float32, device=dev)
         with _timed("project_fwd"):
@@ -202,22 +202,25 @@ class _Blend(torch.autograd.Function):
     exactly as with upstream (mtgs_scene_graph.py:666-667, 1171-1174)."""
 
     @staticmethod
-    def forward(ctx, means2d, geo, colpack, offsets, ids, arena, W, H, tile_w, tile_h, cdim, d_out, ed, absgrad,
-                skip_ptr=None):
+    def forward(ctx, means2d, geo, colpack, lists, arena, W, H, tile_w, tile_h, cdim, d_out, ed, absgrad, pair_cap,
+                counter_ptr, skip_ptr=None):
         lib = _lib.load()
         dev = means2d.device
+        ws, items_ptr, offs_ptr, ncg, cg_shift = lists  # (row, column-group) lists inside the tile-list workspace
         render = torch.empty(1, H, W, d_out, dtype=torch.float32, device=dev)
         alpha = torch.empty(1, H, W, 1, dtype=torch.float32, device=dev)
         last_ids = torch.empty(H, W, dtype=torch.int32, device=dev)
-        records = None
+        records = tile_blocks = None
         if arena.numel() > 0:  # a backward may follow: keep the walk records
-            nbytes = int(lib.b2s_blend_record_bytes(ids.numel(), tile_w * tile_h, cdim))
+            nbytes = int(lib.b2s_blend_record_bytes(pair_cap, tile_w * tile_h, cdim))
             records = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+            tile_blocks = torch.empty(tile_h * tile_w, 2, dtype=torch.int32, device=dev)
         with _timed("blend_fwd"):
-            _lib.check(lib.b2s_blend_fwd(_ptr(means2d), _ptr(geo), _ptr(colpack), _ptr(offsets), _ptr(ids), W, H,
+            _lib.check(lib.b2s_blend_fwd(_ptr(means2d), _ptr(geo), _ptr(colpack), offs_ptr, items_ptr, ncg, cg_shift, W, H,
                                          tile_w, tile_h, cdim, d_out, int(ed), _ptr(render), _ptr(alpha),
-                                         _ptr(last_ids), _ptr(records), skip_ptr, _stream()), "b2s_blend_fwd")
-        ctx.save_for_backward(means2d, offsets, render, alpha, last_ids, records, arena)
+                                         _ptr(last_ids), _ptr(records), counter_ptr, _ptr(tile_blocks), skip_ptr,
+                                         _stream()), "b2s_blend_fwd")
+        ctx.save_for_backward(means2d, render, alpha, last_ids, records, tile_blocks, arena)
         ctx.cfg = (W, H, tile_w, tile_h, cdim, d_out, ed, absgrad, geo.shape[0])
         ctx.set_materialize_grads(False)
         ctx.arena_clean = True
@@ -227,7 +230,7 @@ class _Blend(torch.autograd.Function):
     @staticmethod
     def backward(ctx, v_render, v_alpha, _v_last=None):
         lib = _lib.load()
-        means2d, offsets, render, alpha, last_ids, records, arena = ctx.saved_tensors
+        means2d, render, alpha, last_ids, records, tile_blocks, arena = ctx.saved_tensors
         W, H, tile_w, tile_h, cdim, d_out, ed, absgrad, N = ctx.cfg
         if records is None:
             raise RuntimeError("rasterization was run without gradient tracking; no backward is possible")
@@ -242,14 +245,14 @@ class _Blend(torch.autograd.Function):
         v_colpack = arena[8 * N:].view(N, cdim)
         if N > 0:
             with _timed("blend_bwd"):
-                _lib.check(lib.b2s_blend_bwd(_ptr(offsets), _ptr(records), W, H, tile_w, tile_h, cdim, d_out, int(ed),
+                _lib.check(lib.b2s_blend_bwd(_ptr(tile_blocks), _ptr(records), W, H, tile_w, tile_h, cdim, d_out, int(ed),
                                              _ptr(render), _ptr(alpha), _ptr(last_ids), _ptr(v_render), _ptr(v_alpha),
                                              _ptr(v_xyabs), _ptr(v_geo), _ptr(v_colpack), BWD_PX, _stream()),
                            "b2s_blend_bwd")
         if absgrad:
             # upstream: `means2d.absgrad = v_means2d_abs` on the tensor object handed in by the caller
             means2d.absgrad = v_xyabs[:, 2:4].unsqueeze(0)
-        return (v_xyabs[:, 0:2].unsqueeze(0), v_geo, v_colpack) + (None,) * 12
+        return (v_xyabs[:, 0:2].unsqueeze(0), v_geo, v_colpack) + (None,) * 13
 
 
 # ------------------------------------------------------------------------------------------------
@@ -268,7 +271,7 @@ def _start_totals_readback(totals: Tensor):
     dev = totals.device
     slot = _PINNED_TOTALS.get(dev.index)
     if slot is None:
-        slot = _PINNED_TOTALS[dev.index] = (torch.zeros(6, dtype=torch.int64).pin_memory(), torch.cuda.Event())
+        slot = _PINNED_TOTALS[dev.index] = (torch.zeros(8, dtype=torch.int64).pin_memory(), torch.cuda.Event())
     host, ev = slot
     host.copy_(totals, non_blocking=True)
     ev.record()
@@ -291,26 +294,37 @@ def _sort_depth(keys: Tensor):
 
 
 def _tile_lists(rects: Tensor, order: Tensor, n_vis: Tensor, sizes, tile_w: int, tile_h: int, W: int, H: int,
-                walk: bool, overflow_ptr=None) -> Tuple[Tensor, Tensor]:
-    """Per-tile depth-ordered lists over ``rects``.  ``walk``: the blend's own lists (tight rectangles; offsets carry a
-    trailing total so that no host-side count is needed); otherwise upstream's lists over the 3-sigma rectangles.
-    ``sizes`` = (list length, S, E1, E3, n_vis): the exact sizes summed by the projection kernel for ``rects``, or --
-    with ``overflow_ptr`` (capacity mode) -- capacities."""
+                walk: bool, overflow_ptr=None):
+    """Depth-ordered lists over ``rects``.  ``walk``: the lists the blend walks -- the build stops at the (tile row,
+    column group) level and the blend applies the last filter level lazily; returns (workspace, items pointer, offsets
+    pointer, ncg, cg_shift).  Otherwise upstream's per-tile lists over the 3-sigma rectangles: (flatten_ids,
+    isect_offsets).  ``sizes`` = (list length, S, E1, E3, n_vis): the exact sizes summed for ``rects``, or -- with
+    ``overflow_ptr`` (capacity mode) -- capacities."""
     lib = _lib.load()
     dev = rects.device
     N = rects.shape[0]
     tot = (C.c_longlong * 5)(*sizes)
-    ids = torch.empty(sizes[0], dtype=torch.int32, device=dev)
-    offsets = torch.empty(tile_h * tile_w + (1 if walk else 0), dtype=torch.int32, device=dev)
     wsb = int(lib.b2s_bin_tiles_workspace_bytes(tot, tile_w, tile_h))
     if wsb == 0:
         raise NotImplementedError(f"tile grid {tile_w}x{tile_h} not supported")
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    if walk:
+        ids = offsets = None
+    else:
+        ids = torch.empty(sizes[0], dtype=torch.int32, device=dev)
+        offsets = torch.empty(tile_h * tile_w, dtype=torch.int32, device=dev)
     with _timed("bin_tiles" if walk else "bin_tiles_upstream_lists"):
         _lib.check(lib.b2s_bin_tiles(_ptr(rects), _ptr(order), _ptr(n_vis), tot, N, 16, tile_w, tile_h, W, H,
-                                     None, None, int(walk), overflow_ptr, _ptr(ids), _ptr(offsets), _ptr(ws), wsb,
-                                     _stream()), "b2s_bin_tiles")
-    return ids, offsets
+                                     None, None, 0, overflow_ptr, 3 if walk else 4, _ptr(ids), _ptr(offsets), _ptr(ws),
+                                     wsb, _stream()), "b2s_bin_tiles")
+    if not walk:
+        return ids, offsets
+    io, oo = C.c_size_t(), C.c_size_t()
+    nl, ncg, cgs = C.c_int(), C.c_int(), C.c_int()
+    _lib.check(lib.b2s_bin_tiles_l3_view(tot, tile_w, tile_h, C.byref(io), C.byref(oo), C.byref(nl), C.byref(ncg),
+                                         C.byref(cgs)), "b2s_bin_tiles_l3_view")
+    base = ws.data_ptr()
+    return ws, C.c_void_p(base + io.value), C.c_void_p(base + oo.value), ncg.value, cgs.value
 
 
 def _isect_ids(offsets: Tensor, flatten_ids: Tensor, depths: Tensor) -> Tensor:
@@ -345,24 +359,28 @@ def _rasterize_one(means, quats, scales, opacities, colors, viewmat, K, width, h
     key = (means.device.index, tile_w, tile_h)
     caps = _CAPACITY.get(key)
 
+    counter = C.c_void_p(totals.data_ptr() + 48)  # record-block bump allocator (zeroed with the totals)
+
     def build(sizes, overflow_ptr):
-        # the lists the blend walks: tight rectangles (the exact per-tile test runs lazily while the blend stages a batch)
-        ids, offs = _tile_lists(tight, order, n_vis, sizes, tile_w, tile_h, width, height, True, overflow_ptr)
-        return (ids, offs) + tuple(_Blend.apply(means2d, geo, colpack, offs, ids, arena, width, height, tile_w, tile_h,
-                                                cdim, d_out, ed, bool(absgrad), overflow_ptr))
+        # (tile row, column group) lists over the tight rectangles; the blend applies the last filter level and the
+        # exact per-tile test lazily while it walks
+        lists = _tile_lists(tight, order, n_vis, sizes, tile_w, tile_h, width, height, True, overflow_ptr)
+        return _Blend.apply(means2d, geo, colpack, lists, arena, width, height, tile_w, tile_h, cdim, d_out, ed,
+                            bool(absgrad), sizes[0], counter, overflow_ptr)
 
     if caps is None or SYNC_SIZES or N == 0:
         ev.synchronize()
         tot = [int(v) for v in host.tolist()[:5]]
-        walk_ids, walk_offsets, render, alpha, last_ids = build(tuple(tot), None)
+        render, alpha, last_ids = build(tuple(tot), None)
     else:
         # capacity mode: everything is enqueued before this frame's sizes are known; they are checked afterwards
         flag = C.c_void_p(totals.data_ptr() + 40)
-        walk_ids, walk_offsets, render, alpha, last_ids = build((caps[0], caps[1], caps[2], caps[3], N), flag)
+        render, alpha, last_ids = build((caps[0], caps[1], caps[2], caps[3], N), flag)
         ev.synchronize()
         tot = [int(v) for v in host.tolist()[:5]]
         if any(tot[i] > caps[i] for i in range(4)):  # rare: rebuild with the exact sizes
-            walk_ids, walk_offsets, render, alpha, last_ids = build(tuple(tot), None)
+            totals[6] = 0  # (stream-ordered) reset of the record-block counter
+            render, alpha, last_ids = build(tuple(tot), None)
     if caps is None:
         caps = _CAPACITY[key] = [0, 0, 0, 0]
     for i in range(4):
@@ -370,7 +388,7 @@ def _rasterize_one(means, quats, scales, opacities, colors, viewmat, K, width, h
     # keys with a leading underscore are not part of upstream's info dict (bench.py reads them for K_pairs)
     meta = dict(radii=radii.unsqueeze(0), means2d=means2d, depths=depths.unsqueeze(0),
                 conics=geo.detach()[:, :3].unsqueeze(0), opacities=geo.detach()[:, 3].unsqueeze(0),
-                tiles_per_gauss=tiles.unsqueeze(0), _last_ids=last_ids, _walk_ids=walk_ids, _walk_offsets=walk_offsets)
+                tiles_per_gauss=tiles.unsqueeze(0), _last_ids=last_ids, _tight_rects=tight)
 
     def upstream_lists(_key):
         """upstream's flatten_ids / isect_offsets / isect_ids, on demand (bit-identical to the 64-bit sort)."""

@@ -148,34 +148,25 @@ def test_backward_parity(oracle, cuda_device, scene, mode, rmode, d_in):
 
 
 @pytest.mark.parametrize("scene", ["tiny_ragged", "config1", "street20k", "street20k_540p"])
-def test_walk_lists_are_upstream_lists_minus_dead_pairs(cuda_device, scene):
-    """The lists the blend kernels walk (tight rectangles + exact per-tile test) must be upstream's (tile, depth)-sorted
-    lists with ONLY non-contributing pairs removed: same order, and every pair that reaches alpha >= 1/255 at some pixel
-    centre of its tile (brute force in float64 over all 256 pixels) is present."""
+def test_tight_rectangles_hold_every_contributing_pair(cuda_device, scene):
+    """The blend's lists are built from TIGHT rectangles (upstream's 3-sigma rectangle intersected with the extents of
+    the footprint alpha >= 1/255).  Every (Gaussian, tile) pair of upstream's lists that reaches alpha >= 1/255 at some
+    pixel centre of its tile (brute force in float64 over all 256 pixels) must lie inside the Gaussian's tight
+    rectangle; and the tight rectangles must actually be tighter."""
     s = SCENES[scene]()
     t = _to_dev(s, cuda_device)
     W, H, N = s["width"], s["height"], s["means"].shape[0]
     with torch.no_grad():
         _, _, meta = _gpu_raster(t, s, render_mode="RGB+ED", rasterize_mode="antialiased")
     dev = cuda_device
-    tw, th = meta["tile_width"], meta["tile_height"]
+    tw = meta["tile_width"]
     flat, offs = meta["flatten_ids"].long(), meta["isect_offsets"].reshape(-1).long()
     M = flat.numel()
-    w_offs = meta["_walk_offsets"].long()
-    Mw = int(w_offs[-1])
-    w_ids = meta["_walk_ids"].long()[:Mw]
-    assert w_offs.numel() == tw * th + 1 and bool((w_offs[1:] >= w_offs[:-1]).all()) and int(w_offs[0]) == 0
     tile_up = torch.searchsorted(offs, torch.arange(M, device=dev), right=True) - 1
-    tile_wk = torch.searchsorted(w_offs[:-1].contiguous(), torch.arange(Mw, device=dev), right=True) - 1
-    key_up, key_wk = tile_up * N + flat, tile_wk * N + w_ids
-    # subsequence: every walked pair exists upstream, and positions in upstream's list increase along the walk list
-    srt, perm = torch.sort(key_up)
-    at = torch.searchsorted(srt, key_wk).clamp(max=M - 1)
-    assert bool((srt[at] == key_wk).all()), "walk list holds a pair upstream's list does not"
-    pos = perm[at]
-    assert bool((pos[1:] > pos[:-1]).all()), "walk list is not in upstream's (tile, depth, id) order"
-    in_walk = torch.zeros(M, dtype=torch.bool, device=dev)
-    in_walk[pos] = True
+    tr = meta["_tight_rects"].long()
+    x0, x1, y0, y1 = tr[:, 0] & 0xffff, (tr[:, 0] >> 16) & 0xffff, tr[:, 1] & 0xffff, (tr[:, 1] >> 16) & 0xffff
+    tx, ty = tile_up % tw, tile_up // tw
+    inside = (tx >= x0[flat]) & (tx < x1[flat]) & (ty >= y0[flat]) & (ty < y1[flat])
     # brute force: best alpha of every upstream pair over the pixel centres of its tile
     m2 = meta["means2d"][0].double()
     con = meta["conics"][0].double()
@@ -196,27 +187,12 @@ def test_walk_lists_are_upstream_lists_minus_dead_pairs(cuda_device, scene):
         best[lo:hi] = al.max(dim=1).values
     must = best >= (1.0 / 255.0) * (1 + 1e-3)
     assert int(must.sum()) > 0
-    missing = must & ~in_walk
-    assert int(missing.sum()) == 0, f"{int(missing.sum())} contributing pairs were dropped (best alpha up to {float(best[missing].max()):.4f})"
-    # tightness (informational bound): the tight rectangles alone already remove a good part of the dead pairs; the
-    # exact per-tile test runs later, lazily, while the blend stages a batch
-    dead_kept = in_walk & (best < (1.0 / 255.0) * (1 - 2e-2))
-    assert float(dead_kept.sum()) <= 0.6 * Mw + 8, (int(dead_kept.sum()), Mw)
-    assert Mw < M
-
-
-@pytest.mark.parametrize("px", [4, 8])
-def test_backward_variants_agree_with_the_oracle(oracle, cuda_device, px):
-    """Both builds of the blend backward (4 and 8 pixels per thread) against the oracle, CDIM 4 and 8."""
-    from mtgs_b200 import rendering
-    old = rendering.BWD_PX
-    rendering.BWD_PX = px
-    try:
-        for d_in in (3, 6):
-            test_backward_parity(oracle, cuda_device, "street20k", "antialiased", "RGB+ED", d_in)
-            test_backward_parity(oracle, cuda_device, "tiny_ragged", "antialiased", "RGB+ED", d_in)
-    finally:
-        rendering.BWD_PX = old
+    missing = must & ~inside
+    assert int(missing.sum()) == 0, f"{int(missing.sum())} contributing pairs fall outside the tight rectangles (best alpha up to {float(best[missing].max()):.4f})"
+    n_in = int(inside.sum())
+    assert n_in < M, "tight rectangles are not tighter than upstream's"
+    dead_kept = inside & (best < (1.0 / 255.0) * (1 - 2e-2))
+    assert float(dead_kept.sum()) <= 0.6 * n_in + 8, (int(dead_kept.sum()), n_in)
 
 
 def test_capacity_mode_equals_exact_sizes_and_survives_overflow(cuda_device):
@@ -239,8 +215,6 @@ def test_capacity_mode_equals_exact_sizes_and_survives_overflow(cuda_device):
         with torch.no_grad():
             r1, a1, m1 = _gpu_raster(t, s, **kw)          # capacity mode, capacities sufficient
         assert torch.equal(r0, r1) and torch.equal(a0, a1)
-        n_walk = int(m1["_walk_offsets"][-1])
-        assert m1["_walk_ids"].numel() >= n_walk and torch.equal(m1["_walk_ids"][:n_walk], m0["_walk_ids"][:n_walk])
         for lvl in range(4):                              # every level's capacity too small in turn
             caps = list(rendering._CAPACITY[key])
             small = list(caps)
