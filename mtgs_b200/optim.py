@@ -44,7 +44,8 @@ class FusedAdam(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._chunk = int(_lib.load().b2s_adam_chunk())
         self._layout_key = None
-        self._chunk_tensor = self._chunk_start = self._desc_dev = self._desc_host = None
+        self._chunk_tensor = self._chunk_start = None
+        self._ring, self._ring_pos = [], 0
 
     def _tensors(self):
         out = []
@@ -97,14 +98,23 @@ class FusedAdam(torch.optim.Optimizer):
                     cs.append(s)
             self._chunk_tensor = torch.tensor(ct, dtype=torch.int32, device=dev)
             self._chunk_start = torch.tensor(cs, dtype=torch.int64, device=dev)
-            self._desc_host = torch.empty(C.sizeof(_AdamTensor) * len(key), dtype=torch.uint8).pin_memory()
-            self._desc_dev = torch.empty(C.sizeof(_AdamTensor) * len(key), dtype=torch.uint8, device=dev)
+            # the descriptor table changes every step (bias corrections, learning rates) and travels through pinned
+            # memory asynchronously: a ring of staging slots, each guarded by an event, so that a slot is never
+            # rewritten before its copy has been executed (the host runs ahead of the device)
+            nbytes = C.sizeof(_AdamTensor) * len(key)
+            self._ring = [(torch.empty(nbytes, dtype=torch.uint8).pin_memory(),
+                           torch.empty(nbytes, dtype=torch.uint8, device=dev), torch.cuda.Event()) for _ in range(4)]
+            self._ring_pos = 0
             self._layout_key = key
-        C.memmove(self._desc_host.data_ptr(), C.addressof(descs), C.sizeof(descs))
-        self._desc_dev.copy_(self._desc_host, non_blocking=True)
+        host, desc_dev, ev = self._ring[self._ring_pos]
+        self._ring_pos = (self._ring_pos + 1) % len(self._ring)
+        ev.synchronize()  # no-op unless the device is more than a ring's worth of steps behind
+        C.memmove(host.data_ptr(), C.addressof(descs), C.sizeof(descs))
         with torch.cuda.device(dev):
-            _lib.check(lib.b2s_adam_multi(_ptr(self._desc_dev), _ptr(self._chunk_tensor), _ptr(self._chunk_start),
+            desc_dev.copy_(host, non_blocking=True)
+            _lib.check(lib.b2s_adam_multi(_ptr(desc_dev), _ptr(self._chunk_tensor), _ptr(self._chunk_start),
                                           int(self._chunk_tensor.numel()), _stream()), "b2s_adam_multi")
+            ev.record()
         for p, _ in items:
             self.state[p].pop("_grad_keepalive", None)
         return loss
