@@ -276,7 +276,7 @@ int b2s_arena_bwd(const float *means, const float *scales_raw, const float *quat
  * cull / split / duplicate steps of :476-699.
  * b2s_adam_multi: ONE launch steps every tensor: tensors_dev = device array of descriptors, chunk c of
  *   b2s_adam_chunk() elements belongs to tensor chunk_tensor_dev[c] and starts at element chunk_start_dev[c].
- *   Arithmetic = torch.optim.Adam (no amsgrad): bias_correction{1,2} = 1 - beta^step, computed by the host.
+ *   Arithmetic = torch.optim.Adam (no amsgrad); the step-dependent scalars are computed by the host in double.
  * b2s_densify_stats: for radii > 0: xys_grad_norm += ||grad2d * (W, H) / 2||, vis_counts += 1, max_2dsize =
  *   max(max_2dsize, radii)   (grad2d rows have grad_stride floats: 2, or 4 for the blend's (xy, |xy|) arena).
  * b2s_mask_scan + b2s_mask_gather_rows: order-preserving compaction of [N, row_floats] rows by a uint8 keep mask;
@@ -288,7 +288,9 @@ typedef struct B2sAdamTensor {
     float *m;
     float *v;
     long long n;
-    float lr, beta1, beta2, eps, weight_decay, bias_correction1, bias_correction2, _pad;
+    float lr, beta1, beta2, eps, weight_decay;
+    /* scalars torch.optim.Adam forms in double on the host: lr / (1 - beta1^t), sqrt(1 - beta2^t), 1 - beta1, 1 - beta2 */
+    float step_size, bias_correction2_sqrt, one_minus_beta1, one_minus_beta2, _pad;
 } B2sAdamTensor;
 int b2s_adam_chunk(void);
 int b2s_adam_multi(const B2sAdamTensor *tensors_dev, const int32_t *chunk_tensor_dev,

@@ -24,13 +24,13 @@ k_adam_multi(const B2sAdamTensor *__restrict__ tensors, const int32_t *__restric
     const B2sAdamTensor t = tensors[chunk_tensor[blockIdx.x]];
     const long long s0 = chunk_start[blockIdx.x];
     const long long s1 = s0 + OP_CHUNK < t.n ? s0 + OP_CHUNK : t.n;
-    const float b1 = t.beta1, b2 = t.beta2, ob1 = 1.0f - b1, ob2 = 1.0f - b2;
-    const float step_size = t.lr / t.bias_correction1, inv_sqrt_bc2 = 1.0f / sqrtf(t.bias_correction2);
+    const float b2 = t.beta2, ob1 = t.one_minus_beta1, ob2 = t.one_minus_beta2;
+    const float step_size = t.step_size, bc2_sqrt = t.bias_correction2_sqrt;
     auto upd = [&](float &p, float g, float &m, float &v) {
         if (t.weight_decay != 0.f) g += t.weight_decay * p;
         m = m + (g - m) * ob1;            // torch: exp_avg.lerp_(grad, 1 - beta1)
         v = v * b2 + ob2 * g * g;          // torch: exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
-        const float denom = sqrtf(v) * inv_sqrt_bc2 + t.eps;
+        const float denom = sqrtf(v) / bc2_sqrt + t.eps;  // torch: (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
         p = p - step_size * (m / denom);   // torch: param.addcdiv_(exp_avg, denom, value=-step_size)
     };
     const bool vec = (((uintptr_t)t.p | (uintptr_t)t.g | (uintptr_t)t.m | (uintptr_t)t.v) & 15) == 0;

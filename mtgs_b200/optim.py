@@ -30,8 +30,8 @@ from .rendering import _need_cuda, _ptr, _stream
 class _AdamTensor(C.Structure):  # mirrors B2sAdamTensor in include/b200splat.h
     _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("n", C.c_longlong),
                 ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
-                ("weight_decay", C.c_float), ("bias_correction1", C.c_float), ("bias_correction2", C.c_float),
-                ("_pad", C.c_float)]
+                ("weight_decay", C.c_float), ("step_size", C.c_float), ("bias_correction2_sqrt", C.c_float),
+                ("one_minus_beta1", C.c_float), ("one_minus_beta2", C.c_float), ("_pad", C.c_float)]
 
 
 class FusedAdam(torch.optim.Optimizer):
@@ -86,7 +86,9 @@ class FusedAdam(torch.optim.Optimizer):
             d = descs[i]
             d.p, d.g, d.m, d.v, d.n = p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel()
             d.lr, d.beta1, d.beta2, d.eps, d.weight_decay = group["lr"], b1, b2, group["eps"], group["weight_decay"]
-            d.bias_correction1, d.bias_correction2 = 1.0 - b1 ** st["step"], 1.0 - b2 ** st["step"]
+            d.step_size = group["lr"] / (1.0 - b1 ** st["step"])
+            d.bias_correction2_sqrt = (1.0 - b2 ** st["step"]) ** 0.5
+            d.one_minus_beta1, d.one_minus_beta2 = 1.0 - b1, 1.0 - b2
             key.append(p.numel())
             st["_grad_keepalive"] = g
         key = tuple(key)
