@@ -641,6 +641,13 @@ def main():
         if k in stage_ms:
             gbs = stage_bytes[k] / (stage_ms[k] * 1e-3) / 1e9
             hbm_stages[k] = {"ms": stage_ms[k], "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peak}
+            try:  # DRAM bytes the kernel really moves (ncu capture under profiles/, static) over this run's time
+                tb = json.load(open(tpath)).get(k)
+                if tb:
+                    hbm_stages[k]["dram_traffic_bytes_ncu"] = tb
+                    hbm_stages[k]["dram_frac_of_hbm_peak"] = tb / (stage_ms[k] * 1e-3) / 1e9 / peak
+            except Exception:
+                pass
     try:
         from mtgs_b200.cuda._wrapper import spherical_harmonics
         K_sh = 16
