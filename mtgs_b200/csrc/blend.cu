@@ -128,13 +128,13 @@ k_blend_fwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
     const unsigned lt = lanemask_lt();
 
     // the thread's two pixels are the halves of every float2 below
-    float2 T = make_float2(1.f, 1.f);
+    float2 T = make_float2(in0 ? 1.f : 0.f, in1 ? 1.f : 0.f);  // 0 = finished (terminated, or outside the image)
+    float2 Tout = make_float2(1.f, 1.f);
     float2 acc[CDIM];
 #pragma unroll
     for (int k = 0; k < CDIM; ++k) acc[k] = make_float2(0.f, 0.f);
     const float2 npy = make_float2(-((float)y0 + 0.5f), -((float)y0 + 1.5f));
     int cur0 = 0, cur1 = 0;
-    bool done0 = !in0, done1 = !in1;
     int npend = 0;    // kept entries appended so far (CTA-uniform)
     int nblend = 0;   // entries blended so far = 128 x blocks finished
     int prev_blk = -1, nblocks = 0;  // chain of this tile's record blocks (meaningful in thread 0)
@@ -156,6 +156,9 @@ k_blend_fwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
                 b2s_bulk_commit();
             }
         }
+        // Branch-free inner loop.  A pixel that has terminated (T' <= 1e-4 at some entry) carries T = 0 from then on:
+        // every later entry gives T' = 0, is "not applied" and adds exact zeros, so no per-pixel done flag is tested
+        // here; Tout keeps the transmittance behind the last applied entry (what alpha is computed from).
 #pragma unroll 2
         for (int t = 0; t < cnt; ++t) {
             const float4 sq = s_q[t];
@@ -165,29 +168,27 @@ k_blend_fwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
             const float2 p = splat_power2(sq.z, sq.w, sc.x, dx, dy);
             const float2 ov = mul2(bc2(sc.y), make_float2(ex2_approx(-p.x), ex2_approx(-p.y)));
             const float2 al = make_float2(fminf(B2S_ALPHA_MAX, ov.x), fminf(B2S_ALPHA_MAX, ov.y));
-            const bool ok0 = !done0 && p.x >= 0.f && al.x >= B2S_ALPHA_MIN;
-            const bool ok1 = !done1 && p.y >= 0.f && al.y >= B2S_ALPHA_MIN;
-            if (ok0 || ok1) {
-                const float2 nT = mul2(T, fma2(al, bc2(-1.0f), bc2(1.0f)));  // T (1 - alpha)
-                float2 vis = mul2(al, T);
-                const bool ap0 = ok0 && nT.x > B2S_T_EPS, ap1 = ok1 && nT.y > B2S_T_EPS;  // Gaussian applied
-                done0 = done0 || (ok0 && !ap0);
-                done1 = done1 || (ok1 && !ap1);
-                vis.x = ap0 ? vis.x : 0.f;
-                vis.y = ap1 ? vis.y : 0.f;
-                T.x = ap0 ? nT.x : T.x;
-                T.y = ap1 ? nT.y : T.y;
-                const int id = nblend + t;
-                cur0 = ap0 ? id : cur0;
-                cur1 = ap1 ? id : cur1;
+            const bool ok0 = p.x >= 0.f && al.x >= B2S_ALPHA_MIN;
+            const bool ok1 = p.y >= 0.f && al.y >= B2S_ALPHA_MIN;
+            const float2 nT = mul2(T, fma2(al, bc2(-1.0f), bc2(1.0f)));  // T (1 - alpha)
+            const bool ap0 = ok0 && nT.x > B2S_T_EPS, ap1 = ok1 && nT.y > B2S_T_EPS;  // Gaussian applied
+            float2 vis = mul2(al, T);
+            vis.x = ap0 ? vis.x : 0.f;
+            vis.y = ap1 ? vis.y : 0.f;
+            T.x = ok0 ? (ap0 ? nT.x : 0.f) : T.x;  // applied: T'; hit but T' <= eps: terminate; untouched: keep
+            T.y = ok1 ? (ap1 ? nT.y : 0.f) : T.y;
+            Tout.x = ap0 ? nT.x : Tout.x;
+            Tout.y = ap1 ? nT.y : Tout.y;
+            const int id = nblend + t;
+            cur0 = ap0 ? id : cur0;
+            cur1 = ap1 ? id : cur1;
 #pragma unroll
-                for (int j = 0; j < CQ; ++j) {
-                    const float4 v = s_col[t * CQ + j];
-                    acc[4 * j] = fma2(bc2(v.x), vis, acc[4 * j]);
-                    acc[4 * j + 1] = fma2(bc2(v.y), vis, acc[4 * j + 1]);
-                    acc[4 * j + 2] = fma2(bc2(v.z), vis, acc[4 * j + 2]);
-                    acc[4 * j + 3] = fma2(bc2(v.w), vis, acc[4 * j + 3]);
-                }
+            for (int j = 0; j < CQ; ++j) {
+                const float4 v = s_col[t * CQ + j];
+                acc[4 * j] = fma2(bc2(v.x), vis, acc[4 * j]);
+                acc[4 * j + 1] = fma2(bc2(v.y), vis, acc[4 * j + 1]);
+                acc[4 * j + 2] = fma2(bc2(v.z), vis, acc[4 * j + 2]);
+                acc[4 * j + 3] = fma2(bc2(v.w), vis, acc[4 * j + 3]);
             }
         }
         nblend += cnt;
@@ -199,7 +200,7 @@ k_blend_fwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
     for (int base = start; base < end; base += BL_BATCH) {
         // a TMA store still reading a block buffer must finish before new entries are appended to that buffer
         if (records != nullptr && threadIdx.x == 0) b2s_bulk_wait_read();
-        if (__syncthreads_and(done0 && done1)) { all_done = true; break; }
+        if (__syncthreads_and(T.x == 0.f && T.y == 0.f)) { all_done = true; break; }
         // ballot compaction of the kept entries of this batch: slot order == list order
         const unsigned bal = __ballot_sync(0xffffffffu, nxt.keep);
         if (lane == 0) s_wcnt[warp] = __popc(bal);
@@ -228,14 +229,14 @@ k_blend_fwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
     }
     if (!all_done && npend > nblend) {  // the partial block at the end of the list
         if (records != nullptr && threadIdx.x == 0) b2s_bulk_wait_read();
-        if (!__syncthreads_and(done0 && done1)) process_block((nblend >> 7) & 1, npend - nblend);
+        if (!__syncthreads_and(T.x == 0.f && T.y == 0.f)) process_block((nblend >> 7) & 1, npend - nblend);
     }
     if (threadIdx.x == 0) {
         if (records != nullptr) b2s_bulk_wait_read();  // shared memory must outlive the last store
         if (tile_blocks != nullptr) tile_blocks[tile] = make_int2(prev_blk, nblocks);
     }
 
-    const float T0 = T.x, T1 = T.y;
+    const float T0 = Tout.x, T1 = Tout.y;
     float acc0[CDIM], acc1[CDIM];
 #pragma unroll
     for (int k = 0; k < CDIM; ++k) {
