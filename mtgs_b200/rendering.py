@@ -263,6 +263,10 @@ _PINNED_TOTALS: Dict[int, tuple] = {}
 _CAPACITY: Dict[tuple, list] = {}
 CAPACITY_HEADROOM = 1.25
 SYNC_SIZES = False  # True: always wait for the exact sizes before building the lists (debugging / tests)
+# While a CUDA graph is being captured (mtgs_b200.graph.GraphedStep) nothing may wait for the device: the forward
+# then runs in capacity mode without the host-side check, and every call leaves (totals tensor, capacities) here so
+# that the owner of the graph can verify after a replay that no level overflowed.
+_CAPTURED: list = []
 
 
 def _start_totals_readback(totals: Tensor):
@@ -354,11 +358,12 @@ def _rasterize_one(means, quats, scales, opacities, colors, viewmat, K, width, h
     means2d, geo, colpack, radii, depths, tiles, keys, rects, tight, totals, arena = _Project.apply(
         means, quats, scales, opacities, cols, viewmat, K, width, height, tile_w, tile_h, float(eps2d),
         float(near_plane), float(far_plane), float(radius_clip), calc_comp, with_depth, cdim, want_grad)
-    host, ev = _start_totals_readback(totals)
+    capturing = torch.cuda.is_current_stream_capturing()
+    if not capturing:
+        host, ev = _start_totals_readback(totals)
     order, n_vis = _sort_depth(keys)
     key = (means.device.index, tile_w, tile_h)
     caps = _CAPACITY.get(key)
-
     counter = C.c_void_p(totals.data_ptr() + 48)  # record-block bump allocator (zeroed with the totals)
 
     def build(sizes, overflow_ptr):
@@ -368,7 +373,15 @@ def _rasterize_one(means, quats, scales, opacities, colors, viewmat, K, width, h
         return _Blend.apply(means2d, geo, colpack, lists, arena, width, height, tile_w, tile_h, cdim, d_out, ed,
                             bool(absgrad), sizes[0], counter, overflow_ptr)
 
-    if caps is None or SYNC_SIZES or N == 0:
+    tot = None
+    if capturing:
+        if caps is None:
+            raise RuntimeError("run this call eagerly at least once before capturing it in a CUDA graph: the list "
+                               "capacities are learnt from earlier frames")
+        flag = C.c_void_p(totals.data_ptr() + 40)
+        render, alpha, last_ids = build((caps[0], caps[1], caps[2], caps[3], N), flag)
+        _CAPTURED.append((totals, list(caps), key))
+    elif caps is None or SYNC_SIZES or N == 0:
         ev.synchronize()
         tot = [int(v) for v in host.tolist()[:5]]
         render, alpha, last_ids = build(tuple(tot), None)
@@ -381,10 +394,11 @@ def _rasterize_one(means, quats, scales, opacities, colors, viewmat, K, width, h
         if any(tot[i] > caps[i] for i in range(4)):  # rare: rebuild with the exact sizes
             totals[6] = 0  # (stream-ordered) reset of the record-block counter
             render, alpha, last_ids = build(tuple(tot), None)
-    if caps is None:
-        caps = _CAPACITY[key] = [0, 0, 0, 0]
-    for i in range(4):
-        caps[i] = max(caps[i], int(tot[i] * CAPACITY_HEADROOM) + 4096)
+    if tot is not None:
+        if caps is None:
+            caps = _CAPACITY[key] = [0, 0, 0, 0]
+        for i in range(4):
+            caps[i] = max(caps[i], int(tot[i] * CAPACITY_HEADROOM) + 4096)
     # keys with a leading underscore are not part of upstream's info dict (bench.py reads them for K_pairs)
     meta = dict(radii=radii.unsqueeze(0), means2d=means2d, depths=depths.unsqueeze(0),
                 conics=geo.detach()[:, :3].unsqueeze(0), opacities=geo.detach()[:, 3].unsqueeze(0),
@@ -399,7 +413,7 @@ def _rasterize_one(means, quats, scales, opacities, colors, viewmat, K, width, h
             sizes = [int(v) for v in up.tolist()]
             if sizes[0] >= 2 ** 31:
                 raise RuntimeError(f"{sizes[0]} tile intersections exceed the int32 offset range (same limit as upstream)")
-            sizes[4] = tot[4]  # the depth order holds every visible Gaussian
+            sizes[4] = int(n_vis.item())  # the depth order holds every visible Gaussian
             flat, offs = _tile_lists(rects, order, n_vis, tuple(sizes), tile_w, tile_h, width, height, False)
             return dict(flatten_ids=flat, isect_offsets=offs.view(1, tile_h, tile_w),
                         isect_ids=_isect_ids(offs, flat, depths))
