@@ -259,7 +259,7 @@ def main():
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="multi-GPU gradient exchange: fused into the projection backward over peer memory "
                          "(default) or an NCCL all-reduce after the backward (the baseline it replaces)")
-    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+    ap.add_argument("--graph", default="off", choices=["auto", "on", "off"],
                     help="replay the step as ONE CUDA graph in the HBM-resident timed region (auto: when capture works)")
     ap.add_argument("--bwd-px", type=int, default=0, choices=[0, 4, 8],
                     help="pixels per thread of the blend backward (0 = library default; tuning only)")
