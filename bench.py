@@ -259,7 +259,7 @@ def main():
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="multi-GPU gradient exchange: fused into the projection backward over peer memory "
                          "(default) or an NCCL all-reduce after the backward (the baseline it replaces)")
-    ap.add_argument("--graph", default="off", choices=["auto", "on", "off"],
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the step as ONE CUDA graph in the HBM-resident timed region (auto: when capture works)")
     ap.add_argument("--bwd-px", type=int, default=0, choices=[0, 4, 8],
                     help="pixels per thread of the blend backward (0 = library default; tuning only)")
@@ -433,15 +433,26 @@ def main():
         try:
             from mtgs_b200.graph import GraphedStep
             rendering.PROFILE = None
+            loss = meta = None  # nothing of the eager steps may keep their autograd graphs alive (see GraphedStep)
             graphed = GraphedStep(lambda: step(params), warmup=2)
             graphed.replay()
             graphed.check()
-            graph_note = "whole step (forward + loss + backward" + (" + gradient exchange" if exch is not None else "") + \
-                         ") replayed as one CUDA graph"
+            graph_note = "whole step (forward + loss + backward) replayed as one CUDA graph"
         except Exception as e:  # pragma: no cover
-            graphed, graph_note = None, f"capture failed, eager launches timed instead ({type(e).__name__}: {e})"
             if args.graph == "on":
                 raise
+            # a failed capture leaves the process in a degraded state (measured: 5x slower eager steps afterwards):
+            # start over in a clean process with eager launches, and say so in the line
+            if rank == 0:
+                sampler.stop()
+            sys.stderr.write(f"bench.py: CUDA graph capture failed ({type(e).__name__}: {str(e).splitlines()[0]}); "
+                             f"re-running with --graph off\n")
+            sys.stderr.flush()
+            argv = [a for a in sys.argv if a != "--graph" and not a.startswith("--graph=")]
+            if "--graph" in sys.argv:
+                i = sys.argv.index("--graph")
+                argv = sys.argv[:i] + sys.argv[i + 2:]
+            os.execv(sys.executable, [sys.executable] + argv + ["--graph", "off"])
     flag = torch.tensor([0 if graphed is not None else 1], device=dev)
     if dist is not None:  # every rank must time the same path
         dist.all_reduce(flag, op=dist.ReduceOp.MAX)

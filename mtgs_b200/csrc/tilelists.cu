@@ -25,6 +25,9 @@
 
 #include "common.cuh"
 
+#ifndef B2S_CG_SHIFT_MIN
+#define B2S_CG_SHIFT_MIN 4  // smallest column-group width (log2 tiles): the blend scans whole (row, column-group) lists
+#endif
 constexpr int TL_WARPS = 8;   // warps per CTA; a CTA owns one chunk, warp w the w-th slice of it
 // items per chunk at level K = TL_WARPS slices of 128 (levels 1-2) or 256 (levels 3-4) items: short slices = many
 // warps in flight (a warp is a serial chain of dependent loads and the early levels have few items), CTA-sized
@@ -57,7 +60,7 @@ static inline bool tl_geom(int tile_w, int tile_h, TlGeom &g) {
     g.tile_w = tile_w;
     g.tile_h = tile_h;
     g.rg_shift = tl_shift(tile_h, 3);
-    g.cg_shift = tl_shift(tile_w, 4);
+    g.cg_shift = tl_shift(tile_w, B2S_CG_SHIFT_MIN);
     if (g.rg_shift < 0 || g.cg_shift < 0) return false;
     g.nrg = (tile_h + (1 << g.rg_shift) - 1) >> g.rg_shift;
     g.ncg = (tile_w + (1 << g.cg_shift) - 1) >> g.cg_shift;

@@ -35,18 +35,27 @@ class GraphedStep:
         self.recapture()
 
     def recapture(self) -> None:
-        """Eager warm-up on a side stream (lazy module loading, allocator steady state, list capacities), then capture."""
+        """Eager warm-up (lazy module loading, allocator steady state, list capacities), then capture -- both on ONE
+        side stream: autograd's AccumulateGrad nodes remember the stream they were created on, and a node that lives
+        on another stream than the capture stream invalidates the capture.  The caller must not keep tensors of earlier
+        eager steps alive (they pin the old autograd graph and with it AccumulateGrad nodes of the default stream)."""
+        import gc
+        self.out = None
+        gc.collect()
         torch.cuda.synchronize()
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
+        if getattr(self, "stream", None) is None:
+            self.stream = torch.cuda.Stream()
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
             for _ in range(max(1, self.warmup)):
-                self.fn()
-        torch.cuda.current_stream().wait_stream(side)
+                out = self.fn()
+                del out
+        torch.cuda.current_stream().wait_stream(self.stream)
         torch.cuda.synchronize()
+        gc.collect()
         rendering._CAPTURED.clear()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, pool=self.pool):
+        with torch.cuda.graph(self.graph, pool=self.pool, stream=self.stream):
             self.out = self.fn()
         self._captured = list(rendering._CAPTURED)
         rendering._CAPTURED.clear()
