@@ -250,7 +250,9 @@ def test_graphed_step_replays_the_eager_step(cuda_device):
         ((r * w).sum() + a.sum()).backward()
         return r, a
 
-    r0, a0 = step()
+    # nothing of the eager step may stay alive into the capture: a tensor with a grad_fn pins the autograd graph and
+    # its AccumulateGrad nodes, which belong to the default stream (GraphedStep docstring)
+    r0, a0 = (x.detach().clone() for x in step())
     g0 = {k: t[k].grad.clone() for k in names}
     gs = GraphedStep(step, warmup=2)
     for _ in range(3):
