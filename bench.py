@@ -427,9 +427,10 @@ def main():
     # captured ONCE into a CUDA graph and replayed (same kernels, no host-side launch work, no gaps between dependent
     # kernels); per-stage CUDA-event timing needs the eager path and is taken from a second, untimed pass below.
     graphed, graph_note = None, "off"
-    if world > 1 and args.graph != "off":
-        graph_note = "off (multi-GPU: the gradient exchange's epoch is a host-side counter passed by value)"
+    if arena is not None and args.graph != "off":
+        graph_note = "off (--exchange nccl: the library all-reduce is launched eagerly)"
     elif args.graph != "off":
+        err = None
         try:
             from mtgs_b200.graph import GraphedStep
             rendering.PROFILE = None
@@ -437,21 +438,29 @@ def main():
             graphed = GraphedStep(lambda: step(params), warmup=2)
             graphed.replay()
             graphed.check()
-            graph_note = "whole step (forward + loss + backward) replayed as one CUDA graph"
+            graph_note = "whole step (forward + loss + backward" + (" incl. the fused gradient exchange" if exch is not None
+                                                                     else "") + ") replayed as one CUDA graph"
         except Exception as e:  # pragma: no cover
             if args.graph == "on":
                 raise
+            err = f"{type(e).__name__}: {str(e).splitlines()[0]}"
+        failed = torch.tensor([1 if err else 0], device=dev)
+        if dist is not None:
+            dist.all_reduce(failed, op=dist.ReduceOp.MAX)
+        if int(failed.item()):  # pragma: no cover
             # a failed capture leaves the process in a degraded state (measured: 5x slower eager steps afterwards):
-            # start over in a clean process with eager launches, and say so in the line
+            # every rank starts over in a clean process with eager launches
             if rank == 0:
                 sampler.stop()
-            sys.stderr.write(f"bench.py: CUDA graph capture failed ({type(e).__name__}: {str(e).splitlines()[0]}); "
-                             f"re-running with --graph off\n")
-            sys.stderr.flush()
-            argv = [a for a in sys.argv if a != "--graph" and not a.startswith("--graph=")]
-            if "--graph" in sys.argv:
-                i = sys.argv.index("--graph")
-                argv = sys.argv[:i] + sys.argv[i + 2:]
+                sys.stderr.write(f"bench.py: CUDA graph capture failed ({err or 'on another rank'}); re-running with "
+                                 f"--graph off\n")
+                sys.stderr.flush()
+            if dist is not None:
+                dist.destroy_process_group()
+            argv = list(sys.argv)
+            if "--graph" in argv:
+                i = argv.index("--graph")
+                argv = argv[:i] + argv[i + 2:]
             os.execv(sys.executable, [sys.executable] + argv + ["--graph", "off"])
     flag = torch.tensor([0 if graphed is not None else 1], device=dev)
     if dist is not None:  # every rank must time the same path

@@ -100,7 +100,9 @@ int b2s_project_bwd(const float *means, const float *quats, const float *scales,
  * plain projection backward for the rank-local rows, the reduce of my shard + store of the result into every rank's
  * arena, and a stream-ordered wait.  When it has run, arena holds scale * sum over ranks for the shared rows and the
  * local gradient for the others.  *_ptrs_host are HOST arrays of `world` device pointers (this rank's own buffers at
- * index `rank`); epoch must increase by one per call on every rank.  The waits block like a library collective (ranks
+ * index `rank`); epoch must increase by one per call on every rank, or be 0 on every rank and call: the library then
+ * counts the steps itself in word 32 of this rank's flag buffer (no launch argument changes from step to step, so the
+ * whole step can be captured in a CUDA graph; flag buffers are 256 zero-initialised bytes).  The waits block like a library collective (ranks
  * must stay in lock-step) and give up after timeout_s seconds (<= 0: 120 s): then *status (a word the device can write;
  * pinned host memory lets the host poll it without synchronising) becomes non-zero AND the shared rows of the arena are
  * filled with NaN -- never stale or partial gradients.  Colour gradients of the rank-local rows are left in v_colpack.

@@ -133,7 +133,10 @@ struct B2sExchange {
     int shard;              // Gaussians (rows) owned per rank; multiple of 256
     int d_col;              // colour floats per row that take part in the exchange (d_in, or 0: colours stay local)
     long long slot_floats;  // floats per (owner, source) staging slot = (11 + d_col) * shard
-    unsigned epoch;         // step counter written into the flags
+    unsigned epoch;         // step counter written into the flags (host-counted mode)
+    unsigned *epoch_dev;    // device-counted mode (or null): this rank's own step counter, incremented by the first
+                            // signal kernel of a step -- nothing of the launch depends on a host-side value, so the
+                            // whole step can be replayed from a CUDA graph
     long long timeout_cycles;  // spin-loop budget of the flag waits (SM clock cycles)
     float *stage[B2S_MAX_WORLD];     // stage[r]: rank r's staging buffer [world][slot_floats] (peer-mapped)
     float *arena[B2S_MAX_WORLD];     // arena[r]: rank r's reduced-gradient arena (peer-mapped)

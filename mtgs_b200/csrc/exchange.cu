@@ -67,7 +67,8 @@ k_grad_reduce_bcast(const B2sExchange ex, int n_shared, long long rows_cap, floa
     if (threadIdx.x == 0) s_ok = 1u;
     __syncthreads();
     if (threadIdx.x < ex.world) {
-        if (!ex_wait_flag(ex.flags[ex.rank] + threadIdx.x, ex.epoch, ex.timeout_cycles)) {
+        const unsigned epoch = ex.epoch_dev != nullptr ? *(volatile unsigned *)ex.epoch_dev : ex.epoch;
+        if (!ex_wait_flag(ex.flags[ex.rank] + threadIdx.x, epoch, ex.timeout_cycles)) {
             s_ok = 0u;
             *(volatile unsigned *)status = 1u;
             __threadfence_system();
@@ -116,9 +117,15 @@ k_grad_reduce_bcast(const B2sExchange ex, int n_shared, long long rows_cap, floa
 __global__ void __launch_bounds__(32)
 k_exchange_signal(const B2sExchange ex, int phase) {
     __threadfence_system();
+    unsigned epoch = ex.epoch;
+    if (ex.epoch_dev != nullptr) {  // device-counted steps: the phase-0 signal opens a new step
+        if (phase == 0 && threadIdx.x == 0) *(volatile unsigned *)ex.epoch_dev = *(volatile unsigned *)ex.epoch_dev + 1u;
+        __syncwarp();
+        epoch = *(volatile unsigned *)ex.epoch_dev;
+    }
     if (threadIdx.x < ex.world) {
         volatile unsigned *f = ex.flags[threadIdx.x] + phase * B2S_MAX_WORLD + ex.rank;
-        *f = ex.epoch;
+        *f = epoch;
     }
 }
 
@@ -129,7 +136,8 @@ k_exchange_wait(const B2sExchange ex, int n_shared, long long rows_cap, unsigned
     if (threadIdx.x == 0) s_ok = 1u;
     __syncthreads();
     if (threadIdx.x < ex.world) {
-        if (!ex_wait_flag(ex.flags[ex.rank] + B2S_MAX_WORLD + threadIdx.x, ex.epoch, ex.timeout_cycles)) {
+        const unsigned epoch = ex.epoch_dev != nullptr ? *(volatile unsigned *)ex.epoch_dev : ex.epoch;
+        if (!ex_wait_flag(ex.flags[ex.rank] + B2S_MAX_WORLD + threadIdx.x, epoch, ex.timeout_cycles)) {
             s_ok = 0u;
             *(volatile unsigned *)status = 2u;
         }
@@ -204,6 +212,8 @@ extern "C" int b2s_project_bwd_exchange(
     ex.d_col = exchange_colors ? d_in : 0;
     ex.slot_floats = (long long)(11 + ex.d_col) * ex.shard;
     ex.epoch = epoch;
+    // epoch == 0: device-counted steps; the counter is word 32 of this rank's own flag buffer (peers never touch it)
+    ex.epoch_dev = epoch == 0 ? (unsigned *)(uintptr_t)flag_ptrs_host[rank] + 32 : nullptr;
     ex.timeout_cycles = (long long)((timeout_s > 0.f ? (double)timeout_s : 120.0) * 1.9e9);
     for (int r = 0; r < world; ++r) {
         ex.stage[r] = (float *)(uintptr_t)stage_ptrs_host[r];

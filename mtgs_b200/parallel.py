@@ -183,7 +183,7 @@ class GradExchange:
 
     def __init__(self, n_shared: int, d_in: int, rows_cap: Optional[int] = None, group=None, average: bool = True,
                  device: Optional[torch.device] = None, exchange_colors: bool = True, zero_copy: bool = False,
-                 timeout_s: float = 120.0, _local: Optional[tuple] = None):
+                 timeout_s: float = 120.0, device_epoch: bool = True, _local: Optional[tuple] = None):
         from . import _lib
         import ctypes as C
         self._lib = lib = _lib.load()
@@ -205,6 +205,9 @@ class GradExchange:
         self.scale = 1.0 / self.world if average else 1.0
         self.zero_copy = bool(zero_copy)
         self.timeout_s = float(timeout_s)
+        # device_epoch: the step counter lives on the device (incremented by the step's first signal kernel), so no
+        # launch argument changes between steps and a step can be replayed from a CUDA graph
+        self.device_epoch = bool(device_epoch)
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.shard = int(lib.b2s_exchange_shard_rows(self.n_shared, self.world))
         # the staging buffer is sized for the largest shard n_shared can grow to (rows_cap)
@@ -369,7 +372,7 @@ class GradExchange:
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         self._check(self._lib.b2s_project_bwd_exchange(
             *args, self.n_shared, int(self.exchange_colors), self.world, self.rank, self.rows_cap, self.scale,
-            self.epoch, phases, self.timeout_s,
+            0 if self.device_epoch else self.epoch, phases, self.timeout_s,
             self._ptr_array(self.stage_ptrs), self._ptr_array(self.arena_ptrs), self._ptr_array(self.flag_ptrs),
             C.c_void_p(self.status.data_ptr()), stream),
             "b2s_project_bwd_exchange")
