@@ -447,16 +447,18 @@ def main():
         failed = torch.tensor([1 if err else 0], device=dev)
         if dist is not None:
             dist.all_reduce(failed, op=dist.ReduceOp.MAX)
-        if int(failed.item()):  # pragma: no cover
+        if int(failed.item()) and dist is not None:  # pragma: no cover
+            graphed = None
+            graph_note = f"capture failed ({err or 'on another rank'}); eager launches timed"
+            if rank == 0:
+                sys.stderr.write(f"bench.py: CUDA graph capture failed ({err or 'on another rank'}); timing eager launches\n")
+        elif int(failed.item()):  # pragma: no cover
             # a failed capture leaves the process in a degraded state (measured: 5x slower eager steps afterwards):
-            # every rank starts over in a clean process with eager launches
+            # start over in a clean process with eager launches
             if rank == 0:
                 sampler.stop()
-                sys.stderr.write(f"bench.py: CUDA graph capture failed ({err or 'on another rank'}); re-running with "
-                                 f"--graph off\n")
+                sys.stderr.write(f"bench.py: CUDA graph capture failed ({err}); re-running with --graph off\n")
                 sys.stderr.flush()
-            if dist is not None:
-                dist.destroy_process_group()
             argv = list(sys.argv)
             if "--graph" in argv:
                 i = argv.index("--graph")

@@ -55,8 +55,18 @@ class GraphedStep:
         gc.collect()
         rendering._CAPTURED.clear()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, pool=self.pool, stream=self.stream):
-            self.out = self.fn()
+        # thread_local: only the capturing thread is policed; background threads of the process (NCCL watchdog,
+        # pinned-memory allocator) keep making CUDA calls during the capture, which the default "global" mode forbids
+        try:
+            with torch.cuda.graph(self.graph, pool=self.pool, stream=self.stream, capture_error_mode="thread_local"):
+                self.out = self.fn()
+        except Exception as e:
+            first = e
+            while first.__context__ is not None:  # the error that invalidated the capture, not capture_end's
+                first = first.__context__
+            if first is not e:
+                raise RuntimeError(f"CUDA graph capture failed: {type(first).__name__}: {first}") from e
+            raise
         self._captured = list(rendering._CAPTURED)
         rendering._CAPTURED.clear()
 

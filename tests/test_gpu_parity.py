@@ -245,7 +245,7 @@ def test_graphed_step_replays_the_eager_step(cuda_device):
 
     def step():
         r, a, _ = _gpu_raster(t, s, **kw)
-        for k in names:
+        for k in names + ("viewmat",):
             t[k].grad = None
         ((r * w).sum() + a.sum()).backward()
         return r, a
