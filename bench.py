@@ -420,7 +420,7 @@ def main():
             err = torch.maximum(err, (params[k].grad - want[k]).abs().max() / want[k].abs().max().clamp_min(1e-30))
         dist.all_reduce(err, op=dist.ReduceOp.MAX)
         exchange_max_rel_err = float(err.item())
-        del want, r, a
+        del want, r, a, _  # `_` (meta) holds tensors with a grad_fn: it would pin this step's autograd graph
         barrier()
 
     # ---- timed region 1: inputs resident in HBM.  The step is a fixed launch sequence on static tensors, so it is

@@ -187,18 +187,22 @@ int b2s_bin_isect_ids(const int32_t *isect_offsets, int n_tiles, const int32_t *
  * each tile's chain back to front through double-buffered TMA bulk loads and never touches the lists or the
  * per-Gaussian arrays.  v_xyabs [N,4] = (v_mean2d xy, |v_mean2d| xy), v_geo [N,4] = (v_conic abc, v_opacity_eff),
  * v_colpack [N,cdim]: accumulated with 16-byte vector reductions, zero-filled by the caller (b2s_project_fwd does it).
- * skip_flag: the overflow word of a capacity-mode b2s_bin_tiles (may be NULL). */
+ * skip_flag: the overflow word of a capacity-mode b2s_bin_tiles (may be NULL): when it is set neither kernel does
+ * anything.  record_blocks = b2s_blend_record_blocks(pairs, tiles), the blocks `records` has room for: a forward that
+ * needs more (pairs was a capacity, not this frame's size) writes nothing out of bounds and sets *skip_flag = 9
+ * (exact sizes can never run out). */
+uint32_t b2s_blend_record_blocks(long long pair_capacity, int n_tiles);
 size_t b2s_blend_record_bytes(long long pair_capacity, int n_tiles, int cdim);
 int b2s_blend_fwd(const float *means2d, const float *geo, const float *colpack, const int32_t *list_offsets,
                   const int32_t *list_items, int ncg, int cg_shift, int W, int H, int tile_w, int tile_h,
                   int cdim, int d_out, int expected_depth, float *render, float *alpha, int32_t *last_ids,
-                  float *records, uint32_t *block_counter, int32_t *tile_blocks, const int32_t *skip_flag,
-                  b2s_stream_t stream);
+                  float *records, uint32_t record_blocks, uint32_t *block_counter, int32_t *tile_blocks,
+                  int32_t *skip_flag, b2s_stream_t stream);
 int b2s_blend_bwd(const int32_t *tile_blocks, const float *records, int W, int H, int tile_w, int tile_h,
                   int cdim, int d_out, int expected_depth, const float *render, const float *alpha,
                   const int32_t *last_ids, const float *v_render, const float *v_alpha, float *v_xyabs,
                   float *v_geo, float *v_colpack, int px_per_thread /* 0 = default; 4 or 8 (tuning / tests) */,
-                  b2s_stream_t stream);
+                  const int32_t *skip_flag, b2s_stream_t stream);
 
 /* ---- spherical harmonics (upstream compute_sh fwd / bwd; A.6) ----
  * dirs [N,3], coeffs [N,K,3], masks (uint8, may be NULL), degree in 0..4 with (degree+1)^2 <= K. */

@@ -39,8 +39,9 @@ SIGNATURES = {
                                    C.POINTER(_i)]),
     "b2s_bin_isect_ids": (_i, [_vp, _i, _vp, _vp, _ll, _vp, _vp]),
     "b2s_blend_record_bytes": (_sz, [_ll, _i, _i]),
-    "b2s_blend_fwd": (_i, [_vp] * 5 + [_i] * 9 + [_vp] * 7 + [_vp]),
-    "b2s_blend_bwd": (_i, [_vp] * 2 + [_i] * 7 + [_vp] * 8 + [_i, _vp]),
+    "b2s_blend_record_blocks": (C.c_uint32, [_ll, _i]),
+    "b2s_blend_fwd": (_i, [_vp] * 5 + [_i] * 9 + [_vp] * 4 + [C.c_uint32] + [_vp] * 3 + [_vp]),
+    "b2s_blend_bwd": (_i, [_vp] * 2 + [_i] * 7 + [_vp] * 8 + [_i, _vp, _vp]),
     "b2s_ssim_fwd": (_i, [_vp] * 3 + [_ll, _ll] + [_i] * 4 + [_vp, _i, _f, _f] + [_vp] * 5 + [_vp]),
     "b2s_ssim_bwd": (_i, [_vp] * 6 + [_i] * 4 + [_vp, _i, _vp] + [_vp]),
     "b2s_masked_l1_fwd": (_i, [_vp] * 3 + [_ll, _i, _i, _f, _vp, _vp]),

@@ -103,9 +103,11 @@ k_blend_fwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
             int W, int H, int tile_w, float *__restrict__ render, float *__restrict__ alpha_out,
             int32_t *__restrict__ last_ids, float4 *__restrict__ records /* walk-record blocks, or null */,
             unsigned *__restrict__ blk_counter /* bump allocator of record blocks (zeroed by the caller) */,
+            unsigned block_cap /* record blocks allocated */,
             int2 *__restrict__ tile_blocks /* [tiles]: (last block written, blocks written) */,
-            const int32_t *__restrict__ skip /* or null: non-zero = the lists are invalid (capacity overflow) */) {
-    if (skip != nullptr && *skip != 0) return;
+            int32_t *__restrict__ skip /* or null: non-zero = the lists are invalid (capacity overflow); set here when
+                                          the record blocks run out */) {
+    if (skip != nullptr && *(volatile int32_t *)skip != 0) return;
     constexpr int CQ = CDIM / 4;
     using BL = BlkLayout<CDIM>;
     // two block-shaped buffers: kept entries are packed densely (slot s lives in buffer (s >> 7) & 1), a block is
@@ -143,15 +145,23 @@ k_blend_fwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
     auto process_block = [&](int bufi, int cnt) {
         float4 *s_q = s_blk[bufi], *s_c = s_blk[bufi] + BL_BATCH, *s_col = s_blk[bufi] + 2 * BL_BATCH;
         if (records != nullptr) {
+            bool stored = false;  // (thread 0)
             if (threadIdx.x == 0) {
-                const int blk = (int)atomicAdd(blk_counter, 1u);
-                s_blk[bufi][BL::HDR] = make_float4(__int_as_float(cnt), __int_as_float(prev_blk), 0.f, 0.f);
-                prev_blk = blk;
-                ++nblocks;
+                const unsigned blk = atomicAdd(blk_counter, 1u);
+                if (blk < block_cap) {
+                    s_blk[bufi][BL::HDR] = make_float4(__int_as_float(cnt), __int_as_float(prev_blk), 0.f, 0.f);
+                    prev_blk = (int)blk;
+                    ++nblocks;
+                    stored = true;
+                } else if (skip != nullptr) {
+                    // more pairs than the capacity this launch was sized for: nothing is written out of bounds, the
+                    // frame is flagged and rebuilt (or the graph replay reported) by the host
+                    atomicExch(skip, B2S_OVERFLOW_RECORDS);
+                }
             }
             b2s_fence_async_smem();
             __syncthreads();
-            if (threadIdx.x == 0) {
+            if (stored) {
                 b2s_bulk_s2g(records + (size_t)prev_blk * BL::F4, s_blk[bufi], BL::BYTES);
                 b2s_bulk_commit();
             }
@@ -386,11 +396,13 @@ __device__ __forceinline__ void load_pixel_cotangent(size_t pid, const float *__
 // PX = 8: ONE warp per tile -- one butterfly and no cross-warp sum per (tile, Gaussian); PX = 4: two warps.
 template <int CDIM, int DOUT, bool ED, int PX>
 __global__ void __launch_bounds__(256 / PX, PX == 8 ? (CDIM == 4 ? 14 : 10) : (CDIM == 4 ? 10 : 7))
-k_blend_bwd(const int2 *__restrict__ tile_blocks /* [tiles]: (last record block, blocks written) */,
+k_blend_bwd(const int32_t *__restrict__ skip /* or null: non-zero = the forward of this frame was abandoned */,
+            const int2 *__restrict__ tile_blocks /* [tiles]: (last record block, blocks written) */,
             const float4 *__restrict__ records, int W, int H, int tile_w, const float *__restrict__ render, const float *__restrict__ alpha_in,
             const int32_t *__restrict__ last_ids, const float *__restrict__ v_render,
             const float *__restrict__ v_alpha, float *__restrict__ v_xyabs, float *__restrict__ v_geo,
             float *__restrict__ v_colpack) {
+    if (skip != nullptr && *skip != 0) return;
     constexpr int THREADS = 256 / PX, WARPS = THREADS / 32, NP = PX / 2;
     constexpr int CQ = CDIM / 4;
     constexpr int NV = 8 + CDIM;   // partial sums per Gaussian
@@ -454,7 +466,7 @@ k_blend_bwd(const int2 *__restrict__ tile_blocks /* [tiles]: (last record block,
     // (header: entries, previous block); it may have written blocks behind the last contribution: skip them.
     const int hi0 = maxbin;
     if (hi0 < 0 || tb.y <= 0) return;  // nothing was blended in this tile (CTA-uniform)
-    const int nblk = (hi0 >> 7) + 1;
+    const int nblk = min((hi0 >> 7) + 1, tb.y);
     __shared__ int s_next;
     if (threadIdx.x == 0) {
         int blk = tb.x;
@@ -564,24 +576,25 @@ k_blend_bwd(const int2 *__restrict__ tile_blocks /* [tiles]: (last record block,
 template <int CDIM, int DOUT, bool ED>
 static int launch_fwd(const float *means2d, const float *geo, const float *colpack, const int32_t *list_off,
                       const int32_t *items, int ncg, int cg_shift, int W, int H, int tile_w, int tile_h, float *render,
-                      float *alpha, int32_t *last_ids, float *records, unsigned *blk_counter, int32_t *tile_blocks,
-                      const int32_t *skip, cudaStream_t st) {
+                      float *alpha, int32_t *last_ids, float *records, unsigned *blk_counter, unsigned block_cap,
+                      int32_t *tile_blocks, int32_t *skip, cudaStream_t st) {
     k_blend_fwd<CDIM, DOUT, ED><<<tile_w * tile_h, BL_THREADS, 0, st>>>(
         (const float2 *)means2d, (const float4 *)geo, (const float4 *)colpack, list_off, (const int2 *)items, ncg,
-        cg_shift, W, H, tile_w, render, alpha, last_ids, (float4 *)records, blk_counter, (int2 *)tile_blocks, skip);
+        cg_shift, W, H, tile_w, render, alpha, last_ids, (float4 *)records, blk_counter, block_cap, (int2 *)tile_blocks,
+        skip);
     B2S_LAUNCH_CHECK();
     return B2S_OK;
 }
 template <int CDIM, int DOUT, bool ED>
-static int launch_bwd(const int32_t *tile_blocks, const float *records, int W, int H, int tile_w, int tile_h,
+static int launch_bwd(const int32_t *skip, const int32_t *tile_blocks, const float *records, int W, int H, int tile_w, int tile_h,
                       const float *render, const float *alpha, const int32_t *last_ids, const float *v_render,
                       const float *v_alpha, float *v_xyabs, float *v_geo, float *v_colpack, int px, cudaStream_t st) {
     if (px == 4)
-        k_blend_bwd<CDIM, DOUT, ED, 4><<<tile_w * tile_h, 64, 0, st>>>((const int2 *)tile_blocks, (const float4 *)records,
+        k_blend_bwd<CDIM, DOUT, ED, 4><<<tile_w * tile_h, 64, 0, st>>>(skip, (const int2 *)tile_blocks, (const float4 *)records,
                                                                        W, H, tile_w, render, alpha, last_ids, v_render,
                                                                        v_alpha, v_xyabs, v_geo, v_colpack);
     else
-        k_blend_bwd<CDIM, DOUT, ED, 8><<<tile_w * tile_h, 32, 0, st>>>((const int2 *)tile_blocks, (const float4 *)records,
+        k_blend_bwd<CDIM, DOUT, ED, 8><<<tile_w * tile_h, 32, 0, st>>>(skip, (const int2 *)tile_blocks, (const float4 *)records,
                                                                        W, H, tile_w, render, alpha, last_ids, v_render,
                                                                        v_alpha, v_xyabs, v_geo, v_colpack);
     B2S_LAUNCH_CHECK();
@@ -611,35 +624,42 @@ static int launch_bwd(const int32_t *tile_blocks, const float *records, int W, i
         return B2S_ERR_UNSUPPORTED;                                                                \
     } while (0)
 
+extern "C" uint32_t b2s_blend_record_blocks(long long pair_capacity, int n_tiles) {
+    if (pair_capacity < 0 || n_tiles < 0) return 0;
+    const size_t blocks = (size_t)(pair_capacity >> 7) + (size_t)n_tiles + 1;
+    return blocks > 0xffffffffull ? 0xffffffffu : (uint32_t)blocks;
+}
+
 extern "C" size_t b2s_blend_record_bytes(long long pair_capacity, int n_tiles, int cdim) {
     if (pair_capacity < 0 || n_tiles < 0 || (cdim != 4 && cdim != 8)) return 0;
     // blocks are packed densely per tile: at most ceil(kept / 128) per tile, kept <= (Gaussian, tile) pairs in total
-    const size_t blocks = (size_t)(pair_capacity >> 7) + (size_t)n_tiles + 1;
+    const size_t blocks = b2s_blend_record_blocks(pair_capacity, n_tiles);
     return blocks * ((size_t)BL_BATCH * (size_t)(2 + cdim / 4) + 1) * 16;  // + header
 }
 
 extern "C" int b2s_blend_fwd(const float *means2d, const float *geo, const float *colpack, const int32_t *list_offsets,
                              const int32_t *list_items, int ncg, int cg_shift, int W, int H, int tile_w, int tile_h,
                              int cdim, int d_out, int expected_depth, float *render, float *alpha, int32_t *last_ids,
-                             float *records, uint32_t *block_counter, int32_t *tile_blocks, const int32_t *skip_flag,
-                             b2s_stream_t stream) {
+                             float *records, uint32_t record_blocks, uint32_t *block_counter, int32_t *tile_blocks,
+                             int32_t *skip_flag, b2s_stream_t stream) {
     if (W <= 0 || H <= 0 || tile_w * 16 < W || tile_h * 16 < H || ncg < 1 || cg_shift < 0) return B2S_ERR_ARG;
     if (records != nullptr && (((uintptr_t)records & 127) || !block_counter || !tile_blocks)) return B2S_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     B2S_DISPATCH(launch_fwd, means2d, geo, colpack, list_offsets, list_items, ncg, cg_shift, W, H, tile_w, tile_h, render,
-                 alpha, last_ids, records, block_counter, tile_blocks, skip_flag, st);
+                 alpha, last_ids, records, block_counter, record_blocks, tile_blocks, skip_flag, st);
 }
 
 extern "C" int b2s_blend_bwd(const int32_t *tile_blocks, const float *records, int W, int H, int tile_w, int tile_h,
                              int cdim, int d_out, int expected_depth, const float *render, const float *alpha,
                              const int32_t *last_ids, const float *v_render, const float *v_alpha, float *v_xyabs,
-                             float *v_geo, float *v_colpack, int px_per_thread, b2s_stream_t stream) {
+                             float *v_geo, float *v_colpack, int px_per_thread, const int32_t *skip_flag,
+                             b2s_stream_t stream) {
     if (W <= 0 || H <= 0 || tile_w * 16 < W || tile_h * 16 < H || records == nullptr || tile_blocks == nullptr)
         return B2S_ERR_ARG;
     if ((uintptr_t)records & 127) return B2S_ERR_ARG;
     if (px_per_thread != 0 && px_per_thread != 4 && px_per_thread != 8) return B2S_ERR_UNSUPPORTED;
     const int px = px_per_thread == 0 ? B2S_BWD_PX : px_per_thread;
     cudaStream_t st = (cudaStream_t)stream;
-    B2S_DISPATCH(launch_bwd, tile_blocks, records, W, H, tile_w, tile_h, render, alpha, last_ids, v_render, v_alpha,
+    B2S_DISPATCH(launch_bwd, skip_flag, tile_blocks, records, W, H, tile_w, tile_h, render, alpha, last_ids, v_render, v_alpha,
                  v_xyabs, v_geo, v_colpack, px, st);
 }

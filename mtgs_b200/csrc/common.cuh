@@ -7,6 +7,7 @@
 
 #define B2S_ALPHA_MAX 0.999f
 #define B2S_ALPHA_MIN (1.0f / 255.0f)
+#define B2S_OVERFLOW_RECORDS 9  // value of the overflow word when the blend ran out of record blocks (1..4: list levels)
 #define B2S_T_EPS 1e-4f
 #define B2S_LOG2E 1.4426950408889634f
 #define B2S_LN2 0.6931471805599453f

@@ -65,7 +65,9 @@ class GraphedStep:
             while first.__context__ is not None:  # the error that invalidated the capture, not capture_end's
                 first = first.__context__
             if first is not e:
-                raise RuntimeError(f"CUDA graph capture failed: {type(first).__name__}: {first}") from e
+                import traceback
+                where = "".join(traceback.format_tb(first.__traceback__)[-6:])
+                raise RuntimeError(f"CUDA graph capture failed: {type(first).__name__}: {first}\n{where}") from e
             raise
         self._captured = list(rendering._CAPTURED)
         rendering._CAPTURED.clear()

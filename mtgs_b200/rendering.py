@@ -203,25 +203,33 @@ class _Blend(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means2d, geo, colpack, lists, arena, W, H, tile_w, tile_h, cdim, d_out, ed, absgrad, pair_cap,
-                counter_ptr, skip_ptr=None):
+                totals, use_flag=False):
         lib = _lib.load()
+        # words of the projection's `totals`: [6] = record-block bump allocator (zeroed with the totals),
+        # [5] = the capacity-overflow word
+        counter_ptr = C.c_void_p(totals.data_ptr() + 48)
+        skip_ptr = C.c_void_p(totals.data_ptr() + 40) if use_flag else None
+        ctx.totals = totals  # the backward reads the overflow word: keep the tensor alive
         dev = means2d.device
         ws, items_ptr, offs_ptr, ncg, cg_shift = lists  # (row, column-group) lists inside the tile-list workspace
         render = torch.empty(1, H, W, d_out, dtype=torch.float32, device=dev)
         alpha = torch.empty(1, H, W, 1, dtype=torch.float32, device=dev)
         last_ids = torch.empty(H, W, dtype=torch.int32, device=dev)
         records = tile_blocks = None
+        nblocks = 0
         if arena.numel() > 0:  # a backward may follow: keep the walk records
             nbytes = int(lib.b2s_blend_record_bytes(pair_cap, tile_w * tile_h, cdim))
+            nblocks = int(lib.b2s_blend_record_blocks(pair_cap, tile_w * tile_h))
             records = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
             tile_blocks = torch.empty(tile_h * tile_w, 2, dtype=torch.int32, device=dev)
         with _timed("blend_fwd"):
             _lib.check(lib.b2s_blend_fwd(_ptr(means2d), _ptr(geo), _ptr(colpack), offs_ptr, items_ptr, ncg, cg_shift, W, H,
                                          tile_w, tile_h, cdim, d_out, int(ed), _ptr(render), _ptr(alpha),
-                                         _ptr(last_ids), _ptr(records), counter_ptr, _ptr(tile_blocks), skip_ptr,
-                                         _stream()), "b2s_blend_fwd")
+                                         _ptr(last_ids), _ptr(records), nblocks, counter_ptr, _ptr(tile_blocks),
+                                         skip_ptr, _stream()), "b2s_blend_fwd")
         ctx.save_for_backward(means2d, render, alpha, last_ids, records, tile_blocks, arena)
         ctx.cfg = (W, H, tile_w, tile_h, cdim, d_out, ed, absgrad, geo.shape[0])
+        ctx.skip_ptr = skip_ptr
         ctx.set_materialize_grads(False)
         ctx.arena_clean = True
         ctx.mark_non_differentiable(last_ids)
@@ -247,7 +255,8 @@ class _Blend(torch.autograd.Function):
             with _timed("blend_bwd"):
                 _lib.check(lib.b2s_blend_bwd(_ptr(tile_blocks), _ptr(records), W, H, tile_w, tile_h, cdim, d_out, int(ed),
                                              _ptr(render), _ptr(alpha), _ptr(last_ids), _ptr(v_render), _ptr(v_alpha),
-                                             _ptr(v_xyabs), _ptr(v_geo), _ptr(v_colpack), BWD_PX, _stream()),
+                                             _ptr(v_xyabs), _ptr(v_geo), _ptr(v_colpack), BWD_PX, ctx.skip_ptr,
+                                             _stream()),
                            "b2s_blend_bwd")
         if absgrad:
             # upstream: `means2d.absgrad = v_means2d_abs` on the tensor object handed in by the caller
@@ -364,14 +373,13 @@ def _rasterize_one(means, quats, scales, opacities, colors, viewmat, K, width, h
     order, n_vis = _sort_depth(keys)
     key = (means.device.index, tile_w, tile_h)
     caps = _CAPACITY.get(key)
-    counter = C.c_void_p(totals.data_ptr() + 48)  # record-block bump allocator (zeroed with the totals)
 
     def build(sizes, overflow_ptr):
         # (tile row, column group) lists over the tight rectangles; the blend applies the last filter level and the
         # exact per-tile test lazily while it walks
         lists = _tile_lists(tight, order, n_vis, sizes, tile_w, tile_h, width, height, True, overflow_ptr)
         return _Blend.apply(means2d, geo, colpack, lists, arena, width, height, tile_w, tile_h, cdim, d_out, ed,
-                            bool(absgrad), sizes[0], counter, overflow_ptr)
+                            bool(absgrad), sizes[0], totals, overflow_ptr is not None)
 
     tot = None
     if capturing:
