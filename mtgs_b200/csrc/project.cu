@@ -404,24 +404,45 @@ k_project_bwd(const float *__restrict__ means, const float *__restrict__ quats, 
     }
     if (threadIdx.x == 32) load_camera(viewmat, K, W, H, s_cam);
     __syncthreads();
-    int g = g0 + threadIdx.x;
     float vR[9], vt[3];
 #pragma unroll
     for (int k = 0; k < 9; ++k) vR[k] = 0.f;
     vt[0] = vt[1] = vt[2] = 0.f;
-    const bool live = g < N && radii[g] > 0;
+    // The visible rows are COMPACTED over the CTA (see k_project_fwd): the VJP chain below runs on ceil(n_live / 32)
+    // full warps; a culled row only gets its zeros written by its own thread.
+    __shared__ int s_wlive[8];
+    __shared__ short s_rows[256];
+    const int g_own = g0 + threadIdx.x;
+    const bool own_live = g_own < N && radii[g_own] > 0;
+    {
+        const unsigned bal = __ballot_sync(0xffffffffu, own_live);
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (lane == 0) s_wlive[warp] = __popc(bal);
+        __syncthreads();
+        int off = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) off += (w < warp) ? s_wlive[w] : 0;
+        if (own_live) s_rows[off + __popc(bal & ((1u << lane) - 1u))] = (short)threadIdx.x;
+        __syncthreads();
+    }
+    int n_live = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) n_live += s_wlive[w];
+    const bool live = (int)threadIdx.x < n_live;
+    const int row = live ? (int)s_rows[threadIdx.x] : 0;
+    const int g = g0 + row;
     if (staged) b2s_mbar_wait(&s_bar, 0);
-    const int t3 = 3 * threadIdx.x;
+    const int t3 = 3 * row;
     // this Gaussian's gradient row (zeros when it is culled)
     float o_means[3] = {0.f, 0.f, 0.f}, o_scales[3] = {0.f, 0.f, 0.f}, o_opac = 0.f;
     float4 o_quat = make_float4(0.f, 0.f, 0.f, 0.f);
     if (live) {
         const CamParams &cam = s_cam;
         const float *R = cam.R;
-        const float4 cg = staged ? reinterpret_cast<const float4 *>(s_geo)[threadIdx.x] : geo[g];
-        const float2 gxy = staged ? *reinterpret_cast<const float2 *>(s_vm2d + threadIdx.x * v_m2d_stride)
+        const float4 cg = staged ? reinterpret_cast<const float4 *>(s_geo)[row] : geo[g];
+        const float2 gxy = staged ? *reinterpret_cast<const float2 *>(s_vm2d + row * v_m2d_stride)
                                   : *reinterpret_cast<const float2 *>(v_means2d + (size_t)g * v_m2d_stride);
-        const float4 gge = staged ? reinterpret_cast<const float4 *>(s_vgeo)[threadIdx.x] : v_geo[g];
+        const float4 gge = staged ? reinterpret_cast<const float4 *>(s_vgeo)[row] : v_geo[g];
         float ia = cg.x, ib = cg.y, ic = cg.z;
         // inverse VJP: v_cov2d = -Minv * G * Minv with G = [[ga, gb/2],[gb/2, gc]]
         float ga = gge.x, gb = 0.5f * gge.y, gc = gge.z;
@@ -449,7 +470,7 @@ k_project_bwd(const float *__restrict__ means, const float *__restrict__ quats, 
             o_opac = v_op_eff;
             if (!EXCH) v_opacities[g] = o_opac;
         }
-        float v_depth = with_depth ? (staged ? s_vcol[threadIdx.x * CDIM + d_in] : v_colpack[(size_t)g * CDIM + d_in]) : 0.f;
+        float v_depth = with_depth ? (staged ? s_vcol[row * CDIM + d_in] : v_colpack[(size_t)g * CDIM + d_in]) : 0.f;
 
         float p[3];
         if (staged) { p[0] = s_means[t3]; p[1] = s_means[t3 + 1]; p[2] = s_means[t3 + 2]; }
@@ -457,7 +478,7 @@ k_project_bwd(const float *__restrict__ means, const float *__restrict__ quats, 
         float pc[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) pc[i] = R[i * 3 + 0] * p[0] + R[i * 3 + 1] * p[1] + R[i * 3 + 2] * p[2] + cam.t[i];
-        const float4 q = staged ? reinterpret_cast<const float4 *>(s_quats)[threadIdx.x]
+        const float4 q = staged ? reinterpret_cast<const float4 *>(s_quats)[row]
                                 : reinterpret_cast<const float4 *>(quats)[g];
         float s[3];
         if (staged) { s[0] = s_scales[t3]; s[1] = s_scales[t3 + 1]; s[2] = s_scales[t3 + 2]; }
@@ -575,32 +596,45 @@ k_project_bwd(const float *__restrict__ means, const float *__restrict__ quats, 
                              (vqn[2] - dotp * qy) * inv_norm, (vqn[3] - dotp * qz) * inv_norm);
     }
     if (!EXCH) {
-        if (v_colors_out != nullptr && g < N) {  // contiguous [N, d_in] colour gradient (zeros for culled rows)
+        if (v_colors_out != nullptr && g_own < N) {  // contiguous [N, d_in] colour gradient (zeros for culled rows)
             for (int k = 0; k < d_in; ++k)
-                v_colors_out[(size_t)g * d_in + k] =
-                    live ? (staged ? s_vcol[threadIdx.x * CDIM + k] : v_colpack[(size_t)g * CDIM + k]) : 0.f;
+                v_colors_out[(size_t)g_own * d_in + k] =
+                    own_live ? (staged ? s_vcol[threadIdx.x * CDIM + k] : v_colpack[(size_t)g_own * CDIM + k]) : 0.f;
         }
-        if (live) {
-            v_quats[g] = o_quat;
-        } else if (g < N) {  // culled: define the row (zeros) so callers need no memset pass
-            v_means[3 * g] = v_means[3 * g + 1] = v_means[3 * g + 2] = 0.f;
-            v_scales[3 * g] = v_scales[3 * g + 1] = v_scales[3 * g + 2] = 0.f;
-            v_quats[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-            v_opacities[g] = 0.f;
+        if (live) v_quats[g] = o_quat;
+        if (!own_live && g_own < N) {  // culled: define the row (zeros) so callers need no memset pass
+            v_means[3 * g_own] = v_means[3 * g_own + 1] = v_means[3 * g_own + 2] = 0.f;
+            v_scales[3 * g_own] = v_scales[3 * g_own + 1] = v_scales[3 * g_own + 2] = 0.f;
+            v_quats[g_own] = make_float4(0.f, 0.f, 0.f, 0.f);
+            v_opacities[g_own] = 0.f;
         }
     } else {
         // ---- transpose the CTA's rows through shared memory, then 16-byte coalesced stores into the owner's slot
         float *s_ex = s_dyn;  // [768 means | 1024 quats | 768 scales | 256 opac | d_col * 256 colours]
-        __syncthreads();      // every thread has read its staged inputs: the buffer is reused for the output rows
         const int d_col = ex.d_col;
         const int t = threadIdx.x;
-        s_ex[3 * t] = o_means[0]; s_ex[3 * t + 1] = o_means[1]; s_ex[3 * t + 2] = o_means[2];
-        reinterpret_cast<float4 *>(s_ex + 768)[t] = o_quat;
-        s_ex[1792 + 3 * t] = o_scales[0]; s_ex[1792 + 3 * t + 1] = o_scales[1]; s_ex[1792 + 3 * t + 2] = o_scales[2];
-        s_ex[2560 + t] = o_opac;
-        for (int k = 0; k < d_col; ++k) s_ex[2816 + d_col * t + k] = live ? v_colpack[(size_t)g * CDIM + k] : 0.f;
+        float o_col[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            o_col[k] = (live && k < d_col) ? (staged ? s_vcol[row * CDIM + k] : v_colpack[(size_t)g * CDIM + k]) : 0.f;
+        __syncthreads();      // every thread has read its staged inputs: the buffer is reused for the output rows
+        if (live) {  // the row this thread worked on
+            s_ex[3 * row] = o_means[0]; s_ex[3 * row + 1] = o_means[1]; s_ex[3 * row + 2] = o_means[2];
+            reinterpret_cast<float4 *>(s_ex + 768)[row] = o_quat;
+            s_ex[1792 + 3 * row] = o_scales[0]; s_ex[1792 + 3 * row + 1] = o_scales[1]; s_ex[1792 + 3 * row + 2] = o_scales[2];
+            s_ex[2560 + row] = o_opac;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k < d_col) s_ex[2816 + d_col * row + k] = o_col[k];
+        }
+        if (!own_live) {  // this thread's own row is culled (or beyond N): zeros
+            s_ex[3 * t] = 0.f; s_ex[3 * t + 1] = 0.f; s_ex[3 * t + 2] = 0.f;
+            reinterpret_cast<float4 *>(s_ex + 768)[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+            s_ex[1792 + 3 * t] = 0.f; s_ex[1792 + 3 * t + 1] = 0.f; s_ex[1792 + 3 * t + 2] = 0.f;
+            s_ex[2560 + t] = 0.f;
+            for (int k = 0; k < d_col; ++k) s_ex[2816 + d_col * t + k] = 0.f;
+        }
         __syncthreads();
-        const int g0 = blockIdx.x * 256;
         const int owner = g0 / ex.shard, l0 = g0 - owner * ex.shard;
         const int rows = min(256, N - g0);
         float *slot = ex.stage[owner] + (size_t)ex.rank * ex.slot_floats;
