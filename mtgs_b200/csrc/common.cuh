@@ -134,6 +134,7 @@ struct B2sExchange {
     int shard;              // Gaussians (rows) owned per rank; multiple of 256
     int d_col;              // colour floats per row that take part in the exchange (d_in, or 0: colours stay local)
     long long slot_floats;  // floats per (owner, source) staging slot = (11 + d_col) * shard
+    int cta_rot;            // first 256-row block the fused projection backward works on (see k_project_bwd)
     unsigned epoch;         // step counter written into the flags (host-counted mode)
     unsigned *epoch_dev;    // device-counted mode (or null): this rank's own step counter, incremented by the first
                             // signal kernel of a step -- nothing of the launch depends on a host-side value, so the

@@ -92,11 +92,16 @@ k_grad_reduce_bcast(const B2sExchange ex, int n_shared, long long rows_cap, floa
             else if (e >= b3) { a_p = 10; wp = 1; b0 = b3; }
             else if (e >= b2) { a_p = 7; wp = 3; b0 = b2; }
             else if (e >= b1) { a_p = 3; wp = 4; b0 = b1; }
+            // all the sources' loads in flight before the first add (same summation order as a plain loop)
+            float4 v[B2S_MAX_WORLD];
+#pragma unroll
+            for (int src = 0; src < B2S_MAX_WORLD; ++src)
+                v[src] = src < ex.world ? __ldcs(reinterpret_cast<const float4 *>(mine + (size_t)src * ex.slot_floats + e))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
             float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int src = 0; src < ex.world; ++src) {
-                const float4 v = *reinterpret_cast<const float4 *>(mine + (size_t)src * ex.slot_floats + e);
-                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-            }
+#pragma unroll
+            for (int src = 0; src < B2S_MAX_WORLD; ++src)
+                if (src < ex.world) { s.x += v[src].x; s.y += v[src].y; s.z += v[src].z; s.w += v[src].w; }
             s.x *= scale; s.y *= scale; s.z *= scale; s.w *= scale;
             const long long gi = (long long)wp * ex.rank * ex.shard + (e - b0);  // float index inside arena block p
             const long long limit = (long long)wp * n_shared;
@@ -211,6 +216,7 @@ extern "C" int b2s_project_bwd_exchange(
     ex.shard = b2s_exchange_shard_rows(n_shared, world);
     ex.d_col = exchange_colors ? d_in : 0;
     ex.slot_floats = (long long)(11 + ex.d_col) * ex.shard;
+    ex.cta_rot = ((rank + 1) % world) * (ex.shard / 256);
     ex.epoch = epoch;
     // epoch == 0: device-counted steps; the counter is word 32 of this rank's own flag buffer (peers never touch it)
     ex.epoch_dev = epoch == 0 ? (unsigned *)(uintptr_t)flag_ptrs_host[rank] + 32 : nullptr;

@@ -389,7 +389,10 @@ k_project_bwd(const float *__restrict__ means, const float *__restrict__ quats, 
     // layout (floats): means 768 | quats 1024 | scales 768 | geo 1024 | v_geo 1024 | v_m2d 256 * stride | v_colpack 256 * CDIM
     float *s_means = s_dyn, *s_quats = s_dyn + 768, *s_scales = s_dyn + 1792, *s_geo = s_dyn + 2560, *s_vgeo = s_dyn + 3584,
           *s_vm2d = s_dyn + 4608, *s_vcol = s_dyn + 4608 + 256 * v_m2d_stride;
-    const int g0 = blockIdx.x * 256;
+    // EXCH: every rank walks the owners' shards starting behind its own (rank r begins with the rows rank r + 1 owns),
+    // so at any moment the ranks store into DIFFERENT peers instead of all into the same one (NVLink ingress of one GPU)
+    const int cta = EXCH ? (int)((blockIdx.x + (unsigned)ex.cta_rot) % gridDim.x) : (int)blockIdx.x;
+    const int g0 = cta * 256;
     const bool staged = use_tma && g0 + 256 <= N;  // CTA-uniform
     if (threadIdx.x == 0 && staged) {
         b2s_mbar_init(&s_bar, 1);
