@@ -30,6 +30,29 @@
 //     2 + CDIM/4 L2 atomic operations per (tile, Gaussian) instead of upstream's (9 + CDIM) per (warp, Gaussian).
 #include "common.cuh"
 
+// compile-time tunables (tools/ab_lib.py measures variants; the defaults are the measured best)
+#ifndef B2S_FWD_MINB
+#define B2S_FWD_MINB 1
+#endif
+#ifndef B2S_FWD_UNROLL
+#define B2S_FWD_UNROLL 2
+#endif
+#ifndef B2S_FWD_WARP_EXIT
+#define B2S_FWD_WARP_EXIT 1
+#endif
+#ifndef B2S_FWD_EXIT_CHUNK
+#define B2S_FWD_EXIT_CHUNK 16
+#endif
+#ifndef B2S_BWD_WARP_SKIP
+#define B2S_BWD_WARP_SKIP 1
+#endif
+#ifndef B2S_BWD_FL
+#define B2S_BWD_FL 64
+#endif
+#ifndef B2S_BWD_MINB4
+#define B2S_BWD_MINB4 10
+#endif
+constexpr int BL_FWD_UNROLL = B2S_FWD_UNROLL;
 constexpr int BL_THREADS = 128;
 constexpr int BL_BATCH = 128;  // list entries per walk-record block
 #ifndef B2S_BWD_PX
@@ -97,7 +120,7 @@ __device__ __forceinline__ void fwd_gather(FwdRec &r, int idx, int end, const in
 }
 
 template <int CDIM, int DOUT, bool ED>
-__global__ void __launch_bounds__(BL_THREADS)
+__global__ void __launch_bounds__(BL_THREADS, B2S_FWD_MINB)
 k_blend_fwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, const float4 *__restrict__ colpack,
             const int32_t *__restrict__ list_off /* [lists + 1] */, const int2 *__restrict__ items, int ncg, int cg_shift,
             int W, int H, int tile_w, float *__restrict__ render, float *__restrict__ alpha_out,
@@ -169,8 +192,19 @@ k_blend_fwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
         // Branch-free inner loop.  A pixel that has terminated (T' <= 1e-4 at some entry) carries T = 0 from then on:
         // every later entry gives T' = 0, is "not applied" and adds exact zeros, so no per-pixel done flag is tested
         // here; Tout keeps the transmittance behind the last applied entry (what alpha is computed from).
-#pragma unroll 2
+#if B2S_FWD_WARP_EXIT
+        // a warp whose 64 pixels have all terminated leaves the block early (checked every 32 entries); the entries it
+        // skips would have added exact zeros
+        for (int tb = 0; tb < cnt; tb += B2S_FWD_EXIT_CHUNK) {
+        if (__all_sync(0xffffffffu, T.x == 0.f && T.y == 0.f)) break;
+        const int te = min(cnt, tb + B2S_FWD_EXIT_CHUNK);
+#pragma unroll BL_FWD_UNROLL
+        for (int t = tb; t < te; ++t) {
+#else
+        {
+#pragma unroll BL_FWD_UNROLL
         for (int t = 0; t < cnt; ++t) {
+#endif
             const float4 sq = s_q[t];
             const float4 sc = s_c[t];
             const float dx = sq.x - px;
@@ -200,6 +234,7 @@ k_blend_fwd(const float2 *__restrict__ means2d, const float4 *__restrict__ geo, 
                 acc[4 * j + 2] = fma2(bc2(v.z), vis, acc[4 * j + 2]);
                 acc[4 * j + 3] = fma2(bc2(v.w), vis, acc[4 * j + 3]);
             }
+        }
         }
         nblend += cnt;
     };
@@ -395,7 +430,7 @@ __device__ __forceinline__ void load_pixel_cotangent(size_t pid, const float *__
 // PX pixels per thread (same column, PX adjacent rows) = PX / 2 packed pixel pairs; 256 / PX threads per tile.
 // PX = 8: ONE warp per tile -- one butterfly and no cross-warp sum per (tile, Gaussian); PX = 4: two warps.
 template <int CDIM, int DOUT, bool ED, int PX>
-__global__ void __launch_bounds__(256 / PX, PX == 8 ? (CDIM == 4 ? 14 : 10) : (CDIM == 4 ? 10 : 7))
+__global__ void __launch_bounds__(256 / PX, PX == 8 ? (CDIM == 4 ? 14 : 10) : (CDIM == 4 ? B2S_BWD_MINB4 : 7))
 k_blend_bwd(const int32_t *__restrict__ skip /* or null: non-zero = the forward of this frame was abandoned */,
             const int2 *__restrict__ tile_blocks /* [tiles]: (last record block, blocks written) */,
             const float4 *__restrict__ records, int W, int H, int tile_w, const float *__restrict__ render, const float *__restrict__ alpha_in,
@@ -409,7 +444,7 @@ k_blend_bwd(const int32_t *__restrict__ skip /* or null: non-zero = the forward 
     constexpr int NQUAD = 2 + CQ;  // float4 groups flushed per Gaussian
     using BL = BlkLayout<CDIM>;
     __shared__ __align__(128) float4 s_blk[2][BL::F4];       // two walk-record blocks in flight
-    constexpr int FL = 64;         // list entries per flush round (half a block: keeps s_acc small, 10+ CTAs per SM)
+    constexpr int FL = B2S_BWD_FL; // list entries per flush round (half a block: keeps s_acc small, 10+ CTAs per SM)
     __shared__ __align__(16) float s_acc[WARPS][FL][NV];
     __shared__ __align__(8) unsigned long long s_bar[2];
     __shared__ int s_max[WARPS];
@@ -454,6 +489,7 @@ k_blend_bwd(const int32_t *__restrict__ skip /* or null: non-zero = the forward 
     }
     // last list index any pixel of this tile blended
     maxbin = __reduce_max_sync(0xffffffffu, maxbin);
+    const int wmax = maxbin;  // ... and any pixel of this warp
     if (lane == 0) s_max[warp] = maxbin;
     if (threadIdx.x == 0) {
         b2s_mbar_init(&s_bar[0], 1);
@@ -496,9 +532,15 @@ k_blend_bwd(const int32_t *__restrict__ skip /* or null: non-zero = the forward 
         const int t0 = t1 & ~(FL - 1);
         if (t1 != tmax) __syncthreads();  // the previous round's flush has read s_acc
         for (int t = t1; t >= t0; --t) {
+            const int id = base + t;
+#if B2S_BWD_WARP_SKIP
+            if (id > wmax) {  // behind the last contribution of every pixel of this warp (warp-uniform)
+                if (lane < NV) s_acc[warp][t - t0][lane] = 0.f;
+                continue;
+            }
+#endif
             const float4 sq = s_q[t];
             const float4 sc = s_c[t];
-            const int id = base + t;
             const float dx = sq.x - px;
             float2 dy[NP], al[NP], g[NP];
             bool any_ok = false;
