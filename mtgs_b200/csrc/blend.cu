@@ -46,6 +46,9 @@
 #ifndef B2S_BWD_WARP_SKIP
 #define B2S_BWD_WARP_SKIP 1
 #endif
+#ifndef B2S_BWD_PAIR_SKIP
+#define B2S_BWD_PAIR_SKIP 0
+#endif
 #ifndef B2S_BWD_FL
 #define B2S_BWD_FL 64
 #endif
@@ -454,7 +457,15 @@ k_blend_bwd(const int32_t *__restrict__ skip /* or null: non-zero = the forward 
     const int ti = tile / tile_w, tj = tile - ti * tile_w;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int x = tj * 16 + (lane & 15);
+#if B2S_BWD_PAIR_SKIP
+    // pixel pair q of a lane = rows 4q + 2 (lane >> 4) + {0, 1} of the warp's strip: the warp's pairs q form BANDS of 4
+    // contiguous rows, so a small Gaussian misses whole bands and their gradient terms are skipped (warp-uniform)
+    const int ystrip = ti * 16 + 2 * PX * warp + 2 * (lane >> 4);
+#define B2S_ROW(j) (ystrip + 4 * ((j) >> 1) + ((j) & 1))
+#else
     const int ybase = ti * 16 + 2 * PX * warp + PX * (lane >> 4);
+#define B2S_ROW(j) (ybase + (j))
+#endif
     const float px = (float)x + 0.5f;
     const int2 tb = tile_blocks[tile];
 
@@ -469,14 +480,14 @@ k_blend_bwd(const int32_t *__restrict__ skip /* or null: non-zero = the forward 
 #pragma unroll
         for (int k = 0; k < CDIM; ++k) vrcj[k] = 0.f;
         bin[j] = -1;
-        if (x < W && ybase + j < H) {
-            const size_t pid = (size_t)(ybase + j) * W + x;
+        if (x < W && B2S_ROW(j) < H) {
+            const size_t pid = (size_t)B2S_ROW(j) * W + x;
             load_pixel_cotangent<CDIM, DOUT, ED>(pid, render, alpha_in, v_render, v_alpha, vrcj, vraj, Tfj);
             Tj = Tfj;
             bin[j] = last_ids[pid];
         }
         maxbin = max(maxbin, bin[j]);
-        const float npyj = -((float)(ybase + j) + 0.5f);
+        const float npyj = -((float)B2S_ROW(j) + 0.5f);
         if (j & 1) {
             T[j / 2].y = Tj; Tfvra[j / 2].y = Tfj * vraj; npy[j / 2].y = npyj; Bv[j / 2].y = 0.f;
 #pragma unroll
@@ -543,6 +554,7 @@ k_blend_bwd(const int32_t *__restrict__ skip /* or null: non-zero = the forward 
             const float4 sc = s_c[t];
             const float dx = sq.x - px;
             float2 dy[NP], al[NP], g[NP];
+            bool okq[NP];
             bool any_ok = false;
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
@@ -555,7 +567,8 @@ k_blend_bwd(const int32_t *__restrict__ skip /* or null: non-zero = the forward 
                 const bool ok1 = id <= bin[2 * q + 1] && p.y >= 0.f && a1 >= B2S_ALPHA_MIN;
                 al[q] = make_float2(ok0 ? a0 : 0.f, ok1 ? a1 : 0.f);
                 g[q] = make_float2((ok0 && ov.x <= B2S_ALPHA_MAX) ? ev.x : 0.f, (ok1 && ov.y <= B2S_ALPHA_MAX) ? ev.y : 0.f);
-                any_ok = any_ok || ok0 || ok1;
+                okq[q] = ok0 || ok1;
+                any_ok = any_ok || okq[q];
             }
             if (!__any_sync(0xffffffffu, any_ok)) {
                 if (lane < NV) s_acc[warp][t - t0][lane] = 0.f;
@@ -573,8 +586,12 @@ k_blend_bwd(const int32_t *__restrict__ skip /* or null: non-zero = the forward 
             // raw conic (a, b, c) from the log2-domain coefficients: a = 2 A ln2, b = B ln2, c = 2 C ln2
             const float ca = 2.f * B2S_LN2 * sq.z, cb = B2S_LN2 * sq.w, cc = 2.f * B2S_LN2 * sc.x;
 #pragma unroll
-            for (int q = 0; q < NP; ++q)
+            for (int q = 0; q < NP; ++q) {
+#if B2S_BWD_PAIR_SKIP
+                if (!__any_sync(0xffffffffu, okq[q])) continue;  // no pixel of this band is touched: exact zeros
+#endif
                 pair_grad<CDIM>(v2, T[q], Bv[q], vrc[q], Tfvra[q], col, ca, cb, cc, sc.y, dx, dy[q], al[q], g[q]);
+            }
             float v[16];
 #pragma unroll
             for (int k2 = 0; k2 < 16; ++k2) v[k2] = k2 < NV ? v2[k2].x + v2[k2].y : 0.f;
