@@ -37,6 +37,28 @@ def test_reference_golden_quat_and_sh0(oracle):
     assert list(g["num_sh_bases"]) == [(d + 1) ** 2 for d in range(5)]
 
 
+def test_reference_golden_projection_convention(oracle):
+    """The projected means and depths of the oracle follow the reference's own world -> pixel mapping
+    (mtgs/utils/camera_utils.py:151-174 `project_pix`, run by tests/golden/make_projection_golden.py): OpenCV pose,
+    u = fx x / z + cx with no half-pixel offset.  Every point the oracle keeps must match; every point in front of the
+    camera whose pixel lies well inside the image must be kept."""
+    g = np.load(os.path.join(GOLD, "projection_reference_golden.npz"))
+    n = g["points"].shape[0]
+    viewmat = np.linalg.inv(g["c2w"]).astype(np.float32)
+    K = np.array([[g["fx"], 0, g["cx"]], [0, g["fy"], g["cy"]], [0, 0, 1]], np.float32)
+    W, H = int(g["width"]), int(g["height"])
+    quats = np.tile(np.array([[1.0, 0, 0, 0]], np.float32), (n, 1))
+    scales = np.full((n, 3), 0.05, np.float32)
+    out = oracle.project_fwd(g["points"], quats, scales, viewmat, K, W, H)
+    radii, means2d, depths = out["radii"], out["means2d"], out["depths"]
+    vis = radii > 0
+    uvz = g["uvz"]
+    inside = (uvz[:, 0] > 2) & (uvz[:, 0] < W - 2) & (uvz[:, 1] > 2) & (uvz[:, 1] < H - 2) & (uvz[:, 2] > 0.01)
+    assert vis[inside].all() and inside.sum() > 50
+    np.testing.assert_allclose(means2d[vis], uvz[vis, :2], rtol=2e-5, atol=2e-3)
+    np.testing.assert_allclose(depths[vis], uvz[vis, 2], rtol=2e-5, atol=1e-4)
+
+
 @pytest.mark.parametrize("mode,rmode", [("classic", "RGB"), ("antialiased", "RGB+ED")])
 def test_analytic_backward_matches_float64_autograd(oracle, mode, rmode):
     s = scenes.tiny(n=300)
