@@ -59,6 +59,48 @@ def test_reference_golden_projection_convention(oracle):
     np.testing.assert_allclose(depths[vis], uvz[vis, 2], rtol=2e-5, atol=1e-4)
 
 
+def test_rendering_is_invariant_under_a_rigid_motion_of_world_and_camera(oracle):
+    """Moving the Gaussians and the camera together (means -> R means + t, quats -> q_R (x) quats, viewmat ->
+    viewmat [R t]^-1) must not change the image: a property of any correct projection + EWA + blend, independent of
+    the implementation's arithmetic (so it checks the oracle's chain as a whole, not its op order)."""
+    s = scenes.tiny(n=400)
+    rc, ra, _, _ = _run(oracle, s, render_mode="RGB+ED", rasterize_mode="antialiased")
+    rng = np.random.default_rng(11)
+    q = rng.standard_normal(4)
+    q /= np.linalg.norm(q)
+    Rm = oracle.quat_to_rotmat(q[None].astype(np.float32))[0].astype(np.float64)
+    t = rng.uniform(-3, 3, 3)
+    T = np.eye(4)
+    T[:3, :3], T[:3, 3] = Rm, t
+    moved = dict(s)
+    moved["means"] = (s["means"].astype(np.float64) @ Rm.T + t).astype(np.float32)
+    w1, x1, y1, z1 = q
+    w2, x2, y2, z2 = (s["quats"].astype(np.float64).T)
+    moved["quats"] = np.stack([w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2, w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2,
+                               w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2, w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2], 1).astype(np.float32)
+    moved["viewmat"] = (s["viewmat"].astype(np.float64) @ np.linalg.inv(T)).astype(np.float32)
+    rc2, ra2, _, _ = _run(oracle, moved, render_mode="RGB+ED", rasterize_mode="antialiased")
+    # fp32 inputs were rounded after the motion: compare images with a loose tolerance and a bound on threshold flips
+    bad = np.abs(ra2 - ra) > 2e-3
+    assert bad.mean() < 2e-3, bad.mean()
+    badc = np.abs(rc2[..., :3] - rc[..., :3]) > 2e-3
+    assert badc.mean() < 2e-3, badc.mean()
+
+
+def test_blend_is_linear_in_the_colours(oracle):
+    """render(a c1 + b c2) == a render(c1) + b render(c2) for fixed geometry (alpha does not depend on colour)."""
+    s = scenes.tiny(n=300)
+    rng = np.random.default_rng(12)
+    c1, c2 = s["colors"], rng.uniform(0, 1, s["colors"].shape).astype(np.float32)
+    out = []
+    for c in (c1, c2, (0.25 * c1 + 1.5 * c2).astype(np.float32)):
+        t = dict(s)
+        t["colors"] = c
+        out.append(_run(oracle, t, render_mode="RGB", rasterize_mode="classic"))
+    np.testing.assert_array_equal(out[0][1], out[2][1])  # alpha: bit-identical
+    np.testing.assert_allclose(out[2][0], 0.25 * out[0][0] + 1.5 * out[1][0], rtol=1e-5, atol=2e-6)
+
+
 @pytest.mark.parametrize("mode,rmode", [("classic", "RGB"), ("antialiased", "RGB+ED")])
 def test_analytic_backward_matches_float64_autograd(oracle, mode, rmode):
     s = scenes.tiny(n=300)
