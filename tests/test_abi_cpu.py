@@ -33,6 +33,42 @@ def test_library_exports_every_declared_symbol():
     assert isinstance(_lib.launch_count(), int)
 
 
+def test_ctypes_tables_mirror_the_header_argument_by_argument():
+    """Every prototype of include/b200splat.h has as many parameters as its ctypes argtypes entry in mtgs_b200/_lib.py
+    (a missing or extra argument would shift every later pointer without any error from ctypes)."""
+    from mtgs_b200 import _lib
+    txt = open(os.path.join(ROOT, "include", "b200splat.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    txt = re.sub(r"//[^\n]*", "", txt)
+    protos = dict(re.findall(r"\b(b2s_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S))
+    assert set(protos) == set(_lib.SIGNATURES)
+    def kind_h(a):
+        a = " ".join(a.split())
+        if "*" in a or "[" in a or "b2s_stream_t" in a:
+            return "ptr"
+        if a.startswith("float") or a.startswith("const float"):
+            return "f32"
+        if "long long" in a or "int64_t" in a or "size_t" in a:
+            return "i64"
+        if "uint32_t" in a or "unsigned" in a:
+            return "u32"
+        return "i32" if "int" in a else "?" + a
+
+    def kind_c(t):
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or (isinstance(t, type) and issubclass(t, ctypes._Pointer)):
+            return "ptr"
+        return {ctypes.c_float: "f32", ctypes.c_longlong: "i64", ctypes.c_size_t: "i64", ctypes.c_ulonglong: "i64",
+                ctypes.c_uint32: "u32", ctypes.c_int: "i32"}.get(t, "?" + str(t))
+
+    for name, args in protos.items():
+        args = " ".join(args.split())
+        alist = [] if args in ("", "void") else args.split(",")
+        table = _lib.SIGNATURES[name][1]
+        assert len(alist) == len(table), (name, len(alist), len(table))
+        for i, (a, t) in enumerate(zip(alist, table)):  # ... and the same kind of argument in every position
+            assert kind_h(a) == kind_c(t), (name, i, a.strip(), t)
+
+
 def test_header_cites_reference_call_sites():
     txt = open(os.path.join(ROOT, "include", "b200splat.h")).read()
     assert "mtgs_scene_graph.py:21, 641-662" in txt and "vanilla_gaussian_splatting.py:16, 317" in txt
